@@ -1,0 +1,406 @@
+"""Host-side mirror of the pyredner interface for the one hot path (RenderFunction.forward / backward).
+
+Same names, argument meaning and error behaviour as the reference's Python layer, written from scratch:
+  Camera      pyredner/camera.py:61-122          Shape      pyredner/shape.py:327-402
+  Texture     pyredner/texture.py:10-100         Material   pyredner/material.py:36-100
+  AreaLight   pyredner/area_light.py             Scene      pyredner/scene.py:5-68
+  RenderFunction.serialize_scene / forward / backward   pyredner/render_pytorch.py:68-269 / :652-707 / :1051-1177
+
+`RenderFunction` drives any module that exposes the `redner` pybind surface (src/redner.cpp:20-272).  The product uses
+`redner_b200.redner` (ctypes -> libredner_b200.so -> sm_100a kernels).  The tests additionally pass the compiled,
+unmodified reference module (oracle/_ref) through the very same host code to obtain the oracle's images and gradients.
+"""
+import math
+from typing import List, Optional, Tuple, Union
+
+import torch
+
+_backend = None
+_device = None
+_use_correlated_random_number = False
+
+
+def default_backend():
+    global _backend
+    if _backend is None:
+        from . import redner as rb  # raises if libredner_b200.so is not built
+        _backend = rb
+    return _backend
+
+
+def set_device(device):
+    """pyredner.set_device (pyredner/device.py:26-33)."""
+    global _device
+    _device = torch.device(device)
+
+
+def get_device():
+    if _device is not None:
+        return _device
+    if torch.cuda.is_available():
+        return torch.device("cuda:%d" % torch.cuda.current_device())
+    raise RuntimeError("redner_b200: no CUDA device is visible and there is no CPU fallback for rendering")
+
+
+def set_use_correlated_random_number(v: bool):
+    global _use_correlated_random_number
+    _use_correlated_random_number = bool(v)
+
+
+class Camera:
+    def __init__(self, position=None, look_at=None, up=None, fov=None, clip_near: float = 1e-4, resolution: Tuple[int, int] = (256, 256),
+                 viewport=None, cam_to_world=None, intrinsic_mat=None, distortion_params=None, camera_type=0):
+        if position is None and look_at is None and up is None:
+            assert cam_to_world is not None
+        for t, n in ((position, 3), (look_at, 3), (up, 3), (fov, 1)):
+            if t is not None:
+                assert t.dtype == torch.float32 and tuple(t.shape) == (n,)
+        assert isinstance(clip_near, float)
+        self.position, self.look_at, self.up = position, look_at, up
+        self.fov = fov
+        self.cam_to_world = cam_to_world
+        self.world_to_cam = torch.inverse(cam_to_world).contiguous() if cam_to_world is not None else None
+        if intrinsic_mat is None:
+            if int(camera_type) == 0:
+                f = 1.0 / torch.tan(0.5 * fov * (math.pi / 180.0))
+                one = torch.ones([1], dtype=torch.float32, device=f.device)
+                intrinsic_mat = torch.diag(torch.cat([f, f, one], 0)).contiguous()
+            else:
+                intrinsic_mat = torch.eye(3, dtype=torch.float32)
+        self.intrinsic_mat = intrinsic_mat
+        self.intrinsic_mat_inv = torch.inverse(intrinsic_mat).contiguous()
+        self.distortion_params = distortion_params
+        self.clip_near = clip_near
+        self.resolution = resolution  # (height, width)
+        self.viewport = viewport      # (y0, x0, y1, x1) or None
+        self.camera_type = camera_type
+
+
+class Texture:
+    """Texture + box-filtered mip pyramid (pyredner/texture.py:34-70)."""
+
+    def __init__(self, texels: torch.Tensor, uv_scale: Optional[torch.Tensor] = None):
+        if uv_scale is None:
+            uv_scale = torch.tensor([1.0, 1.0], device=texels.device)
+        assert texels.dtype == torch.float32 and uv_scale.dtype == torch.float32
+        self.uv_scale = uv_scale
+        self.texels = texels
+
+    @property
+    def texels(self):
+        return self._texels
+
+    @texels.setter
+    def texels(self, value):
+        self._texels = value
+        t = value
+        if t.dim() >= 2:
+            size = max(t.shape[0], t.shape[1])
+            levels = min(math.ceil(math.log(size, 2) + 1), 8)
+            ch = t.shape[2]
+            box = torch.ones(ch, 1, 2, 2, device=t.device) / 4.0
+            mip = [t.contiguous()]
+            prev = t.unsqueeze(0).permute(0, 3, 1, 2)
+            for _ in range(1, levels):
+                cur = torch.nn.functional.pad(prev, (0, 1, 0, 1), mode="circular")
+                cur = torch.nn.functional.conv2d(cur, box, groups=ch)
+                size_next = (max(cur.shape[2] // 2, 1), max(cur.shape[3] // 2, 1))
+                cur = torch.nn.functional.interpolate(cur, size=size_next, mode="area")
+                mip.append(cur.squeeze(0).permute(1, 2, 0).contiguous())
+                prev = cur
+        else:
+            mip = [t]
+        self.mipmap = mip
+
+
+def _as_texture(x, default=None):
+    if x is None:
+        return default
+    if isinstance(x, Texture):
+        return x
+    return Texture(x)
+
+
+class Material:
+    def __init__(self, diffuse_reflectance=None, specular_reflectance=None, roughness=None, generic_texture=None, normal_map=None,
+                 two_sided: bool = False, use_vertex_color: bool = False):
+        if diffuse_reflectance is None:
+            diffuse_reflectance = torch.zeros(3)
+        dev = diffuse_reflectance.texels.device if isinstance(diffuse_reflectance, Texture) else diffuse_reflectance.device
+        compute_specular = specular_reflectance is not None
+        if specular_reflectance is None:
+            specular_reflectance = torch.zeros(3, device=dev)
+        if roughness is None:
+            roughness = torch.ones(1, device=dev)
+        self.diffuse_reflectance = _as_texture(diffuse_reflectance)
+        self.specular_reflectance = _as_texture(specular_reflectance)
+        self.roughness = _as_texture(roughness)
+        self.generic_texture = _as_texture(generic_texture)
+        self.normal_map = _as_texture(normal_map)
+        self.compute_specular_lighting = compute_specular
+        self.two_sided = two_sided
+        self.use_vertex_color = use_vertex_color
+
+
+class Shape:
+    def __init__(self, vertices, indices, material_id: int, uvs=None, normals=None, uv_indices=None, normal_indices=None, colors=None):
+        assert vertices.dtype == torch.float32 and vertices.is_contiguous() and vertices.dim() == 2 and vertices.shape[1] == 3
+        assert indices.dtype == torch.int32 and indices.is_contiguous() and indices.dim() == 2 and indices.shape[1] == 3
+        for t, dt in ((uvs, torch.float32), (normals, torch.float32), (uv_indices, torch.int32), (normal_indices, torch.int32), (colors, torch.float32)):
+            if t is not None:
+                assert t.dtype == dt and t.is_contiguous()
+        self.vertices, self.indices, self.material_id = vertices, indices, material_id
+        self.uvs, self.normals, self.uv_indices, self.normal_indices, self.colors = uvs, normals, uv_indices, normal_indices, colors
+        self.light_id = -1
+
+
+class AreaLight:
+    def __init__(self, shape_id: int, intensity: torch.Tensor, two_sided: bool = False, directly_visible: bool = True):
+        assert intensity.dtype == torch.float32 and tuple(intensity.shape) == (3,)
+        self.shape_id, self.intensity, self.two_sided, self.directly_visible = shape_id, intensity, two_sided, directly_visible
+
+
+class Scene:
+    def __init__(self, camera: Camera, shapes: List[Shape], materials: List[Material], area_lights: List[AreaLight], envmap=None):
+        self.camera, self.shapes, self.materials, self.area_lights, self.envmap = camera, shapes, materials, area_lights, envmap
+
+
+class _Ctx:
+    pass
+
+
+def _ptr(backend, t, kind="float"):
+    ctor = backend.float_ptr if kind == "float" else backend.int_ptr
+    return ctor(t.data_ptr() if t is not None else 0)
+
+
+def _serialize_texture(tex, args, device):
+    if tex is None:
+        args.append(0)
+        return
+    args.append(len(tex.mipmap))
+    for m in tex.mipmap:
+        assert torch.isfinite(m).all()
+        assert m.is_contiguous()
+        args.append(m.to(device))
+    assert torch.isfinite(tex.uv_scale).all()
+    args.append(tex.uv_scale.to(device))
+
+
+class RenderFunction(torch.autograd.Function):
+    """torch.autograd.Function around `redner.render` (pyredner/render_pytorch.py:63-1177).
+
+    `RenderFunction.apply(seed, *args)` with `args = RenderFunction.serialize_scene(...)`.  The module implementing the
+    `redner` surface is the LAST serialized argument, so the same host code can drive the product and the oracle."""
+
+    @staticmethod
+    def serialize_scene(scene: Scene, num_samples: Union[int, Tuple[int, int]], max_bounces: int, channels=None, sampler_type=None,
+                        use_primary_edge_sampling: bool = True, use_secondary_edge_sampling: bool = True, sample_pixel_center: bool = False,
+                        device: Optional[torch.device] = None, backend=None):
+        backend = backend or default_backend()
+        if channels is None:
+            channels = [backend.channels.radiance]
+        if sampler_type is None:
+            sampler_type = backend.SamplerType.independent
+        if device is None:
+            device = get_device()
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda:%d" % torch.cuda.current_device())
+        cam = scene.camera
+        for light_id, light in enumerate(scene.area_lights):
+            scene.shapes[light.shape_id].light_id = light_id
+        if max_bounces == 0:
+            use_secondary_edge_sampling = False
+        vis = False  # does any parameter need discontinuity (edge) sampling? (render_pytorch.py:144-160)
+        for t in (cam.position, cam.look_at, cam.up, cam.cam_to_world, cam.world_to_cam, cam.intrinsic_mat, cam.intrinsic_mat_inv, cam.distortion_params):
+            if t is not None:
+                assert torch.isfinite(t).all()
+                vis = vis or t.requires_grad
+        args = [len(scene.shapes), len(scene.materials), len(scene.area_lights)]
+        args += [cam.position.cpu() if cam.position is not None else None, cam.look_at.cpu() if cam.look_at is not None else None,
+                 cam.up.cpu() if cam.up is not None else None]
+        args += [cam.cam_to_world.cpu().contiguous() if cam.cam_to_world is not None else None,
+                 cam.world_to_cam.cpu().contiguous() if cam.world_to_cam is not None else None]
+        args += [cam.intrinsic_mat_inv.cpu().contiguous(), cam.intrinsic_mat.cpu().contiguous()]
+        args.append(cam.distortion_params.cpu().contiguous() if cam.distortion_params is not None else None)
+        args += [cam.clip_near, cam.resolution]
+        vp = cam.viewport if cam.viewport is not None else (0, 0, cam.resolution[0], cam.resolution[1])
+        vp = (max(vp[0], 0), max(vp[1], 0), min(vp[2], cam.resolution[0]), min(vp[3], cam.resolution[1]))
+        args += [vp, cam.camera_type]
+        for s in scene.shapes:
+            assert torch.isfinite(s.vertices).all()
+            vis = vis or s.vertices.requires_grad
+            args += [s.vertices.to(device), s.indices.to(device)]
+            for t in (s.uvs, s.normals, s.uv_indices, s.normal_indices, s.colors):
+                if t is not None and t.is_floating_point():
+                    assert torch.isfinite(t).all()
+                args.append(t.to(device) if t is not None else None)
+            args += [s.material_id, s.light_id]
+        for m in scene.materials:
+            for tex in (m.diffuse_reflectance, m.specular_reflectance, m.roughness, m.generic_texture, m.normal_map):
+                _serialize_texture(tex, args, device)
+            args += [m.compute_specular_lighting, m.two_sided, m.use_vertex_color]
+        for light in scene.area_lights:
+            args += [light.shape_id, light.intensity.cpu(), light.two_sided, light.directly_visible]
+        if scene.envmap is not None:
+            raise NotImplementedError("environment maps: second wave (SURVEY.md section 2 row 13)")
+        args.append(None)
+        args += [num_samples, max_bounces, channels, sampler_type]
+        args += [use_primary_edge_sampling and vis, use_secondary_edge_sampling and vis]
+        args += [sample_pixel_center, device, backend]
+        return args
+
+    @staticmethod
+    def _unpack(seed, args):
+        it = iter(args)
+        nxt = lambda: next(it)  # noqa: E731
+        c = _Ctx()
+        num_shapes, num_materials, num_lights = nxt(), nxt(), nxt()
+        cam_pos, cam_look, cam_up, c2w, w2c, intr_inv, intr, dist = nxt(), nxt(), nxt(), nxt(), nxt(), nxt(), nxt(), nxt()
+        clip_near, resolution, viewport, camera_type = nxt(), nxt(), nxt(), nxt()
+        shape_args, mat_args, light_args = [], [], []
+        for _ in range(num_shapes):
+            shape_args.append([nxt() for _ in range(9)])
+        for _ in range(num_materials):
+            texs = []
+            for _ in range(5):
+                n = nxt()
+                if n == 0:
+                    texs.append(None)
+                else:
+                    mips = [nxt() for _ in range(n)]
+                    texs.append((mips, nxt()))
+            mat_args.append((texs, nxt(), nxt(), nxt()))
+        for _ in range(num_lights):
+            light_args.append([nxt() for _ in range(4)])
+        envmap = nxt()
+        assert envmap is None
+        num_samples, max_bounces, channels, sampler_type = nxt(), nxt(), nxt(), nxt()
+        use_prim, use_sec, pixel_center, device, backend = nxt(), nxt(), nxt(), nxt(), nxt()
+        rb = backend
+        fp, ip = (lambda t: _ptr(rb, t, "float")), (lambda t: _ptr(rb, t, "int"))
+        camera = rb.Camera(resolution[1], resolution[0], fp(cam_pos if c2w is None else None), fp(cam_look if c2w is None else None),
+                           fp(cam_up if c2w is None else None), fp(c2w), fp(w2c), fp(intr_inv), fp(intr), fp(dist), clip_near,
+                           rb.CameraType(int(camera_type)),
+                           rb.Vector2i(viewport[1], viewport[0]), rb.Vector2i(viewport[3], viewport[2]))
+        shapes = []
+        for v, i, uv, n, uvi, ni, col, mid, lid in shape_args:
+            assert v.is_contiguous() and i.is_contiguous()
+            shapes.append(rb.Shape(fp(v), ip(i), fp(uv), fp(n), ip(uvi), ip(ni), fp(col), int(v.shape[0]), int(uv.shape[0]) if uv is not None else 0,
+                                   int(n.shape[0]) if n is not None else 0, int(i.shape[0]), mid, lid))
+
+        def make_tex(cls, t, nch_default):
+            if t is None:
+                return cls([], [], [], nch_default, rb.float_ptr(0))
+            mips, uv_scale = t
+            if mips[0].dim() == 3:
+                return cls([fp(m) for m in mips], [int(m.shape[1]) for m in mips], [int(m.shape[0]) for m in mips], int(mips[0].shape[2]), fp(uv_scale))
+            return cls([fp(mips[0])], [0], [0], int(mips[0].shape[0]), fp(uv_scale))
+
+        materials = []
+        for texs, spec, two_sided, vcol in mat_args:
+            materials.append(rb.Material(make_tex(rb.Texture3, texs[0], 3), make_tex(rb.Texture3, texs[1], 3), make_tex(rb.Texture1, texs[2], 1),
+                                         make_tex(rb.TextureN, texs[3], 0), make_tex(rb.Texture3, texs[4], 3), spec, two_sided, vcol))
+        lights = [rb.AreaLight(sid, fp(inten), ts, dv) for sid, inten, ts, dv in light_args]
+        use_gpu = device.type == "cuda"
+        gpu_index = device.index if device.index is not None else -1
+        c.scene = rb.Scene(camera, shapes, materials, lights, None, use_gpu, gpu_index, use_prim, use_sec)
+        ns = num_samples if isinstance(num_samples, (tuple, list)) else (num_samples, num_samples)
+        channels = [rb.channels(int(ch)) for ch in channels]
+        c.options = rb.RenderOptions(seed[0], ns[0], max_bounces, channels, rb.SamplerType(int(sampler_type)), pixel_center)
+        c.camera, c.shapes, c.materials, c.lights = camera, shapes, materials, lights
+        c.shape_args, c.mat_args, c.light_args = shape_args, mat_args, light_args
+        c.num_samples, c.channels, c.viewport, c.device, c.backend, c.seed = ns, channels, viewport, device, rb, seed
+        c.use_look_at = c2w is None
+        return c
+
+    @staticmethod
+    def forward(ctx, seed, *args):
+        assert isinstance(seed, (tuple, int))
+        if not isinstance(seed, tuple):
+            seed = (seed, seed if _use_correlated_random_number else seed + 1000003)
+        c = RenderFunction._unpack(seed, args)
+        rb = c.backend
+        nch = rb.compute_num_channels(c.channels, c.scene.max_generic_texture_dimension)
+        h, w = c.viewport[2] - c.viewport[0], c.viewport[3] - c.viewport[1]
+        img = torch.zeros(h, w, nch, device=c.device)
+        rb.render(c.scene, c.options, rb.float_ptr(img.data_ptr()), rb.float_ptr(0), None, rb.float_ptr(0), rb.float_ptr(0))
+        ctx.c = c
+        ctx.args = args  # keeps the tensors alive (the native side only holds raw pointers)
+        return img
+
+    @staticmethod
+    def backward(ctx, grad_img):
+        c = ctx.c
+        rb, dev = c.backend, c.device
+        if not grad_img.is_contiguous():
+            grad_img = grad_img.contiguous()
+        assert torch.isfinite(grad_img).all()
+        z = lambda *shape: torch.zeros(*shape, device=dev)  # noqa: E731
+        fp = lambda t: _ptr(rb, t, "float")  # noqa: E731
+        if c.use_look_at:
+            d_pos, d_look, d_up, d_c2w, d_w2c = z(3), z(3), z(3), None, None
+        else:
+            d_pos, d_look, d_up, d_c2w, d_w2c = None, None, None, z(4, 4), z(4, 4)
+        d_intr_inv, d_intr = z(3, 3), z(3, 3)
+        d_camera = rb.DCamera(fp(d_pos), fp(d_look), fp(d_up), fp(d_c2w), fp(d_w2c), fp(d_intr_inv), fp(d_intr), rb.float_ptr(0))
+        d_shape_bufs, d_shapes = [], []
+        for v, i, uv, n, uvi, ni, col, mid, lid in c.shape_args:
+            bufs = (z(*v.shape), z(*uv.shape) if uv is not None else None, z(*n.shape) if n is not None else None, z(*col.shape) if col is not None else None)
+            d_shape_bufs.append(bufs)
+            d_shapes.append(rb.DShape(fp(bufs[0]), fp(bufs[1]), fp(bufs[2]), fp(bufs[3])))
+
+        def make_dtex(cls, t, nch_default):
+            if t is None:
+                return None, cls([], [], [], nch_default, rb.float_ptr(0))
+            mips, uv_scale = t
+            d_mips = [torch.zeros_like(m) for m in mips]
+            d_uv = torch.zeros(2, device=dev)
+            if mips[0].dim() == 3:
+                tex = cls([fp(m) for m in d_mips], [int(m.shape[1]) for m in mips], [int(m.shape[0]) for m in mips], int(mips[0].shape[2]), fp(d_uv))
+            else:
+                tex = cls([fp(d_mips[0])], [0], [0], int(mips[0].shape[0]), fp(d_uv))
+            return (d_mips, d_uv), tex
+
+        d_mat_bufs, d_materials = [], []
+        for texs, spec, two_sided, vcol in c.mat_args:
+            classes = (rb.Texture3, rb.Texture3, rb.Texture1, rb.TextureN, rb.Texture3)
+            made = [make_dtex(cls, t, nd) for cls, t, nd in zip(classes, texs, (3, 3, 1, 0, 3))]
+            d_mat_bufs.append([m[0] for m in made])
+            d_materials.append(rb.DMaterial(*[m[1] for m in made]))
+        d_intensities = [z(3) for _ in c.light_args]
+        d_lights = [rb.DAreaLight(fp(t)) for t in d_intensities]
+        d_scene = rb.DScene(d_camera, d_shapes, d_materials, d_lights, None, dev.type == "cuda", dev.index if dev.index is not None else -1)
+        c.options.seed = c.seed[1]
+        c.options.num_samples = c.num_samples[1]
+        rb.render(c.scene, c.options, rb.float_ptr(0), fp(grad_img), d_scene, rb.float_ptr(0), rb.float_ptr(0))
+
+        out = [None]  # seed
+        out += [None, None, None]  # counts
+        cpu = lambda t: t.cpu() if t is not None else None  # noqa: E731
+        out += [cpu(d_pos), cpu(d_look), cpu(d_up), cpu(d_c2w), cpu(d_w2c), cpu(d_intr_inv), cpu(d_intr), None]
+        out += [None, None, None, None]  # clip_near, resolution, viewport, camera_type
+        for bufs in d_shape_bufs:
+            out += [bufs[0], None, bufs[1], bufs[2], None, None, bufs[3], None, None]
+        for mb, (texs, _, _, _) in zip(d_mat_bufs, c.mat_args):
+            for b, t in zip(mb, texs):
+                out.append(None)  # number of levels
+                if t is not None:
+                    out += list(b[0])
+                    out.append(b[1])
+            out += [None, None, None]
+        for d_i in d_intensities:
+            out += [None, d_i.cpu(), None, None]
+        out.append(None)  # envmap
+        out += [None] * 9  # num_samples .. backend
+        return tuple(out)
+
+
+def render_pathtracing(scene: Scene, num_samples=(4, 4), max_bounces: int = 1, seed: int = 0, sampler_type=None, device=None, backend=None,
+                       use_primary_edge_sampling=True, use_secondary_edge_sampling=True):
+    """pyredner.render_pathtracing (pyredner/render_utils.py:505-573) for a single scene."""
+    args = RenderFunction.serialize_scene(scene, num_samples, max_bounces, sampler_type=sampler_type, device=device, backend=backend,
+                                          use_primary_edge_sampling=use_primary_edge_sampling,
+                                          use_secondary_edge_sampling=use_secondary_edge_sampling)
+    return RenderFunction.apply(seed, *args)

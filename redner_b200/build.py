@@ -1,0 +1,79 @@
+"""In-tree build of libredner_b200.so (hand-written CUDA for sm_100a + the C ABI) with nvcc.
+
+    python -m redner_b200.build            # build if sources are newer than the library
+    python -m redner_b200.build --force
+
+The library is placed next to this file (redner_b200/libredner_b200.so) so that it travels with the repository
+snapshot to the GPU box.  No JIT cache, no torch extension machinery: the product is a plain C-ABI shared object.
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+DATA = os.path.join(HERE, "data")
+LIB = os.path.join(HERE, "libredner_b200.so")
+LIB_F64 = os.path.join(HERE, "libredner_b200_f64.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def _stale(lib):
+    if not os.path.exists(lib):
+        return True
+    t = os.path.getmtime(lib)
+    srcs = glob.glob(os.path.join(CSRC, "*")) + glob.glob(os.path.join(HERE, "..", "include", "*.h")) + [__file__]
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def build(force=False, double=False, verbose=False):
+    lib = LIB_F64 if double else LIB
+    if not force and not _stale(lib):
+        return lib
+    objdir = os.path.join(HERE, "_build_f64" if double else "_build")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    common = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math" if False else "-fmad=true", "-Xcompiler", "-fPIC", "-I", os.path.join(HERE, "..", "include")]
+    if double:
+        common += ["-DRB_REAL_DOUBLE"]
+    if verbose:
+        common += ["-Xptxas", "-v"]
+    objs = []
+    procs = []
+    for src in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        objs.append(obj)
+        procs.append((src, subprocess.Popen([nvcc] + ARCH + common + ["-c", src, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    tab = os.path.join(objdir, "rb_tables.o")
+    objs.append(tab)
+    procs.append(("rb_tables.cpp", subprocess.Popen(["g++", "-O2", "-fPIC", "-DRB_DATA_DIR=" + DATA, "-c", os.path.join(CSRC, "rb_tables.cpp"), "-o", tab],
+                                                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    failed = False
+    for src, p in procs:
+        out = p.communicate()[0].decode()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write("[redner_b200.build] FAILED %s\n%s\n" % (src, out))
+        elif verbose or out.strip():
+            sys.stderr.write("[redner_b200.build] %s\n%s\n" % (src, out))
+    if failed:
+        raise RuntimeError("redner_b200: nvcc compilation failed")
+    cmd = [nvcc] + ARCH + ["-shared", "-o", lib] + objs + ["-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout.decode())
+        raise RuntimeError("redner_b200: link failed")
+    return lib
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, double="--f64" in sys.argv, verbose="-v" in sys.argv)
+    print(path)

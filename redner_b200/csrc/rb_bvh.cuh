@@ -1,0 +1,130 @@
+// Triangle BVH traversal (own structure; replaces Embree rtcIntersect1/rtcOccluded1 and OptiX Prime queries,
+// reference call sites src/scene.cpp:503-597 (closest hit) and :629-690 (any hit)).
+//
+// Layout: binary LBVH, 64-byte nodes holding BOTH children's boxes (one 4x16 B fetch per step, served by L1/L2 --
+// every BASELINE scene's BVH is < 2 MB and L2-resident).  Leaves reference one pre-gathered triangle (48 B,
+// three float4 loads) stored in Morton order, so neighbouring rays touch neighbouring memory.
+// Each thread walks its own ray with a short stack in local memory; rays of a warp are coherent by construction
+// (lanes of a warp are samples of the same / adjacent pixels, see rb_render.cuh).
+//
+// The triangle test is a Pluecker edge-function test evaluated in fp32 with the same operation nesting as
+// Embree 3.6's robust-mode intersector (edge tests U, V, W with fused multiply-adds, inclusive zero), because
+// parity with the reference means agreeing with Embree's hit/miss decisions on silhouette pixels.
+#pragma once
+#include "rb_types.cuh"
+
+#define RB_BVH_STACK 64
+
+RB_D float rb_msub(float a, float b, float c) { return fmaf(a, b, -c); }
+struct F3 {
+    float x, y, z;
+};
+RB_D F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+RB_D F3 f3_sub(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RB_D F3 f3_add(F3 a, F3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RB_D F3 f3_cross(F3 a, F3 b) { return f3(rb_msub(a.y, b.z, a.z * b.y), rb_msub(a.z, b.x, a.x * b.z), rb_msub(a.x, b.y, a.y * b.x)); }
+RB_D float f3_dot(F3 a, F3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+
+// Returns true and the hit distance if the ray hits the triangle within (tnear, tfar].
+RB_D bool tri_test(F3 O, F3 D, float tnear, float tfar, const BVHTri& tri, float& t_out) {
+    F3 v0 = f3_sub(f3(tri.v0.x, tri.v0.y, tri.v0.z), O);
+    F3 v1 = f3_sub(f3(tri.v1.x, tri.v1.y, tri.v1.z), O);
+    F3 v2 = f3_sub(f3(tri.v2.x, tri.v2.y, tri.v2.z), O);
+    F3 e0 = f3_sub(v2, v0), e1 = f3_sub(v0, v1), e2 = f3_sub(v1, v2);
+    float U = f3_dot(f3_cross(f3_add(v2, v0), e0), D);
+    float V = f3_dot(f3_cross(f3_add(v0, v1), e1), D);
+    float W = f3_dot(f3_cross(f3_add(v1, v2), e2), D);
+    float mn = fminf(U, fminf(V, W)), mx = fmaxf(U, fmaxf(V, W));
+    if (!(mn >= 0.0f || mx <= 0.0f)) return false;
+    F3 Ng = f3_cross(e2, e1);
+    float den = 2.0f * f3_dot(Ng, D);
+    if (den == 0.0f) return false;
+    float T = 2.0f * f3_dot(v0, Ng);
+    float absDen = fabsf(den);
+    float Ts = den < 0.0f ? -T : T;
+    if (!(absDen * tnear < Ts && Ts <= absDen * tfar)) return false;
+    t_out = Ts / absDen;
+    return true;
+}
+
+struct BoxRay {
+    float ox, oy, oz;    // org * inv_dir (negated use)
+    float ix, iy, iz;    // 1 / dir
+};
+RB_D float safe_rcp(float d) { return 1.0f / (fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); }
+
+// slab test for one child box; returns entry distance or +inf when missed
+RB_D float box_test(const BoxRay& r, float lox, float hix, float loy, float hiy, float loz, float hiz, float tnear, float tfar) {
+    float tx0 = (lox - r.ox) * r.ix, tx1 = (hix - r.ox) * r.ix;
+    float ty0 = (loy - r.oy) * r.iy, ty1 = (hiy - r.oy) * r.iy;
+    float tz0 = (loz - r.oz) * r.iz, tz1 = (hiz - r.oz) * r.iz;
+    float t0 = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tnear));
+    float t1 = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tfar));
+    // boxes are padded at build time; the extra relative slack covers the rounding of the slab products
+    return (t0 <= t1 * 1.0000004f) ? t0 : INFINITY;
+}
+
+template <bool ANY_HIT>
+RB_D bool bvh_trace(const DevScene& sc, const Ray& ray, int& shape_id, int& tri_id, float& t_hit) {
+    shape_id = -1;
+    tri_id = -1;
+    float tnear = (float)ray.tmin, tfar = (float)ray.tmax;
+    F3 O = f3((float)ray.org.x, (float)ray.org.y, (float)ray.org.z);
+    F3 D = f3((float)ray.dir.x, (float)ray.dir.y, (float)ray.dir.z);
+    if (sc.num_tris <= 0) return false;
+    // zero / degenerate directions never hit (src/scene.cpp:577-578)
+    if (D.x * D.x + D.y * D.y + D.z * D.z <= 1e-3f) return false;
+    if (!(tfar >= tnear)) return false;
+    BoxRay br;
+    br.ix = safe_rcp(D.x); br.iy = safe_rcp(D.y); br.iz = safe_rcp(D.z);
+    br.ox = O.x; br.oy = O.y; br.oz = O.z;
+    int stack[RB_BVH_STACK];
+    int sp = 0;
+    int node = sc.bvh_root;
+    bool hit = false;
+    const float4* nodes4 = reinterpret_cast<const float4*>(sc.bvh_nodes);
+    const float4* tris4 = reinterpret_cast<const float4*>(sc.bvh_tris);
+    while (true) {
+        if (node >= 0) {
+            float4 bx = __ldg(nodes4 + 4 * (size_t)node + 0);
+            float4 by = __ldg(nodes4 + 4 * (size_t)node + 1);
+            float4 bz = __ldg(nodes4 + 4 * (size_t)node + 2);
+            float4 ch = __ldg(nodes4 + 4 * (size_t)node + 3);
+            int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
+            float tl = box_test(br, bx.x, bx.y, by.x, by.y, bz.x, bz.y, tnear, tfar);
+            float tr = box_test(br, bx.z, bx.w, by.z, by.w, bz.z, bz.w, tnear, tfar);
+            bool hl = tl < INFINITY, hr = tr < INFINITY;
+            if (hl && hr) {
+                int first = left, second = right;
+                if (tr < tl) { first = right; second = left; }
+                if (sp < RB_BVH_STACK) stack[sp++] = second;
+                node = first;
+                continue;
+            } else if (hl) {
+                node = left;
+                continue;
+            } else if (hr) {
+                node = right;
+                continue;
+            }
+        } else {
+            int slot = ~node;
+            BVHTri tri;
+            tri.v0 = __ldg(tris4 + 3 * (size_t)slot + 0);
+            tri.v1 = __ldg(tris4 + 3 * (size_t)slot + 1);
+            tri.v2 = __ldg(tris4 + 3 * (size_t)slot + 2);
+            float t;
+            if (tri_test(O, D, tnear, tfar, tri, t)) {
+                hit = true;
+                tfar = t;
+                shape_id = __float_as_int(tri.v0.w);
+                tri_id = __float_as_int(tri.v1.w);
+                if (ANY_HIT) break;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    t_hit = tfar;
+    return hit;
+}

@@ -1,0 +1,270 @@
+// Camera: primary ray generation (with finite-difference ray differentials), screen projection of
+// edges, and their adjoints.
+//   sample_primary            src/camera.h:121-197       primary_ray_sampler   src/camera.cpp:8-43
+//   d_sample_primary_ray      src/camera.h:199-500       camera_to_screen      src/camera.h:508-559
+//   project / d_project       src/camera.h:561-591, :731-830   in_screen       src/camera.h:1049-1067
+// The forward ray is evaluated in double from the float camera parameters exactly like the reference
+// (Real == double there) and rounded to fp32 once, so the rays entering the fp32 BVH traversal are the
+// same fp32 rays the reference hands to Embree (src/scene.cpp:556-567).
+// Supported: perspective and orthographic cameras without distortion (fisheye / panorama / Brown-Conrady
+// are rejected by rb_scene_create; SURVEY.md section 7 step 9 "second wave").
+#pragma once
+#include "rb_types.cuh"
+
+struct D3 {
+    double x, y, z;
+};
+RB_HD D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+RB_HD D3 d3_normalize(D3 v) {
+    double l = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+    if (l <= 0) return d3(0, 0, 0);
+    return d3(v.x / l, v.y / l, v.z / l);
+}
+
+RB_HD void cam_sample_primary(const DevCamera& cam, double sx, double sy, D3& org, D3& dir) {
+    const double* C = cam.c2w;
+    const double* I = cam.intr_inv;
+    double aspect = double(cam.width) / double(cam.height);
+    if (cam.type == RB_CAMERA_PERSPECTIVE) {
+        // org = xfm_point(c2w, 0)
+        double iw = 1.0 / C[15];
+        org = d3(C[3] * iw, C[7] * iw, C[11] * iw);
+        double px = (sx - 0.5) * 2.0, py = (sy - 0.5) * (-2.0) / aspect, pz = 1.0;
+        D3 d = d3(I[0] * px + I[1] * py + I[2] * pz, I[3] * px + I[4] * py + I[5] * pz, I[6] * px + I[7] * py + I[8] * pz);
+        D3 n = d3_normalize(d);
+        D3 w = d3(C[0] * n.x + C[1] * n.y + C[2] * n.z, C[4] * n.x + C[5] * n.y + C[6] * n.z, C[8] * n.x + C[9] * n.y + C[10] * n.z);
+        dir = d3_normalize(w);
+    } else { // orthographic
+        double px = (sx - 0.5) * 2.0, py = (sy - 0.5) * (-2.0) / aspect, pz = 0.0;
+        D3 l = d3(I[0] * px + I[1] * py + I[2] * pz, I[3] * px + I[4] * py + I[5] * pz, I[6] * px + I[7] * py + I[8] * pz);
+        double tx = C[0] * l.x + C[1] * l.y + C[2] * l.z + C[3];
+        double ty = C[4] * l.x + C[5] * l.y + C[6] * l.z + C[7];
+        double tz = C[8] * l.x + C[9] * l.y + C[10] * l.z + C[11];
+        double tw = C[12] * l.x + C[13] * l.y + C[14] * l.z + C[15];
+        double iw = 1.0 / tw;
+        org = d3(tx * iw, ty * iw, tz * iw);
+        dir = d3_normalize(d3(C[2], C[6], C[10]));
+    }
+}
+
+RB_HD Ray make_ray(D3 o, D3 d) {
+    Ray r;
+    r.org = mk3((Real)o.x, (Real)o.y, (Real)o.z);
+    r.dir = mk3((Real)d.x, (Real)d.y, (Real)d.z);
+    r.tmin = Real(1e-3);
+    r.tmax = INFINITY;
+    return r;
+}
+
+// Primary ray + ray differential at normalised screen position (sx, sy).
+RB_HD void cam_primary_ray(const DevCamera& cam, double sx, double sy, Ray& ray, RayDiff& rd) {
+    D3 o, d, ox, dx, oy, dy;
+    cam_sample_primary(cam, sx, sy, o, d);
+    const double delta = 1e-3;
+    cam_sample_primary(cam, sx + delta, sy, ox, dx);
+    cam_sample_primary(cam, sx, sy + delta, oy, dy);
+    double psx = 0.5 / cam.width, psy = 0.5 / cam.height;
+    ray = make_ray(o, d);
+    rd.org_dx = mk3((Real)(psx * (ox.x - o.x) / delta), (Real)(psx * (ox.y - o.y) / delta), (Real)(psx * (ox.z - o.z) / delta));
+    rd.org_dy = mk3((Real)(psy * (oy.x - o.x) / delta), (Real)(psy * (oy.y - o.y) / delta), (Real)(psy * (oy.z - o.z) / delta));
+    rd.dir_dx = mk3((Real)(psx * (dx.x - d.x) / delta), (Real)(psx * (dx.y - d.y) / delta), (Real)(psx * (dx.z - d.z) / delta));
+    rd.dir_dy = mk3((Real)(psy * (dy.x - d.x) / delta), (Real)(psy * (dy.y - d.y) / delta), (Real)(psy * (dy.z - d.z) / delta));
+}
+
+RB_HD M4 cam_m4(const double* a) {
+    M4 r;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) r.m[i][j] = (Real)a[4 * i + j];
+    return r;
+}
+RB_HD M3 cam_m3(const double* a) {
+    M3 r;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r.m[i][j] = (Real)a[3 * i + j];
+    return r;
+}
+
+// Per-thread camera-gradient accumulator.  The reference does one atomic per scalar per pixel into the same
+// <= 30 addresses (src/camera.h:244-259) -- its worst contention point.  Here every thread owns a strided
+// column in shared memory; the block reduces once at kernel end and issues one double atomic per scalar.
+// Layout (RB_CAM_ACC floats): [0..15] d_cam_to_world, [16..31] d_world_to_cam, [32..40] d_intr_inv, [41..49] d_intr.
+#define RB_CAM_ACC 50
+struct CamAcc {
+    float* base; // shared memory, element k of this thread at base[k * stride]
+    int stride;
+    RB_D void add(int k, Real v) { base[k * stride] += (float)v; }
+    RB_D void add_c2w(const M4& d) {
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++)
+                if (d.m[i][j] != 0) add(4 * i + j, d.m[i][j]);
+    }
+    RB_D void add_w2c(const M4& d) {
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++)
+                if (d.m[i][j] != 0) add(16 + 4 * i + j, d.m[i][j]);
+    }
+    RB_D void add_intr_inv(const M3& d) {
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) add(32 + 3 * i + j, d.m[i][j]);
+    }
+    RB_D void add_intr(const M3& d) {
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) add(41 + 3 * i + j, d.m[i][j]);
+    }
+};
+
+// Adjoint of cam_sample_primary w.r.t. camera parameters (screen-position gradients are only needed for
+// distortion / screen_gradient_image; the latter is accumulated by the caller through d_screen).
+RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx, Real sy, const DRay& d_ray, CamAcc& acc, V2* d_screen) {
+    M4 C = cam_m4(cam.c2w);
+    M3 I = cam_m3(cam.intr_inv);
+    Real aspect = Real(cam.width) / Real(cam.height);
+    M4 d_C = zero_m4();
+    M3 d_I = zero_m3();
+    if (cam.type == RB_CAMERA_PERSPECTIVE) {
+        V3 pt = mk3((sx - Real(0.5)) * 2, (sy - Real(0.5)) * (-2) / aspect, 1);
+        V3 dir = mul(I, pt);
+        V3 n_dir = normalize(dir);
+        V3 world_dir = xfm_vector(C, n_dir);
+        V3 d_world_dir = d_normalize(world_dir, d_ray.dir);
+        V3 d_n_dir = zero3();
+        d_xfm_vector(C, n_dir, d_world_dir, d_C, d_n_dir);
+        V3 d_dir = d_normalize(dir, d_n_dir);
+        d_outer_acc(d_I, d_dir, pt);
+        V3 d_cam_org = zero3();
+        d_xfm_point(C, zero3(), d_ray.org, d_C, d_cam_org);
+        if (d_screen != nullptr) {
+            V3 d_pt = mul_t(d_dir, I);
+            d_screen->x += d_pt.x * 2;
+            d_screen->y += d_pt.y * (-2 / aspect);
+        }
+    } else {
+        // NOTE: the reference's adjoint uses pt.z = 1 here although the forward uses 0 (src/camera.h:283-285 vs :146-148);
+        // reproduced for parity.
+        V3 pt = mk3((sx - Real(0.5)) * 2, (sy - Real(0.5)) * (-2) / aspect, 1);
+        V3 local_org = mul(I, pt);
+        V3 dir = xfm_vector(C, mk3(0, 0, 1));
+        V3 d_dir = d_normalize(dir, d_ray.dir);
+        V3 d_local_dir = zero3();
+        d_xfm_vector(C, mk3(0, 0, 1), d_dir, d_C, d_local_dir);
+        V3 d_local_org = zero3();
+        d_xfm_point(C, local_org, d_ray.org, d_C, d_local_org);
+        d_outer_acc(d_I, d_local_org, pt);
+        if (d_screen != nullptr) {
+            V3 d_pt = mul_t(d_local_org, I);
+            d_screen->x += d_pt.x * 2;
+            d_screen->y += d_pt.y * (-2 / aspect);
+        }
+    }
+    acc.add_intr_inv(d_I);
+    acc.add_c2w(d_C);
+}
+
+// ---- screen projection of a world-space segment (primary edge sampling) ----
+RB_HD V2 cam_to_screen(const DevCamera& cam, V3 pt) {
+    M3 K = cam_m3(cam.intr);
+    Real aspect = Real(cam.width) / Real(cam.height);
+    V3 ip = mul(K, pt);
+    if (cam.type == RB_CAMERA_PERSPECTIVE) {
+        Real x = (ip.x / ip.z + 1) * Real(0.5);
+        Real y = (-(ip.y / ip.z) * aspect + 1) * Real(0.5);
+        return mk2(x, y);
+    } else {
+        Real x = (ip.x + 1) * Real(0.5);
+        Real y = (-ip.y * aspect + 1) * Real(0.5);
+        return mk2(x, y);
+    }
+}
+RB_HD bool cam_project(const DevCamera& cam, V3 p0, V3 p1, V2& pp0, V2& pp1) {
+    M4 W = cam_m4(cam.w2c);
+    V3 a = xfm_point(W, p0), b = xfm_point(W, p1);
+    Real cn = cam.clip_near;
+    if (a.z < cn && b.z < cn) return false;
+    if (a.z < cn) {
+        V3 dir = a - b;
+        Real t = -(b.z - cn) / dir.z;
+        a = b + t * dir;
+    } else if (b.z < cn) {
+        V3 dir = b - a;
+        Real t = -(a.z - cn) / dir.z;
+        b = a + t * dir;
+    }
+    pp0 = cam_to_screen(cam, a);
+    pp1 = cam_to_screen(cam, b);
+    return true;
+}
+RB_D void d_cam_to_screen(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt) {
+    M3 K = cam_m3(cam.intr);
+    Real aspect = Real(cam.width) / Real(cam.height);
+    V3 ip = mul(K, pt);
+    M3 d_K = zero_m3();
+    V3 d_ip;
+    if (cam.type == RB_CAMERA_PERSPECTIVE) {
+        V2 q = mk2(ip.x / ip.z, ip.y / ip.z);
+        V2 d_q = mk2(dx * Real(0.5), dy * Real(-0.5) * aspect);
+        d_ip = mk3(d_q.x / ip.z, d_q.y / ip.z, -(d_q.x * q.x / ip.z + d_q.y * q.y / ip.z));
+    } else {
+        d_ip = mk3(dx * Real(0.5), dy * Real(-0.5) * aspect, 0);
+    }
+    d_outer_acc(d_K, d_ip, pt);
+    acc.add_intr(d_K);
+    d_pt += mul_t(d_ip, K);
+}
+RB_D void d_cam_project(const DevCamera& cam, V3 p0, V3 p1, Real dp0x, Real dp0y, Real dp1x, Real dp1y, CamAcc& acc, V3& d_p0,
+                        V3& d_p1) {
+    M4 W = cam_m4(cam.w2c);
+    V3 a = xfm_point(W, p0), b = xfm_point(W, p1);
+    Real cn = cam.clip_near;
+    if (a.z < cn && b.z < cn) return;
+    V3 ca = a, cb = b;
+    if (a.z < cn) {
+        V3 dir = a - b;
+        Real t = -(b.z - cn) / dir.z;
+        ca = b + t * dir;
+    } else if (b.z < cn) {
+        V3 dir = b - a;
+        Real t = -(a.z - cn) / dir.z;
+        cb = a + t * dir;
+    }
+    V3 d_ca = zero3(), d_cb = zero3();
+    d_cam_to_screen(cam, ca, dp0x, dp0y, acc, d_ca);
+    d_cam_to_screen(cam, cb, dp1x, dp1y, acc, d_cb);
+    V3 d_a = zero3(), d_b = zero3();
+    // The "+ clip_near" below reproduces the reference's sign (src/camera.h:776,:791 vs :578,:584).
+    if (a.z < cn) {
+        V3 dir = a - b;
+        Real t = -(b.z + cn) / dir.z;
+        d_b += d_ca;
+        Real dt = dot(dir, d_ca);
+        V3 ddir = t * d_ca;
+        d_b.z += (-dt / dir.z);
+        ddir.z -= dt * t / dir.z;
+        d_a += ddir;
+        d_b -= ddir;
+        d_b += d_cb;
+    } else if (b.z < cn) {
+        V3 dir = b - a;
+        Real t = -(a.z + cn) / dir.z;
+        d_a += d_cb;
+        Real dt = dot(dir, d_cb);
+        V3 ddir = t * d_cb;
+        d_a.z += (-dt / dir.z);
+        ddir.z -= dt * t / dir.z;
+        d_b += ddir;
+        d_a -= ddir;
+        d_a += d_ca;
+    } else {
+        d_a += d_ca;
+        d_b += d_cb;
+    }
+    M4 d_W = zero_m4();
+    d_xfm_point(W, p0, d_a, d_W, d_p0);
+    d_xfm_point(W, p1, d_b, d_W, d_p1);
+    // d_cam_to_world = -W^T d_W W^T is applied once, at the end, on the reduced accumulator (it is linear in d_W).
+    acc.add_w2c(d_W);
+}
+RB_HD bool cam_in_screen(const DevCamera& cam, V2 pt) {
+    int xi = int(pt.x * cam.width), yi = int(pt.y * cam.height);
+    if (xi < cam.vp_beg[0] || xi >= cam.vp_end[0] || yi < cam.vp_beg[1] || yi >= cam.vp_end[1]) return false;
+    return pt.x >= 0 && pt.x < 1 && pt.y >= 0 && pt.y < 1;
+}

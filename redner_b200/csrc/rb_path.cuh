@@ -1,0 +1,368 @@
+// Per-path device code: light sampling, per-vertex radiance estimate (NEE + BSDF sampling with power-2 MIS),
+// the bounce loop, and the hand-derived adjoint of one path vertex.
+//   light_point_sampler             src/scene.cpp:692-741
+//   primary_contribs_accumulator    src/primary_contribution.cpp:6-35  (radiance channel)
+//   path_contribs_accumulator       src/path_contribution.cpp:5-154
+//   d_path_contribs_accumulator     src/path_contribution.cpp:156-592
+//   bounce loop                     src/pathtracer.cpp:292-390
+// One thread carries one path from the camera (or from an edge ray) to its end; nothing but the final pixel /
+// gradient contributions leaves the SM.
+#pragma once
+#include "rb_bvh.cuh"
+#include "rb_camera.cuh"
+#include "rb_material.cuh"
+#include "rb_sampler.cuh"
+#include "rb_shape.cuh"
+
+// upper_bound on an ascending double table: number of entries <= x (thrust::upper_bound, src/scene.cpp:698)
+RB_D int cdf_pick(const double* cdf, int n, double x) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (cdf[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return rb_clampi(lo - 1, 0, n - 1);
+}
+
+struct LightSampleRec {
+    Isect isect;      // (light shape, triangle)
+    V2 uv;            // the 2-D sample used on the triangle
+    bool unoccluded;  // shadow ray reached the light (nee_ray.tmax >= 0)
+};
+
+RB_D bool closest_hit(const DevScene& sc, const Ray& ray, Isect& is) {
+    float t;
+    return bvh_trace<false>(sc, ray, is.shape_id, is.tri_id, t);
+}
+RB_D bool any_hit(const DevScene& sc, const Ray& ray) {
+    int s, tr;
+    float t;
+    return bvh_trace<true>(sc, ray, s, tr, t);
+}
+
+// Pick a light, a triangle on it and a point on the triangle; trace the shadow ray.
+RB_D void sample_light(const DevScene& sc, const SurfacePoint& sp, double light_sel, double tri_sel, V2 uv, LightSampleRec& rec,
+                       SurfacePoint& lp) {
+    int light_id = cdf_pick(sc.light_cdf, sc.num_lights, light_sel);
+    const DevLight& light = sc.lights[light_id];
+    const rb_shape& shape = sc.shapes[light.shape_id];
+    const double* acdf = sc.area_cdf_pool + sc.area_cdf_offset[light_id];
+    int tri = cdf_pick(acdf, shape.num_triangles, tri_sel);
+    rec.isect.shape_id = light.shape_id;
+    rec.isect.tri_id = tri;
+    rec.uv = uv;
+    lp = sample_light_triangle(shape, tri, uv);
+    Ray sh;
+    V3 d = lp.position - sp.position;
+    sh.org = sp.position;
+    sh.dir = normalize(d);
+    sh.tmin = Real(1e-3);
+    sh.tmax = (1 - Real(1e-3)) * length(d);
+    rec.unoccluded = !any_hit(sc, sh);
+}
+
+// Emission seen along a primary / edge ray (radiance channel of accumulate_primary_contribs).
+RB_D V3 hit_emission(const DevScene& sc, const Isect& is, const SurfacePoint& sp, V3 wi) {
+    if (!is.valid()) return zero3();
+    const rb_shape& shape = sc.shapes[is.shape_id];
+    if (shape.light_id >= 0) {
+        const DevLight& light = sc.lights[shape.light_id];
+        if (light.directly_visible && (light.two_sided || dot(wi, sp.shading_frame.n) > 0))
+            return mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
+    }
+    return zero3();
+}
+
+RB_D Real mis_power2(Real p_other, Real p_this) {
+    double r = (double)p_other / (double)p_this;
+    return (Real)(1.0 / (1.0 + r * r));
+}
+
+// Radiance estimate at one vertex: returns nee + scatter (not yet multiplied by the throughput) and the
+// throughput factor for the next vertex.
+RB_D V3 vertex_estimate(const DevScene& sc, const rb_material& mat, const SurfacePoint& sp, V3 wi, Real min_rough, const LightSampleRec& ls,
+                        const SurfacePoint& lp, const Isect& bis, const SurfacePoint& bp, V3& scatter_factor, bool& scatter_ok) {
+    V3 nee = zero3();
+    if (ls.unoccluded) {
+        const rb_shape& lshape = sc.shapes[ls.isect.shape_id];
+        V3 dir = lp.position - sp.position;
+        Real dist_sq = length_sq(dir);
+        V3 wo = dir / sqrt(dist_sq);
+        if (dist_sq > Real(1e-20) && lshape.light_id >= 0) {
+            const DevLight& light = sc.lights[lshape.light_id];
+            if (light.two_sided || dot(-wo, lp.shading_frame.n) > 0) {
+                V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+                Real G = fabs(dot(wo, lp.geom_normal)) / dist_sq;
+                Real pdf_nee = (Real)(sc.light_pmf[lshape.light_id] / sc.light_areas[lshape.light_id]);
+                Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough) * G;
+                Real w = mis_power2(pdf_b, pdf_nee);
+                nee = (w * G / pdf_nee) * f * mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
+            }
+        }
+    }
+    V3 scatter = zero3();
+    scatter_factor = zero3();
+    scatter_ok = false;
+    if (bis.valid()) {
+        const rb_shape& bshape = sc.shapes[bis.shape_id];
+        V3 dir = bp.position - sp.position;
+        Real dist_sq = length_sq(dir);
+        V3 wo = dir / sqrt(dist_sq);
+        Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
+        if (dist_sq > Real(1e-20) && pdf_b > Real(1e-20)) {
+            V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+            if (bshape.light_id >= 0) {
+                const DevLight& light = sc.lights[bshape.light_id];
+                if (light.two_sided || dot(-wo, bp.shading_frame.n) > 0) {
+                    Real G = fabs(dot(wo, bp.geom_normal)) / dist_sq;
+                    Real pdf_nee = (Real)(sc.light_pmf[bshape.light_id] * (1.0 / sc.light_areas[bshape.light_id])) / G;
+                    Real w = mis_power2(pdf_nee, pdf_b);
+                    scatter = (w / pdf_b) * f * mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
+                }
+            }
+            scatter_factor = f / pdf_b;
+            scatter_ok = true;
+        }
+    }
+    return nee + scatter;
+}
+
+// What the adjoint pass needs to know about path vertex d (everything else is recomputed).
+struct VertexRec {
+    Ray ray;       // ray that reached the vertex
+    RayDiff rd_in; // its differential before the hit
+    Isect isect;
+    V3 thr;
+    Real min_rough;
+    LightSampleRec light;
+};
+
+// Follows a path from an already intersected vertex through at most (max_bounces - depth_begin) bounces and
+// returns the sum of throughput-weighted vertex estimates.  `smp` must be positioned at the light-sample
+// dimension of depth `depth_begin`.  If REC, vertices are written to rec[depth - depth_begin] and *num_rec is
+// the number of vertices at which an estimate was formed.
+template <bool REC>
+RB_D V3 trace_bounces(const DevScene& sc, Sampler& smp, Ray ray, RayDiff rd_in, Isect is, V3 thr, Real min_rough, int depth_begin,
+                      int max_bounces, VertexRec* rec, int rec_stride, int* num_rec) {
+    V3 L = zero3();
+    int count = 0;
+    if (sc.num_lights > 0) {
+        for (int depth = depth_begin; depth < max_bounces && is.valid(); depth++) {
+            RayDiff rd;
+            SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd_in, rd);
+            const rb_material& mat = sc.materials[sc.shapes[is.shape_id].material_id];
+            V3 wi = -ray.dir;
+            double l_sel = smp.next(), t_sel = smp.next(), lu = smp.next(), lv = smp.next();
+            LightSampleRec ls;
+            SurfacePoint lp;
+            sample_light(sc, sp, l_sel, t_sel, mk2((Real)lu, (Real)lv), ls, lp);
+            double bu = smp.next(), bv = smp.next(), bw = smp.next();
+            if (REC) {
+                VertexRec& r = rec[(size_t)count * rec_stride];
+                r.ray = ray;
+                r.rd_in = rd_in;
+                r.isect = is;
+                r.thr = thr;
+                r.min_rough = min_rough;
+                r.light = ls;
+            }
+            RayDiff rd_b;
+            Real next_rough;
+            V3 dir = bsdf_sample_dir(mat, sp, wi, mk2((Real)bu, (Real)bv), bw, min_rough, rd, rd_b, next_rough);
+            Ray nray;
+            nray.org = sp.position;
+            nray.dir = dir;
+            nray.tmin = Real(1e-3);
+            nray.tmax = INFINITY;
+            Isect bis = no_isect();
+            SurfacePoint bp = zero_point();
+            RayDiff rd_after;
+            if (closest_hit(sc, nray, bis)) bp = make_surface_point(sc.shapes[bis.shape_id], bis.tri_id, nray, rd_b, rd_after);
+            V3 factor;
+            bool ok;
+            V3 est = vertex_estimate(sc, mat, sp, wi, min_rough, ls, lp, bis, bp, factor, ok);
+            L += thr * est;
+            count++;
+            thr = ok ? thr * factor : zero3();
+            ray = nray;
+            rd_in = rd_b;
+            is = bis;
+            min_rough = next_rough;
+        }
+    }
+    if (REC) {
+        // terminal vertex: no estimate is formed there, but the adjoint of the previous vertex needs its hit
+        VertexRec& r = rec[(size_t)count * rec_stride];
+        r.ray = ray;
+        r.rd_in = rd_in;
+        r.isect = is;
+        r.thr = thr;
+        r.min_rough = min_rough;
+        *num_rec = count;
+    }
+    return L;
+}
+
+// Gradient sinks for geometry: per-corner scatter with warp aggregation.
+RB_D void scatter_vertex_grads(const DevScene& sc, const DevDScene& ds, const Isect& is, const V3 d_vp[3], const V3 d_vn[3], const V2 d_vuv[3],
+                               const V3 d_vc[3]) {
+    const rb_shape& s = sc.shapes[is.shape_id];
+    const rb_dshape& d = ds.shapes[is.shape_id];
+    TriAttribs a;
+    tri_attribs(s, is.tri_id, a);
+    for (int k = 0; k < 3; k++) {
+        if (d.vertices) agg_add3(d.vertices + 3 * (size_t)a.ind[k], d_vp[k]);
+        if (s.uvs && d.uvs) agg_add2(d.uvs + 2 * (size_t)a.uv_ind[k], d_vuv[k]);
+        if (s.normals && d.normals) agg_add3(d.normals + 3 * (size_t)a.n_ind[k], d_vn[k]);
+        if (s.colors && d.colors) agg_add3(d.colors + 3 * (size_t)a.ind[k], d_vc[k]);
+    }
+}
+
+// Adjoint state flowing from vertex d+1 to vertex d.
+struct VertexAdjoint {
+    V3 d_thr;
+    DRay d_ray;
+    SurfacePoint d_point;
+};
+RB_D VertexAdjoint zero_vertex_adjoint() {
+    VertexAdjoint a;
+    a.d_thr = zero3();
+    a.d_ray = zero_dray();
+    a.d_point = zero_point();
+    return a;
+}
+
+// Adjoint of vertex_estimate + throughput update at vertex `cur`, given the adjoint arriving from vertex `nxt`.
+// d_contrib = weight * d_image[pixel] (radiance channels).
+RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const VertexRec& cur, const VertexRec* nxt, V3 d_contrib,
+                            const VertexAdjoint& next) {
+    VertexAdjoint out = zero_vertex_adjoint();
+    const rb_shape& shape = sc.shapes[cur.isect.shape_id];
+    const rb_material& mat = sc.materials[shape.material_id];
+    const rb_material& d_mat = ds.materials[shape.material_id];
+    RayDiff rd;
+    SurfacePoint sp = make_surface_point(shape, cur.isect.tri_id, cur.ray, cur.rd_in, rd);
+    V3 wi = -cur.ray.dir;
+    V3 p = sp.position;
+    V3 thr = cur.thr;
+    Real min_rough = cur.min_rough;
+    // ---- next event estimation
+    if (cur.light.unoccluded) {
+        const Isect& lis = cur.light.isect;
+        const rb_shape& lshape = sc.shapes[lis.shape_id];
+        SurfacePoint lp = sample_light_triangle(lshape, lis.tri_id, cur.light.uv);
+        V3 dir = lp.position - p;
+        Real dist_sq = length_sq(dir);
+        V3 wo = dir / sqrt(dist_sq);
+        if (lshape.light_id >= 0) {
+            const DevLight& light = sc.lights[lshape.light_id];
+            if (light.two_sided || dot(-wo, lp.shading_frame.n) > 0) {
+                V3 d_lv[3] = {zero3(), zero3(), zero3()};
+                V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+                Real cos_l = dot(wo, lp.geom_normal);
+                Real G = fabs(cos_l) / dist_sq;
+                V3 Le = mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
+                Real pdf_nee = (Real)(sc.light_pmf[lshape.light_id] * (1.0 / sc.light_areas[lshape.light_id]));
+                Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough) * G;
+                Real mis = mis_power2(pdf_b, pdf_nee);
+                V3 nee = (mis * G / pdf_nee) * f * Le;
+                V3 d_nee = d_contrib * thr;
+                out.d_thr += d_contrib * nee;
+                Real wgt = mis / pdf_nee;
+                // derivatives of the MIS weight and of the light-selection pmf are ignored (src/path_contribution.cpp:239)
+                Real d_wgt = G * sum(d_nee * f * Le);
+                Real d_pdf_nee = -d_wgt * wgt / pdf_nee;
+                Real d_G = wgt * sum(d_nee * f * Le);
+                V3 d_f = wgt * G * (d_nee * Le);
+                V3 d_Le = wgt * G * (d_nee * f);
+                Real d_area = -d_pdf_nee * pdf_nee / shape_tri_area(lshape, lis.tri_id);
+                d_shape_tri_area(lshape, lis.tri_id, d_area, d_lv);
+                agg_add3(ds.light_intensity[lshape.light_id], d_Le);
+                Real d_cos_l = cos_l > 0 ? d_G / dist_sq : -d_G / dist_sq;
+                Real d_dist_sq = -d_G * G / dist_sq;
+                V3 d_wo = d_cos_l * lp.geom_normal;
+                SurfacePoint d_lp = zero_point();
+                d_lp.geom_normal = d_cos_l * wo;
+                V3 d_wi = zero3();
+                d_bsdf_eval(mat, d_mat, sp, wi, wo, min_rough, d_f, out.d_point, d_wi, d_wo);
+                V3 d_dir = d_wo / sqrt(dist_sq);
+                Real d_sqrt = -sum(d_wo * dir) / dist_sq;
+                d_dist_sq += Real(0.5) * d_sqrt / sqrt(dist_sq);
+                d_dir += d_length_sq(dir, d_dist_sq);
+                d_lp.position += d_dir;
+                out.d_point.position -= d_dir;
+                out.d_ray.dir -= d_wi;
+                d_sample_light_triangle(lshape, lis.tri_id, cur.light.uv, d_lp, d_lv);
+                int idx[3];
+                shape_tri(lshape, lis.tri_id, idx);
+                float* dv = ds.shapes[lis.shape_id].vertices;
+                if (dv) {
+                    agg_add3(dv + 3 * (size_t)idx[0], d_lv[0]);
+                    agg_add3(dv + 3 * (size_t)idx[1], d_lv[1]);
+                    agg_add3(dv + 3 * (size_t)idx[2], d_lv[2]);
+                }
+            }
+        }
+    }
+    // ---- BSDF-sampled continuation
+    if (nxt != nullptr && nxt->isect.valid()) {
+        const Isect& bis = nxt->isect;
+        const rb_shape& bshape = sc.shapes[bis.shape_id];
+        RayDiff rd_after;
+        SurfacePoint bp = make_surface_point(bshape, bis.tri_id, nxt->ray, nxt->rd_in, rd_after);
+        V3 dir = bp.position - p;
+        Real dist_sq = length_sq(dir);
+        V3 wo = dir / sqrt(dist_sq);
+        Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
+        if (pdf_b > 0) {
+            V3 d_bvp[3] = {zero3(), zero3(), zero3()}, d_bvn[3] = {zero3(), zero3(), zero3()}, d_bvc[3] = {zero3(), zero3(), zero3()};
+            V2 d_bvuv[3] = {zero2(), zero2(), zero2()};
+            V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+            V3 factor = f / pdf_b;
+            out.d_thr += next.d_thr * factor;
+            V3 d_factor = next.d_thr * thr;
+            // the derivative w.r.t. pdf_bsdf is dropped on purpose (src/path_contribution.cpp:369-376)
+            V3 d_f = d_factor / pdf_b;
+            if (bshape.light_id >= 0) {
+                const DevLight& light = sc.lights[bshape.light_id];
+                if (light.two_sided || dot(-wo, bp.shading_frame.n) > 0) {
+                    Real G = fabs(dot(wo, bp.geom_normal)) / dist_sq;
+                    V3 Le = mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
+                    Real pdf_nee = (Real)(sc.light_pmf[bshape.light_id] * (1.0 / sc.light_areas[bshape.light_id])) / G;
+                    Real mis = mis_power2(pdf_nee, pdf_b);
+                    V3 scatter = (mis / pdf_b) * f * Le;
+                    V3 d_scatter = d_contrib * thr;
+                    out.d_thr += d_contrib * scatter;
+                    Real wgt = mis / pdf_b;
+                    d_f += wgt * (d_scatter * Le);
+                    agg_add3(ds.light_intensity[bshape.light_id], wgt * (d_scatter * f));
+                }
+            }
+            V3 d_wi = zero3();
+            V3 d_wo = next.d_ray.dir;
+            d_bsdf_eval(mat, d_mat, sp, wi, wo, min_rough, d_f, out.d_point, d_wi, d_wo);
+            V3 d_dir = d_wo / sqrt(dist_sq);
+            Real d_sqrt = -sum(d_wo * dir) / dist_sq;
+            Real d_dist_sq = Real(0.5) * d_sqrt / sqrt(dist_sq);
+            d_dir += d_length_sq(dir, d_dist_sq);
+            SurfacePoint d_bp = next.d_point;
+            d_bp.position += d_dir;
+            DRay d_ray = zero_dray();
+            RayDiff d_rd_b = zero_raydiff();
+            Ray bray;
+            bray.org = sp.position;
+            bray.dir = wo;
+            bray.tmin = Real(1e-3);
+            bray.tmax = INFINITY;
+            d_make_surface_point(bshape, bis.tri_id, bray, nxt->rd_in, d_bp, zero_raydiff(), d_ray, d_rd_b, d_bvp, d_bvn, d_bvuv, d_bvc);
+            // position gradient through the sampled direction only below glossy vertices (src/path_contribution.cpp:447-455)
+            if (min_rough > Real(0.01)) {
+                out.d_point.position -= d_dir;
+                out.d_point.position += d_ray.org;
+            }
+            out.d_ray.dir -= d_wi;
+            scatter_vertex_grads(sc, ds, bis, d_bvp, d_bvn, d_bvuv, d_bvc);
+        }
+    }
+    return out;
+}

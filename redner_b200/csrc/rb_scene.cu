@@ -1,0 +1,750 @@
+// Scene construction: GPU LBVH over all triangles of all shapes, light distributions, edge list.
+// Reference counterpart: Scene::Scene src/scene.cpp:63-307 (Embree/OptiX build :78-155, light CDFs :197-253,
+// compute_area_cdf :38-61) and EdgeSampler::EdgeSampler src/edge.cpp:233-383.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "rb_edge.cuh"
+#include "rb_scene.cuh"
+
+static thread_local std::string g_last_error;
+void rb_set_error(const std::string& msg) { g_last_error = msg; }
+extern "C" const char* rb_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* rb_version(void) { return "redner_b200 0.1 (sm_100a)"; }
+
+template <typename T>
+static int dev_alloc(rb_scene* sc, T** out, size_t count, cudaStream_t stream) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    RB_CUDA_OK(cudaMallocAsync(&p, bytes, stream));
+    sc->allocs.push_back(p);
+    *out = (T*)p;
+    return 0;
+}
+template <typename T>
+static int dev_upload(rb_scene* sc, T** out, const T* host, size_t count, cudaStream_t stream) {
+    if (dev_alloc(sc, out, count, stream)) return 1;
+    if (count > 0) RB_CUDA_OK(cudaMemcpyAsync(*out, host, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ BVH build
+__device__ __forceinline__ unsigned int f2ord(float f) {
+    unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int o) {
+    unsigned int b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ void global_to_shape(const int* tri_offset, int num_shapes, int g, int& shape, int& tri) {
+    int lo = 0, hi = num_shapes; // offsets has num_shapes + 1 entries
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (tri_offset[mid] <= g) lo = mid; else hi = mid;
+    }
+    shape = lo;
+    tri = g - tri_offset[lo];
+}
+
+__global__ void k_scene_bounds(const rb_shape* shapes, const int* tri_offset, int num_shapes, int T, unsigned int* bounds) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < T; g += gridDim.x * blockDim.x) {
+        int s, t;
+        global_to_shape(tri_offset, num_shapes, g, s, t);
+        const rb_shape& sh = shapes[s];
+        for (int k = 0; k < 3; k++) {
+            int vi = sh.indices[3 * (size_t)t + k];
+            for (int a = 0; a < 3; a++) {
+                float c = sh.vertices[3 * (size_t)vi + a];
+                lo[a] = fminf(lo[a], c);
+                hi[a] = fmaxf(hi[a], c);
+            }
+        }
+    }
+    for (int a = 0; a < 3; a++) {
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int a = 0; a < 3; a++) {
+            atomicMin(&bounds[a], f2ord(lo[a]));
+            atomicMax(&bounds[3 + a], f2ord(hi[a]));
+        }
+    }
+}
+__device__ __forceinline__ unsigned long long expand21(unsigned int v) {
+    unsigned long long x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffULL;
+    x = (x | x << 16) & 0x1f0000ff0000ffULL;
+    x = (x | x << 8) & 0x100f00f00f00f00fULL;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+__global__ void k_morton(const rb_shape* shapes, const int* tri_offset, int num_shapes, int T, const unsigned int* bounds,
+                         unsigned long long* keys, int* vals) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= T) return;
+    int s, t;
+    global_to_shape(tri_offset, num_shapes, g, s, t);
+    const rb_shape& sh = shapes[s];
+    float c[3] = {0, 0, 0};
+    for (int k = 0; k < 3; k++) {
+        int vi = sh.indices[3 * (size_t)t + k];
+        for (int a = 0; a < 3; a++) c[a] += sh.vertices[3 * (size_t)vi + a];
+    }
+    unsigned int q[3];
+    for (int a = 0; a < 3; a++) {
+        float lo = ord2f(bounds[a]), hi = ord2f(bounds[3 + a]);
+        float ext = fmaxf(hi - lo, 1e-30f);
+        float u = (c[a] * (1.0f / 3.0f) - lo) / ext;
+        u = fminf(fmaxf(u, 0.f), 1.f);
+        q[a] = (unsigned int)fminf(u * 2097152.0f, 2097151.0f);
+    }
+    keys[g] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+    vals[g] = g;
+}
+__global__ void k_leaves(const rb_shape* shapes, const int* tri_offset, int num_shapes, int T, const int* sorted_vals,
+                         const unsigned int* bounds, BVHTri* tris, float* leaf_box) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    int g = sorted_vals[i];
+    int s, t;
+    global_to_shape(tri_offset, num_shapes, g, s, t);
+    const rb_shape& sh = shapes[s];
+    float v[3][3];
+    for (int k = 0; k < 3; k++) {
+        int vi = sh.indices[3 * (size_t)t + k];
+        for (int a = 0; a < 3; a++) v[k][a] = sh.vertices[3 * (size_t)vi + a];
+    }
+    BVHTri tr;
+    tr.v0 = make_float4(v[0][0], v[0][1], v[0][2], __int_as_float(s));
+    tr.v1 = make_float4(v[1][0], v[1][1], v[1][2], __int_as_float(t));
+    tr.v2 = make_float4(v[2][0], v[2][1], v[2][2], 0.f);
+    tris[i] = tr;
+    float ext = 0.f;
+    for (int a = 0; a < 3; a++) ext = fmaxf(ext, ord2f(bounds[3 + a]) - ord2f(bounds[a]));
+    for (int a = 0; a < 3; a++) {
+        float lo = fminf(v[0][a], fminf(v[1][a], v[2][a])), hi = fmaxf(v[0][a], fmaxf(v[1][a], v[2][a]));
+        float pad = fmaxf(fabsf(lo), fabsf(hi)) * 4e-7f + ext * 1e-7f;
+        leaf_box[6 * (size_t)i + a] = lo - pad;
+        leaf_box[6 * (size_t)i + 3 + a] = hi + pad;
+    }
+}
+__device__ __forceinline__ int lbvh_delta(const unsigned long long* keys, int T, int i, int j) {
+    if (j < 0 || j >= T) return -1;
+    unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll(a ^ b);
+}
+// Karras 2012: one thread per internal node.
+__global__ void k_karras(const unsigned long long* keys, int T, BVHNode* nodes, int* parent_inner, int* parent_leaf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T - 1) return;
+    int d = (lbvh_delta(keys, T, i, i + 1) - lbvh_delta(keys, T, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = lbvh_delta(keys, T, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, T, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (lbvh_delta(keys, T, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = lbvh_delta(keys, T, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (lbvh_delta(keys, T, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int left = (lo == gamma) ? ~gamma : gamma;
+    int right = (hi == gamma + 1) ? ~(gamma + 1) : (gamma + 1);
+    nodes[i].left = left;
+    nodes[i].right = right;
+    nodes[i].pad0 = nodes[i].pad1 = 0;
+    if (left >= 0) parent_inner[left] = i; else parent_leaf[~left] = i;
+    if (right >= 0) parent_inner[right] = i; else parent_leaf[~right] = i;
+    if (i == 0) parent_inner[0] = -1;
+}
+__device__ __forceinline__ void load_box(const float* leaf_box, const float* inner_box, int child, float b[6]) {
+    const float* p = child >= 0 ? inner_box + 6 * (size_t)child : leaf_box + 6 * (size_t)(~child);
+    for (int k = 0; k < 6; k++) b[k] = p[k];
+}
+__global__ void k_refit(int T, BVHNode* nodes, const int* parent_inner, const int* parent_leaf, const float* leaf_box, float* inner_box,
+                        int* flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    int node = parent_leaf[i];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&flags[node], 1) == 0) return; // first arrival: sibling subtree not finished yet
+        __threadfence();
+        float l[6], r[6];
+        load_box(leaf_box, inner_box, nodes[node].left, l);
+        load_box(leaf_box, inner_box, nodes[node].right, r);
+        nodes[node].lo_x_hi_x = make_float4(l[0], l[3], r[0], r[3]);
+        nodes[node].lo_y_hi_y = make_float4(l[1], l[4], r[1], r[4]);
+        nodes[node].lo_z_hi_z = make_float4(l[2], l[5], r[2], r[5]);
+        for (int k = 0; k < 3; k++) {
+            inner_box[6 * (size_t)node + k] = fminf(l[k], r[k]);
+            inner_box[6 * (size_t)node + 3 + k] = fmaxf(l[k], r[k]);
+        }
+        node = parent_inner[node];
+    }
+}
+
+int rb_build_bvh(rb_scene* sc, cudaStream_t stream) {
+    int num_shapes = (int)sc->shapes.size();
+    std::vector<int> offs(num_shapes + 1, 0);
+    for (int i = 0; i < num_shapes; i++) offs[i + 1] = offs[i] + sc->shapes[i].num_triangles;
+    int T = offs[num_shapes];
+    sc->dev.num_tris = T;
+    sc->dev.bvh_nodes = nullptr;
+    sc->dev.bvh_tris = nullptr;
+    sc->dev.bvh_root = 0;
+    if (T == 0) return 0;
+    int* d_offs;
+    if (dev_upload(sc, &d_offs, offs.data(), offs.size(), stream)) return 1;
+    unsigned int* d_bounds;
+    if (dev_alloc(sc, &d_bounds, 6, stream)) return 1;
+    unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    RB_CUDA_OK(cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+    unsigned long long *keys, *keys_sorted;
+    int *vals, *vals_sorted, *parent_inner, *parent_leaf, *flags;
+    float *leaf_box, *inner_box;
+    BVHTri* tris;
+    BVHNode* nodes;
+    if (dev_alloc(sc, &keys, T, stream) || dev_alloc(sc, &keys_sorted, T, stream) || dev_alloc(sc, &vals, T, stream) ||
+        dev_alloc(sc, &vals_sorted, T, stream) || dev_alloc(sc, &parent_inner, T, stream) || dev_alloc(sc, &parent_leaf, T, stream) ||
+        dev_alloc(sc, &flags, T, stream) || dev_alloc(sc, &leaf_box, 6 * (size_t)T, stream) || dev_alloc(sc, &inner_box, 6 * (size_t)T, stream) ||
+        dev_alloc(sc, &tris, T, stream) || dev_alloc(sc, &nodes, T, stream))
+        return 1;
+    int B = 256, G = (T + B - 1) / B;
+    k_scene_bounds<<<std::min(G, 1184), B, 0, stream>>>(sc->dev.shapes, d_offs, num_shapes, T, d_bounds);
+    k_morton<<<G, B, 0, stream>>>(sc->dev.shapes, d_offs, num_shapes, T, d_bounds, keys, vals);
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, vals, vals_sorted, T, 0, 63, stream);
+    unsigned char* tmp;
+    if (dev_alloc(sc, &tmp, tmp_bytes, stream)) return 1;
+    RB_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, vals, vals_sorted, T, 0, 63, stream));
+    k_leaves<<<G, B, 0, stream>>>(sc->dev.shapes, d_offs, num_shapes, T, vals_sorted, d_bounds, tris, leaf_box);
+    if (T > 1) {
+        RB_CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(int) * T, stream));
+        k_karras<<<G, B, 0, stream>>>(keys_sorted, T, nodes, parent_inner, parent_leaf);
+        k_refit<<<G, B, 0, stream>>>(T, nodes, parent_inner, parent_leaf, leaf_box, inner_box, flags);
+        sc->dev.bvh_root = 0;
+    } else {
+        sc->dev.bvh_root = ~0;
+    }
+    RB_CUDA_OK(cudaGetLastError());
+    sc->dev.bvh_nodes = nodes;
+    sc->dev.bvh_tris = tris;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ lights
+// Host mirrors of the geometry (needed for the serial double-precision CDFs the reference builds, and for edges).
+struct HostMesh {
+    std::vector<float> vertices, normals;
+    std::vector<int> indices;
+};
+static int fetch_mesh(const rb_shape& s, HostMesh& m, bool want_normals, cudaStream_t stream) {
+    m.vertices.resize(3 * (size_t)s.num_vertices);
+    m.indices.resize(3 * (size_t)s.num_triangles);
+    if (s.num_vertices > 0)
+        RB_CUDA_OK(cudaMemcpyAsync(m.vertices.data(), s.vertices, m.vertices.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    if (s.num_triangles > 0)
+        RB_CUDA_OK(cudaMemcpyAsync(m.indices.data(), s.indices, m.indices.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    (void)want_normals;
+    return 0;
+}
+
+static std::vector<HostMesh>& host_meshes(rb_scene* sc) {
+    static thread_local std::vector<HostMesh> meshes;
+    (void)sc;
+    return meshes;
+}
+
+int rb_build_lights(rb_scene* sc, cudaStream_t stream) {
+    int L = (int)sc->lights.size();
+    sc->dev.num_lights = L;
+    sc->dev.lights = nullptr;
+    if (L == 0) return 0;
+    auto& meshes = host_meshes(sc);
+    std::vector<double> pmf(L), cdf(L), areas(L), pool;
+    std::vector<int> offsets(L);
+    double total = 0;
+    for (int l = 0; l < L; l++) {
+        const DevLight& light = sc->lights[l];
+        const HostMesh& m = meshes[light.shape_id];
+        int T = (int)m.indices.size() / 3;
+        offsets[l] = (int)pool.size();
+        std::vector<double> a(T);
+        double sum_area = 0; // serial sum in triangle order == thrust::reduce on the CPP backend (src/scene.cpp:43-45)
+        for (int t = 0; t < T; t++) {
+            const int* id = &m.indices[3 * (size_t)t];
+            double v[3][3];
+            for (int k = 0; k < 3; k++)
+                for (int c = 0; c < 3; c++) v[k][c] = m.vertices[3 * (size_t)id[k] + c];
+            double e1[3] = {v[1][0] - v[0][0], v[1][1] - v[0][1], v[1][2] - v[0][2]};
+            double e2[3] = {v[2][0] - v[0][0], v[2][1] - v[0][1], v[2][2] - v[0][2]};
+            double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+            a[t] = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+            sum_area += a[t];
+        }
+        double run = 0;
+        for (int t = 0; t < T; t++) { // exclusive scan, then normalise
+            pool.push_back(run / sum_area);
+            run += a[t];
+        }
+        areas[l] = sum_area;
+        double lum = 0.212671f * (double)light.intensity[0] + 0.715160f * (double)light.intensity[1] + 0.072169f * (double)light.intensity[2];
+        pmf[l] = sum_area * lum * double(M_PI);
+        total += pmf[l];
+    }
+    if (!(total > 0)) {
+        rb_set_error("rb_scene_create: total light importance is not positive (src/scene.cpp:243)");
+        return 1;
+    }
+    for (int l = 0; l < L; l++) pmf[l] /= total;
+    cdf[0] = 0;
+    for (int l = 1; l < L; l++) cdf[l] = cdf[l - 1] + pmf[l - 1];
+    DevLight* d_lights;
+    double *d_pmf, *d_cdf, *d_areas, *d_pool;
+    int* d_off;
+    if (dev_upload(sc, &d_lights, sc->lights.data(), L, stream) || dev_upload(sc, &d_pmf, pmf.data(), L, stream) ||
+        dev_upload(sc, &d_cdf, cdf.data(), L, stream) || dev_upload(sc, &d_areas, areas.data(), L, stream) ||
+        dev_upload(sc, &d_pool, pool.data(), pool.size(), stream) || dev_upload(sc, &d_off, offsets.data(), L, stream))
+        return 1;
+    RB_CUDA_OK(cudaStreamSynchronize(stream)); // host vectors go out of scope
+    sc->dev.lights = d_lights;
+    sc->dev.light_pmf = d_pmf;
+    sc->dev.light_cdf = d_cdf;
+    sc->dev.light_areas = d_areas;
+    sc->dev.area_cdf_pool = d_pool;
+    sc->dev.area_cdf_offset = d_off;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ edges
+static bool pos_less(const float* a, const float* b) { // strict lexicographic order on positions
+    if (a[0] != b[0]) return a[0] < b[0];
+    if (a[1] != b[1]) return a[1] < b[1];
+    return a[2] < b[2];
+}
+static bool pos_eq(const float* a, const float* b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
+
+int rb_build_edges(rb_scene* sc, cudaStream_t stream) {
+    sc->dev.edges = nullptr;
+    sc->dev.num_edges = 0;
+    sc->dev.prim_edge_pmf = sc->dev.prim_edge_cdf = nullptr;
+    if (!sc->dev.use_primary_edge && !sc->dev.use_secondary_edge) return 0;
+    auto& meshes = host_meshes(sc);
+    int S = (int)sc->shapes.size();
+    // host-addressable shape table for the shared RB_HD helpers
+    std::vector<rb_shape> hs(sc->shapes);
+    for (int s = 0; s < S; s++) {
+        hs[s].vertices = meshes[s].vertices.data();
+        hs[s].indices = meshes[s].indices.data();
+        // `normals` is only tested for null-ness by edge_is_silhouette
+    }
+    std::vector<Edge> edges;
+    for (int s = 0; s < S; s++) {
+        const HostMesh& m = meshes[s];
+        int T = (int)m.indices.size() / 3;
+        std::vector<Edge> he(3 * (size_t)T);
+        for (int t = 0; t < T; t++) {
+            const int* id = &m.indices[3 * (size_t)t];
+            for (int k = 0; k < 3; k++) {
+                int a = id[k], b = id[(k + 1) % 3];
+                Edge e;
+                e.shape_id = s;
+                e.v0 = std::min(a, b);
+                e.v1 = std::max(a, b);
+                e.f0 = t;
+                e.f1 = -1;
+                he[3 * (size_t)t + k] = e;
+            }
+        }
+        std::stable_sort(he.begin(), he.end(), [](const Edge& x, const Edge& y) { return x.v0 != y.v0 ? x.v0 < y.v0 : x.v1 < y.v1; });
+        // merge runs of equal (v0, v1): f0 of the first, f1 = f0 of the last (src/edge.cpp:86-90, :266-273)
+        std::vector<Edge> merged;
+        for (size_t i = 0; i < he.size();) {
+            size_t j = i + 1;
+            while (j < he.size() && he[j].v0 == he[i].v0 && he[j].v1 == he[i].v1) j++;
+            Edge e = he[i];
+            if (j - i >= 2) e.f1 = he[j - 1].f0;
+            merged.push_back(e);
+            i = j;
+        }
+        // seam repair: sort by end-point POSITIONS and pair up unmatched duplicates (src/edge.cpp:103-166, :280-288)
+        const float* V = m.vertices.data();
+        auto key = [&](const Edge& e, const float*& lo, const float*& hi) {
+            lo = V + 3 * (size_t)e.v0;
+            hi = V + 3 * (size_t)e.v1;
+            if (pos_less(hi, lo)) std::swap(lo, hi);
+        };
+        std::stable_sort(merged.begin(), merged.end(), [&](const Edge& x, const Edge& y) {
+            const float *xl, *xh, *yl, *yh;
+            key(x, xl, xh);
+            key(y, yl, yh);
+            if (!pos_eq(xl, yl)) return pos_less(xl, yl);
+            if (!pos_eq(xh, yh)) return pos_less(xh, yh);
+            return false;
+        });
+        std::vector<int> new_f1(merged.size());
+        for (size_t i = 0; i < merged.size(); i++) {
+            new_f1[i] = merged[i].f1;
+            if (merged[i].f1 != -1) continue;
+            const float *l, *h, *cl, *ch;
+            key(merged[i], l, h);
+            if (i > 0) {
+                key(merged[i - 1], cl, ch);
+                if (pos_eq(l, cl) && pos_eq(h, ch)) new_f1[i] = merged[i - 1].f0;
+            }
+            if (i + 1 < merged.size()) {
+                key(merged[i + 1], cl, ch);
+                if (pos_eq(l, cl) && pos_eq(h, ch)) new_f1[i] = merged[i + 1].f0;
+            }
+        }
+        for (size_t i = 0; i < merged.size(); i++) {
+            merged[i].f1 = new_f1[i];
+            edges.push_back(merged[i]);
+        }
+    }
+    // drop edges between coplanar faces (src/edge.cpp:293-296)
+    std::vector<Edge> kept;
+    for (const Edge& e : edges)
+        if (!edge_is_flat(hs.data(), e)) kept.push_back(e);
+    edges.swap(kept);
+    int E = (int)edges.size();
+    sc->dev.num_edges = E;
+    if (E == 0) return 0;
+    Edge* d_edges;
+    if (dev_upload(sc, &d_edges, edges.data(), E, stream)) return 1;
+    sc->dev.edges = d_edges;
+    if (sc->dev.use_primary_edge) {
+        // screen-space length of camera silhouettes -> PMF / CDF (src/edge.cpp:186-214, :298-331)
+        std::vector<double> pmf(E), cdf(E);
+        const DevCamera& cam = sc->dev.cam;
+        double iw = 1.0 / cam.c2w[15];
+        V3 org = mk3((Real)(cam.c2w[3] * iw), (Real)(cam.c2w[7] * iw), (Real)(cam.c2w[11] * iw));
+        double total = 0;
+        for (int i = 0; i < E; i++) {
+            const Edge& e = edges[i];
+            V3 v0 = edge_v0(hs.data(), e), v1 = edge_v1(hs.data(), e);
+            V2 p0, p1, c0, c1;
+            double w = 0;
+            if (cam_project(cam, v0, v1, p0, p1) && clip_line_unit(p0, p1, c0, c1) && edge_is_silhouette(hs.data(), org, e)) w = length(c1 - c0);
+            pmf[i] = w;
+            total += w;
+        }
+        double run = 0;
+        for (int i = 0; i < E; i++) {
+            pmf[i] = total > 0 ? pmf[i] / total : 0.0;
+            cdf[i] = run;
+            run += pmf[i];
+        }
+        double *d_pmf, *d_cdf;
+        if (dev_upload(sc, &d_pmf, pmf.data(), E, stream) || dev_upload(sc, &d_cdf, cdf.data(), E, stream)) return 1;
+        sc->dev.prim_edge_pmf = d_pmf;
+        sc->dev.prim_edge_cdf = d_cdf;
+    }
+    RB_CUDA_OK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ tables (per device, uploaded once)
+struct DeviceTables {
+    unsigned long long* sobol = nullptr;
+    float* ltc = nullptr;
+    int sobol_dims = 0;
+};
+static std::mutex g_tab_mutex;
+static DeviceTables g_tables[64];
+static int get_tables(int device, DeviceTables& out) {
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    DeviceTables& t = g_tables[device & 63];
+    if (t.sobol == nullptr) {
+        size_t sb = rb_sobol_table_end - rb_sobol_table_begin;
+        size_t lb = rb_ltc_table_end - rb_ltc_table_begin;
+        RB_CUDA_OK(cudaMalloc(&t.sobol, sb));
+        RB_CUDA_OK(cudaMemcpy(t.sobol, rb_sobol_table_begin, sb, cudaMemcpyHostToDevice));
+        RB_CUDA_OK(cudaMalloc(&t.ltc, lb));
+        RB_CUDA_OK(cudaMemcpy(t.ltc, rb_ltc_table_begin, lb, cudaMemcpyHostToDevice));
+        t.sobol_dims = (int)(sb / (52 * sizeof(unsigned long long)));
+    }
+    out = t;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+static double lookat_d[16];
+static void host_look_at(const float* pos, const float* look, const float* up, double* m) {
+    auto norm = [](double* v) {
+        double l = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (l > 0) { v[0] /= l; v[1] /= l; v[2] /= l; } else { v[0] = v[1] = v[2] = 0; }
+    };
+    auto crs = [](const double* a, const double* b, double* c) {
+        c[0] = a[1] * b[2] - a[2] * b[1];
+        c[1] = a[2] * b[0] - a[0] * b[2];
+        c[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    double d[3] = {(double)look[0] - pos[0], (double)look[1] - pos[1], (double)look[2] - pos[2]};
+    norm(d);
+    double u[3] = {up[0], up[1], up[2]};
+    norm(u);
+    double r[3];
+    crs(d, u, r);
+    norm(r);
+    double nu[3];
+    crs(r, d, nu);
+    norm(nu);
+    double out[16] = {r[0], nu[0], d[0], pos[0], r[1], nu[1], d[1], pos[1], r[2], nu[2], d[2], pos[2], 0, 0, 0, 1};
+    memcpy(m, out, sizeof(out));
+    (void)lookat_d;
+}
+static void host_inverse4(const double* m, double* o) {
+    M4 a;
+    // use a double Gauss-Jordan elimination
+    double A[4][8];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            A[i][j] = m[4 * i + j];
+            A[i][4 + j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int c = 0; c < 4; c++) {
+        int piv = c;
+        for (int r = c + 1; r < 4; r++)
+            if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+        for (int k = 0; k < 8; k++) std::swap(A[c][k], A[piv][k]);
+        double d = A[c][c];
+        for (int k = 0; k < 8; k++) A[c][k] /= d;
+        for (int r = 0; r < 4; r++)
+            if (r != c) {
+                double f = A[r][c];
+                for (int k = 0; k < 8; k++) A[r][k] -= f * A[c][k];
+            }
+    }
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) o[4 * i + j] = A[i][4 + j];
+    (void)a;
+}
+
+extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
+    if (!desc || !out) {
+        rb_set_error("rb_scene_create: null argument");
+        return 1;
+    }
+    *out = nullptr;
+    if (!desc->use_gpu) {
+        rb_set_error("rb_scene_create: use_gpu == 0 requested, but redner_b200 has no CPU path (CUDA sm_100a only)");
+        return 1;
+    }
+    if (desc->envmap != nullptr) {
+        rb_set_error("rb_scene_create: environment maps are not implemented yet (SURVEY.md section 2 row 13, second wave)");
+        return 1;
+    }
+    const rb_camera& c = desc->camera;
+    if (c.camera_type != RB_CAMERA_PERSPECTIVE && c.camera_type != RB_CAMERA_ORTHOGRAPHIC) {
+        rb_set_error("rb_scene_create: only perspective / orthographic cameras are implemented (fisheye, panorama: second wave)");
+        return 1;
+    }
+    if (c.has_distortion) {
+        rb_set_error("rb_scene_create: camera distortion parameters are not implemented yet (second wave)");
+        return 1;
+    }
+    int count = 0;
+    RB_CUDA_OK(cudaGetDeviceCount(&count));
+    if (count <= 0) {
+        rb_set_error("rb_scene_create: no CUDA device visible; redner_b200 has no CPU fallback");
+        return 1;
+    }
+    int prev = 0;
+    RB_CUDA_OK(cudaGetDevice(&prev));
+    int device = desc->gpu_index >= 0 ? desc->gpu_index : prev;
+    RB_CUDA_OK(cudaSetDevice(device));
+    rb_scene* sc = new rb_scene();
+    sc->device = device;
+    sc->cam = c;
+    cudaStream_t stream = 0;
+    auto fail = [&]() {
+        rb_scene_destroy(sc);
+        cudaSetDevice(prev);
+        return 1;
+    };
+    // camera (double copies, src/camera.h:44-55)
+    DevCamera& dc = sc->dev.cam;
+    memset(&sc->dev, 0, sizeof(DevScene));
+    dc.width = c.width;
+    dc.height = c.height;
+    dc.use_look_at = c.use_look_at;
+    for (int i = 0; i < 3; i++) {
+        dc.position[i] = c.position[i];
+        dc.look[i] = c.look[i];
+        dc.up[i] = c.up[i];
+    }
+    if (c.use_look_at) {
+        host_look_at(c.position, c.look, c.up, dc.c2w);
+        host_inverse4(dc.c2w, dc.w2c);
+    } else {
+        for (int i = 0; i < 16; i++) {
+            dc.c2w[i] = c.cam_to_world[i];
+            dc.w2c[i] = c.world_to_cam[i];
+        }
+    }
+    for (int i = 0; i < 9; i++) {
+        dc.intr_inv[i] = c.intrinsic_mat_inv[i];
+        dc.intr[i] = c.intrinsic_mat[i];
+    }
+    dc.clip_near = c.clip_near;
+    dc.type = c.camera_type;
+    dc.vp_beg[0] = c.viewport_beg[0];
+    dc.vp_beg[1] = c.viewport_beg[1];
+    dc.vp_end[0] = c.viewport_end[0];
+    dc.vp_end[1] = c.viewport_end[1];
+
+    sc->shapes.assign(desc->shapes, desc->shapes + desc->num_shapes);
+    sc->materials.assign(desc->materials, desc->materials + desc->num_materials);
+    for (int l = 0; l < desc->num_lights; l++) {
+        DevLight dl;
+        dl.shape_id = desc->lights[l].shape_id;
+        for (int k = 0; k < 3; k++) dl.intensity[k] = desc->lights[l].intensity[k];
+        dl.two_sided = desc->lights[l].two_sided;
+        dl.directly_visible = desc->lights[l].directly_visible;
+        if (dl.shape_id < 0 || dl.shape_id >= desc->num_shapes) {
+            rb_set_error("rb_scene_create: area light refers to an invalid shape");
+            return fail();
+        }
+        sc->lights.push_back(dl);
+    }
+    for (int s = 0; s < desc->num_shapes; s++) {
+        const rb_shape& sh = sc->shapes[s];
+        if (sh.material_id < 0 || sh.material_id >= desc->num_materials) {
+            rb_set_error("rb_scene_create: shape refers to an invalid material");
+            return fail();
+        }
+        if (sh.vertices == nullptr || sh.indices == nullptr) {
+            rb_set_error("rb_scene_create: shape without vertices / indices");
+            return fail();
+        }
+    }
+    sc->max_generic_texture_dimension = 0;
+    for (const rb_material& m : sc->materials)
+        if (m.generic_texture.num_levels > 0) sc->max_generic_texture_dimension = std::max(sc->max_generic_texture_dimension, m.generic_texture.channels);
+
+    rb_shape* d_shapes;
+    rb_material* d_materials;
+    if (dev_upload(sc, &d_shapes, sc->shapes.data(), sc->shapes.size(), stream) ||
+        dev_upload(sc, &d_materials, sc->materials.data(), sc->materials.size(), stream))
+        return fail();
+    sc->dev.shapes = d_shapes;
+    sc->dev.num_shapes = (int)sc->shapes.size();
+    sc->dev.materials = d_materials;
+    sc->dev.num_materials = (int)sc->materials.size();
+    sc->dev.use_primary_edge = desc->use_primary_edge_sampling;
+    sc->dev.use_secondary_edge = desc->use_secondary_edge_sampling;
+    DeviceTables tabs;
+    if (get_tables(device, tabs)) return fail();
+    sc->dev.sobol_matrices = tabs.sobol;
+    sc->dev.sobol_dims = tabs.sobol_dims;
+    sc->dev.ltc_table = tabs.ltc;
+    sc->dev.edge_nodes = nullptr;
+    sc->dev.edge_root_cs = sc->dev.edge_root_ncs = -1;
+
+    auto t0 = std::chrono::high_resolution_clock::now();
+    if (rb_build_bvh(sc, stream)) return fail();
+    auto t1 = std::chrono::high_resolution_clock::now();
+    // host mirrors (lights need serial double CDFs; edges need topology + positions)
+    bool need_edges = sc->dev.use_primary_edge || sc->dev.use_secondary_edge;
+    auto& meshes = host_meshes(sc);
+    meshes.assign(sc->shapes.size(), HostMesh());
+    std::vector<char> need(sc->shapes.size(), need_edges ? 1 : 0);
+    for (const DevLight& l : sc->lights) need[l.shape_id] = 1;
+    for (size_t s = 0; s < sc->shapes.size(); s++)
+        if (need[s] && fetch_mesh(sc->shapes[s], meshes[s], false, stream)) return fail();
+    if (cudaStreamSynchronize(stream) != cudaSuccess) {
+        rb_set_error("rb_scene_create: device-to-host geometry copy failed (are the shape buffers device pointers?)");
+        return fail();
+    }
+    if (rb_build_lights(sc, stream)) return fail();
+    auto t2 = std::chrono::high_resolution_clock::now();
+    if (rb_build_edges(sc, stream)) return fail();
+    auto t3 = std::chrono::high_resolution_clock::now();
+    sc->build_ms_bvh = std::chrono::duration<float, std::milli>(t1 - t0).count();
+    sc->build_ms_lights = std::chrono::duration<float, std::milli>(t2 - t1).count();
+    sc->build_ms_edges = std::chrono::duration<float, std::milli>(t3 - t2).count();
+    meshes.clear();
+    if (cudaStreamSynchronize(stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        rb_set_error("rb_scene_create: scene build kernels failed");
+        return fail();
+    }
+    cudaSetDevice(prev);
+    *out = sc;
+    return 0;
+}
+
+extern "C" void rb_scene_destroy(rb_scene* sc) {
+    if (!sc) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(sc->device);
+    for (void* p : sc->allocs) cudaFreeAsync(p, 0);
+    cudaSetDevice(prev);
+    delete sc;
+}
+
+extern "C" int rb_scene_max_generic_texture_dimension(const rb_scene* sc) { return sc ? sc->max_generic_texture_dimension : 0; }
+
+extern "C" int rb_scene_set_partition(rb_scene* sc, int part, int num_parts, int rows_per_stripe) {
+    if (!sc || num_parts < 1 || part < 0 || part >= num_parts || rows_per_stripe < 1) {
+        rb_set_error("rb_scene_set_partition: invalid arguments");
+        return 1;
+    }
+    sc->part = part;
+    sc->num_parts = num_parts;
+    sc->rows_per_stripe = rows_per_stripe;
+    return 0;
+}
+
+extern "C" int rb_scene_last_stats(const rb_scene* sc, int* launches, float* ms) {
+    if (!sc) return 1;
+    if (launches) *launches = sc->last_launches;
+    if (ms) *ms = sc->last_kernel_ms;
+    return 0;
+}
+
+// compute_num_channels, src/channels.cpp:42-113
+extern "C" int rb_compute_num_channels(const int* channels, int n, int max_generic) {
+    int total = 0;
+    for (int i = 0; i < n; i++) {
+        switch (channels[i]) {
+            case RB_CH_RADIANCE: case RB_CH_POSITION: case RB_CH_GEOMETRY_NORMAL: case RB_CH_SHADING_NORMAL:
+            case RB_CH_DIFFUSE_REFLECTANCE: case RB_CH_SPECULAR_REFLECTANCE: case RB_CH_VERTEX_COLOR:
+                total += 3;
+                break;
+            case RB_CH_ALPHA: case RB_CH_DEPTH: case RB_CH_ROUGHNESS: case RB_CH_SHAPE_ID: case RB_CH_TRIANGLE_ID: case RB_CH_MATERIAL_ID:
+                total += 1;
+                break;
+            case RB_CH_UV: case RB_CH_BARYCENTRIC:
+                total += 2;
+                break;
+            case RB_CH_GENERIC_TEXTURE:
+                total += max_generic;
+                break;
+            default:
+                return -1;
+        }
+    }
+    return total;
+}

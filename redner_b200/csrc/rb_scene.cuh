@@ -1,0 +1,50 @@
+// Host-side scene object behind the C ABI (rb_scene).  Mirrors what Scene::Scene builds in the reference
+// (src/scene.cpp:63-307) with B200-native replacements: GPU LBVH instead of Embree/OptiX Prime, stream-ordered
+// pool allocations instead of cudaMallocManaged buffers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "rb_types.cuh"
+
+struct rb_scene {
+    int device = 0;
+    DevScene dev;   // passed by value to kernels
+    rb_camera cam;  // host copy of the descriptor camera
+    std::vector<void*> allocs; // device allocations owned by the scene
+    std::vector<rb_shape> shapes;
+    std::vector<rb_material> materials;
+    std::vector<DevLight> lights;
+    int max_generic_texture_dimension = 0;
+    int has_envmap = 0;
+    // partition (multi-GPU)
+    int part = 0, num_parts = 1, rows_per_stripe = 16;
+    // stats of the last render
+    int last_launches = 0;
+    float last_kernel_ms = 0.f;
+    // scene-build timings (ms, host clock) for reporting
+    float build_ms_bvh = 0.f, build_ms_lights = 0.f, build_ms_edges = 0.f;
+};
+
+void rb_set_error(const std::string& msg);
+#define RB_CUDA_OK(expr)                                                                                       \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) {                                                                               \
+            rb_set_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" +      \
+                         std::to_string(__LINE__) + " (" #expr ")");                                           \
+            return 1;                                                                                          \
+        }                                                                                                      \
+    } while (0)
+
+// tables embedded into the shared object (rb_tables.cpp)
+extern "C" const unsigned char rb_sobol_table_begin[];
+extern "C" const unsigned char rb_sobol_table_end[];
+extern "C" const unsigned char rb_ltc_table_begin[];
+extern "C" const unsigned char rb_ltc_table_end[];
+
+int rb_build_bvh(rb_scene* sc, cudaStream_t stream);
+int rb_build_lights(rb_scene* sc, cudaStream_t stream);
+int rb_build_edges(rb_scene* sc, cudaStream_t stream);

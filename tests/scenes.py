@@ -1,0 +1,125 @@
+"""Seeded synthetic scenes shared by the parity tests, the golden-vector generator and bench.py.
+
+Geometry follows the reference's own test scripts:
+  C1  tests/test_single_triangle.py:17-90      one grey triangle + quad light, 256x256, max_bounces 1
+  C2  tests/test_shadow_blocker.py:11-59       floor + blocker + small light (geometry), 512x512, max_bounces 1
+plus small procedural scenes (`glossy_room`, `sphere_box`) that exercise the specular lobe, shading normals, uv /
+textures and multi-bounce paths without needing mesh files.
+"""
+import math
+
+import torch
+
+from redner_b200 import api
+
+
+def _t(x, device, dtype=torch.float32, grad=False):
+    t = torch.tensor(x, dtype=dtype, device=device)
+    if grad:
+        t.requires_grad_(True)
+    return t
+
+
+def single_triangle(device, resolution=(256, 256), grad=True):
+    cam = api.Camera(position=torch.tensor([0.0, 0.0, -5.0]), look_at=torch.tensor([0.0, 0.0, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
+                     fov=torch.tensor([45.0]), clip_near=1e-2, resolution=resolution)
+    if grad:
+        cam.position.requires_grad_(True)
+    mat_grey = api.Material(diffuse_reflectance=_t([0.5, 0.5, 0.5], device, grad=grad))
+    tri = api.Shape(_t([[-2.0, 1.5, 0.3], [0.9, 1.2, -0.3], [-0.4, -1.4, 0.2]], device, grad=grad), _t([[0, 1, 2]], device, torch.int32), 0)
+    light = api.Shape(_t([[-1.0, -1.0, -7.0], [1.0, -1.0, -7.0], [-1.0, 1.0, -7.0], [1.0, 1.0, -7.0]], device),
+                      _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 0)
+    al = api.AreaLight(1, torch.tensor([20.0, 20.0, 20.0], requires_grad=grad))
+    return api.Scene(cam, [tri, light], [mat_grey], [al])
+
+
+def shadow_blocker(device, resolution=(512, 512), grad=True):
+    cam = api.Camera(position=torch.tensor([0.0, 2.0, -5.0]), look_at=torch.tensor([0.0, 0.0, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
+                     fov=torch.tensor([45.0]), clip_near=1e-2, resolution=resolution)
+    mat_grey = api.Material(diffuse_reflectance=_t([0.5, 0.5, 0.5], device, grad=grad))
+    mat_black = api.Material(diffuse_reflectance=_t([0.0, 0.0, 0.0], device))
+    floor = api.Shape(_t([[-2.0, 0.0, -2.0], [-2.0, 0.0, 2.0], [2.0, 0.0, -2.0], [2.0, 0.0, 2.0]], device),
+                      _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 0)
+    blocker = api.Shape(_t([[-0.2, 3.5, -0.8], [-0.8, 3.0, 0.3], [0.4, 2.8, -0.8], [0.3, 3.2, 1.0]], device, grad=grad),
+                        _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 0)
+    light = api.Shape(_t([[-0.1, 5, -0.1], [-0.1, 5, 0.1], [0.1, 5, -0.1], [0.1, 5, 0.1]], device),
+                      _t([[0, 2, 1], [1, 2, 3]], device, torch.int32), 1)
+    al = api.AreaLight(2, torch.tensor([1000.0, 1000.0, 1000.0], requires_grad=grad))
+    return api.Scene(cam, [floor, blocker, light], [mat_grey, mat_black], [al])
+
+
+def uv_sphere(device, radius, center, n_theta=12, n_phi=24, grad=False):
+    """Closed sphere with per-vertex normals and uvs (exercises shading normals + uv derivatives)."""
+    verts, uvs, normals, idx = [], [], [], []
+    for i in range(n_theta + 1):
+        th = math.pi * i / n_theta
+        for j in range(n_phi + 1):
+            ph = 2 * math.pi * j / n_phi
+            n = (math.sin(th) * math.cos(ph), math.cos(th), math.sin(th) * math.sin(ph))
+            verts.append([center[0] + radius * n[0], center[1] + radius * n[1], center[2] + radius * n[2]])
+            normals.append(list(n))
+            uvs.append([j / n_phi, i / n_theta])
+    for i in range(n_theta):
+        for j in range(n_phi):
+            a = i * (n_phi + 1) + j
+            b = a + n_phi + 1
+            if i != 0:
+                idx.append([a, a + 1, b])
+            if i != n_theta - 1:
+                idx.append([a + 1, b + 1, b])
+    return (_t(verts, device, grad=grad), _t(idx, device, torch.int32), _t(uvs, device), _t(normals, device))
+
+
+def glossy_room(device, resolution=(128, 128), grad=True, textured=True):
+    """Open box (floor, back wall, side wall) with a glossy textured floor, a Phong-shaded sphere and two area lights."""
+    g = torch.Generator().manual_seed(7)
+    cam = api.Camera(position=torch.tensor([0.3, 1.4, -4.5]), look_at=torch.tensor([0.0, 0.6, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
+                     fov=torch.tensor([40.0]), clip_near=1e-2, resolution=resolution)
+    if textured:
+        tex = (0.2 + 0.6 * torch.rand(16, 16, 3, generator=g)).to(device)
+        rough = (0.05 + 0.3 * torch.rand(16, 16, 1, generator=g)).to(device)
+    else:
+        tex = torch.tensor([0.45, 0.4, 0.35], device=device)
+        rough = torch.tensor([0.15], device=device)
+    if grad:
+        tex.requires_grad_(True)
+        rough.requires_grad_(True)
+    m_floor = api.Material(diffuse_reflectance=api.Texture(tex, torch.tensor([2.0, 2.0], device=device)),
+                           specular_reflectance=_t([0.3, 0.3, 0.3], device, grad=grad), roughness=api.Texture(rough, torch.tensor([2.0, 2.0], device=device)))
+    m_wall = api.Material(diffuse_reflectance=_t([0.6, 0.3, 0.25], device, grad=grad), two_sided=True)
+    m_ball = api.Material(diffuse_reflectance=_t([0.2, 0.35, 0.6], device, grad=grad), specular_reflectance=_t([0.5, 0.5, 0.5], device, grad=grad),
+                          roughness=_t([0.2], device, grad=grad))
+    m_light = api.Material(diffuse_reflectance=_t([0.0, 0.0, 0.0], device))
+    floor = api.Shape(_t([[-2.5, 0.0, -2.5], [-2.5, 0.0, 2.5], [2.5, 0.0, -2.5], [2.5, 0.0, 2.5]], device),
+                      _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 0, uvs=_t([[0.0, 0.0], [0.0, 1.0], [1.0, 0.0], [1.0, 1.0]], device))
+    back = api.Shape(_t([[-2.5, 0.0, 2.5], [-2.5, 3.0, 2.5], [2.5, 0.0, 2.5], [2.5, 3.0, 2.5]], device),
+                     _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 1)
+    side = api.Shape(_t([[-2.5, 0.0, -2.5], [-2.5, 3.0, -2.5], [-2.5, 0.0, 2.5], [-2.5, 3.0, 2.5]], device),
+                     _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 1)
+    v, i, uv, n = uv_sphere(device, 0.7, (0.2, 0.7, 0.3), grad=grad)
+    ball = api.Shape(v, i, 2, uvs=uv, normals=n)
+    l1 = api.Shape(_t([[-0.6, 2.9, -0.6], [-0.6, 2.9, 0.6], [0.6, 2.9, -0.6], [0.6, 2.9, 0.6]], device),
+                   _t([[0, 2, 1], [1, 2, 3]], device, torch.int32), 3)
+    l2 = api.Shape(_t([[1.8, 0.8, -1.5], [1.8, 1.6, -1.5], [2.2, 0.8, -0.9]], device), _t([[0, 1, 2]], device, torch.int32), 3)
+    lights = [api.AreaLight(4, torch.tensor([25.0, 24.0, 22.0], requires_grad=grad)),
+              api.AreaLight(5, torch.tensor([8.0, 10.0, 14.0], requires_grad=grad), two_sided=True)]
+    return api.Scene(cam, [floor, back, side, ball, l1, l2], [m_floor, m_wall, m_ball, m_light], lights)
+
+
+def random_soup(device, num_tris=2000, resolution=(256, 256), seed=3):
+    """Random triangle soup under one light: BVH / traversal stress (many shapes' worth of edges, deep tree)."""
+    g = torch.Generator().manual_seed(seed)
+    c = (torch.rand(num_tris, 1, 3, generator=g) - 0.5) * torch.tensor([4.0, 2.5, 3.0]) + torch.tensor([0.0, 1.3, 0.5])
+    v = (c + 0.25 * (torch.rand(num_tris, 3, 3, generator=g) - 0.5)).reshape(-1, 3).contiguous()
+    i = torch.arange(3 * num_tris, dtype=torch.int32).reshape(-1, 3).contiguous()
+    cam = api.Camera(position=torch.tensor([0.0, 1.5, -6.0]), look_at=torch.tensor([0.0, 1.0, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
+                     fov=torch.tensor([45.0]), clip_near=1e-2, resolution=resolution)
+    m = api.Material(diffuse_reflectance=_t([0.6, 0.6, 0.6], device), two_sided=True)
+    m_l = api.Material(diffuse_reflectance=_t([0.0, 0.0, 0.0], device))
+    soup = api.Shape(v.to(device), i.to(device), 0)
+    floor = api.Shape(_t([[-4.0, 0.0, -4.0], [-4.0, 0.0, 4.0], [4.0, 0.0, -4.0], [4.0, 0.0, 4.0]], device), _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 0)
+    light = api.Shape(_t([[-1.0, 4.5, -1.0], [-1.0, 4.5, 1.0], [1.0, 4.5, -1.0], [1.0, 4.5, 1.0]], device), _t([[0, 2, 1], [1, 2, 3]], device, torch.int32), 1)
+    return api.Scene(cam, [soup, floor, light], [m, m_l], [api.AreaLight(2, torch.tensor([30.0, 30.0, 30.0]))])
+
+
+SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room}

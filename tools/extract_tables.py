@@ -22,7 +22,7 @@ import numpy as np
 
 REF = os.environ.get("REDNER_REF", "/root/reference")
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "redner_b200", "data")
-NUM_DIMS = 256  # 256 dims x 52 x 8 B = 106 KB
+NUM_DIMS = 1024  # all 1024 dims x 52 x 8 B = 426 KB
 
 
 def main():
