@@ -139,7 +139,7 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or os.environ.get("REDNER_B200_LIB", LIB_PATH)
+    p = path or LIB_PATH
     if not os.path.exists(p):
         raise OSError("redner_b200: %s not found -- build it with `python -m redner_b200.build` "
                       "(there is no CPU or PyTorch fallback for the render path)" % p)

@@ -7,6 +7,14 @@
 #pragma once
 #include "rb_math.cuh"
 
+#ifdef RB_CPU_EMU
+// host-compiled debug emulator (tools/cpu_emu): single "lane", plain adds
+RB_D void rb_red_add(float* addr, float v) { *addr += v; }
+template <int N>
+RB_D void warp_agg_add(float* addr, const float (&val)[N]) {
+    for (int i = 0; i < N; i++) addr[i] += val[i];
+}
+#else
 RB_D void rb_red_add(float* addr, float v) { atomicAdd(addr, v); }
 
 // Combine `n` consecutive floats (n <= 9) across the lanes of the current convergence group that
@@ -47,6 +55,7 @@ RB_D void warp_agg_add(float* addr, const float (&val)[N]) {
             if (v[i] != 0.f) rb_red_add(addr + i, v[i]);
     }
 }
+#endif // RB_CPU_EMU
 RB_D void agg_add3(float* addr, V3 v) {
     float a[3] = {(float)v.x, (float)v.y, (float)v.z};
     warp_agg_add<3>(addr, a);

@@ -10,6 +10,7 @@
 // A warp owns 32/L pixels with L lanes per pixel (L = min(32, 2^floor(log2 spp))); lanes of a pixel are its
 // samples, so rays of a warp are coherent in the BVH, the pixel is reduced with shuffles and written by one lane
 // without atomics (deterministic image), and gradient atomics are aggregated per warp before they reach L2.
+// The per-sample logic itself lives in rb_render.cuh.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -17,23 +18,10 @@
 #include <string>
 #include <vector>
 
-#include "rb_edge.cuh"
-#include "rb_path.cuh"
+#include "rb_render.cuh"
 #include "rb_scene.cuh"
 
 #define RB_BLOCK 128
-
-struct KernelArgs {
-    RenderParams rp;
-    int lanes_per_pixel; // L
-    int owned_rows;      // rows of the viewport this device renders
-    float* image;        // forward
-    const float* d_image;
-    float* screen_grad;
-    DevDScene ds;
-    VertexRec* records; // [threads][max_bounces + 1]
-    int rec_per_thread;
-};
 
 // j-th owned row -> viewport row, for the round-robin stripe partition
 RB_D int owned_row_to_row(const RenderParams& rp, int j) {
@@ -50,7 +38,7 @@ static int count_owned_rows(int H, int part, int num_parts, int rps) {
 struct WorkItem {
     bool valid;
     int pixel;    // viewport-relative pixel id (y * vp_w + x)
-    int px, py;   // absolute pixel coordinates
+    int px, py;   // viewport-relative pixel coordinates
     int sample_lane;
 };
 RB_D WorkItem warp_work(const RenderParams& rp, int L, int owned_rows, long long group) {
@@ -69,22 +57,6 @@ RB_D WorkItem warp_work(const RenderParams& rp, int L, int owned_rows, long long
     w.py = y;
     return w;
 }
-RB_D unsigned long long main_draws_per_sample(const RenderParams& rp) {
-    return (unsigned long long)((rp.sample_pixel_center ? 0 : 2) + 7 * rp.max_bounces);
-}
-
-// Camera sample -> primary ray (viewport offset applied), src/camera.cpp:8-43.
-RB_D void primary_ray_for(const DevScene& sc, const RenderParams& rp, const WorkItem& w, Sampler& smp, double& sx, double& sy, Ray& ray,
-                          RayDiff& rd) {
-    double jx = 0.5, jy = 0.5;
-    if (!rp.sample_pixel_center) {
-        jx = smp.next();
-        jy = smp.next();
-    }
-    sx = (double(w.px + sc.cam.vp_beg[0]) + jx) / double(sc.cam.width);
-    sy = (double(w.py + sc.cam.vp_beg[1]) + jy) / double(sc.cam.height);
-    cam_primary_ray(sc.cam, sx, sy, ray, rd);
-}
 
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(RB_BLOCK) k_forward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
@@ -96,29 +68,12 @@ __global__ void __launch_bounds__(RB_BLOCK) k_forward(const __grid_constant__ De
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int nb = (rp.spp + L - 1) / L;
-    const Real weight = Real(1) / Real(rp.spp);
     for (long long g = warp; g < groups; g += nwarps) {
         WorkItem w = warp_work(rp, L, ka.owned_rows, g);
         V3 acc = zero3();
         for (int b = 0; b < nb; b++) {
             int s = b * L + w.sample_lane;
-            if (w.valid && s < rp.spp) {
-                Sampler smp;
-                smp.init(rp.sampler_type, rp.seed, w.pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
-                double sx, sy;
-                Ray ray;
-                RayDiff rd;
-                primary_ray_for(sc, rp, w, smp, sx, sy, ray, rd);
-                Isect is = no_isect();
-                if (closest_hit(sc, ray, is)) {
-                    RayDiff rd_after;
-                    SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
-                    V3 L0 = hit_emission(sc, is, sp, -ray.dir);
-                    acc += weight * L0;
-                    V3 Lb = trace_bounces<false>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, nullptr, 0, nullptr);
-                    acc += weight * Lb;
-                }
-            }
+            if (w.valid && s < rp.spp) acc += forward_sample(sc, rp, w.pixel, w.px, w.py, s);
         }
         for (int off = L >> 1; off > 0; off >>= 1) {
             acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
@@ -153,9 +108,7 @@ __global__ void __launch_bounds__(RB_BLOCK) k_backward(const __grid_constant__ D
     CamAcc cam_acc;
     cam_acc.base = cam_smem + threadIdx.x;
     cam_acc.stride = RB_BLOCK;
-
     const RenderParams& rp = ka.rp;
-    const DevDScene& ds = ka.ds;
     const int L = ka.lanes_per_pixel;
     const int P = 32 / L;
     long long n_px = (long long)ka.owned_rows * rp.vp_w;
@@ -164,122 +117,19 @@ __global__ void __launch_bounds__(RB_BLOCK) k_backward(const __grid_constant__ D
     long long warp = gtid >> 5;
     long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int nb = (rp.spp + L - 1) / L;
-    const Real weight = Real(1) / Real(rp.spp);
     VertexRec* recs = ka.records + (size_t)gtid * ka.rec_per_thread;
     for (long long g = warp; g < groups; g += nwarps) {
         WorkItem w = warp_work(rp, L, ka.owned_rows, g);
         for (int b = 0; b < nb; b++) {
             int s = b * L + w.sample_lane;
-            if (!(w.valid && s < rp.spp)) continue;
-            Sampler smp;
-            smp.init(rp.sampler_type, rp.seed, w.pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
-            double sx, sy;
-            Ray ray;
-            RayDiff rd;
-            primary_ray_for(sc, rp, w, smp, sx, sy, ray, rd);
-            Isect is = no_isect();
-            if (!closest_hit(sc, ray, is)) continue;
-            const float* dpx = ka.d_image + (size_t)rp.nd * w.pixel + rp.rad_dim;
-            V3 d_contrib = weight * mk3(dpx[0], dpx[1], dpx[2]);
-            int nrec = 0;
-            trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, recs, 1, &nrec);
-            // reverse sweep over the interior vertices (src/pathtracer.cpp:431-714)
-            VertexAdjoint adj = zero_vertex_adjoint();
-            for (int d = nrec - 1; d >= 0; d--) {
-                VertexRec cur = recs[d];
-                VertexRec nxt = recs[d + 1];
-                adj = d_vertex(sc, ds, cur, &nxt, d_contrib, adj);
-            }
-            // first vertex: emission adjoint (src/primary_contribution.cpp:449-466) ...
-            RayDiff rd_after;
-            SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
-            {
-                const rb_shape& shape = sc.shapes[is.shape_id];
-                V3 wi = -ray.dir;
-                if (shape.light_id >= 0 && dot(wi, sp.shading_frame.n) > 0) {
-                    const DevLight& light = sc.lights[shape.light_id];
-                    if (light.directly_visible) agg_add3(ds.light_intensity[shape.light_id], d_contrib);
-                }
-            }
-            // ... and the hit itself back to the mesh and the camera (src/primary_intersection.cpp:5-130)
-            V3 d_vp[3] = {zero3(), zero3(), zero3()}, d_vn[3] = {zero3(), zero3(), zero3()}, d_vc[3] = {zero3(), zero3(), zero3()};
-            V2 d_vuv[3] = {zero2(), zero2(), zero2()};
-            DRay d_ray = adj.d_ray;
-            RayDiff d_prd = zero_raydiff();
-            d_make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, adj.d_point, zero_raydiff(), d_ray, d_prd, d_vp, d_vn, d_vuv, d_vc);
-            scatter_vertex_grads(sc, ds, is, d_vp, d_vn, d_vuv, d_vc);
-            const Real delta = Real(1e-3);
-            Real psx = Real(0.5) / sc.cam.width, psy = Real(0.5) / sc.cam.height;
-            DRay d_ray_dx, d_ray_dy;
-            d_ray_dx.org = d_prd.org_dx * (psx / delta);
-            d_ray_dx.dir = d_prd.dir_dx * (psx / delta);
-            d_ray_dy.org = d_prd.org_dy * (psy / delta);
-            d_ray_dy.dir = d_prd.dir_dy * (psy / delta);
-            d_ray.org += (d_prd.org_dx * (-psx) + d_prd.org_dy * (-psy)) / delta;
-            d_ray.dir += (d_prd.dir_dx * (-psx) + d_prd.dir_dy * (-psy)) / delta;
-            V2 d_screen = zero2();
-            V2* d_screen_ptr = ka.screen_grad ? &d_screen : nullptr;
-            d_cam_sample_primary(sc.cam, (Real)sx, (Real)sy, d_ray, cam_acc, d_screen_ptr);
-            d_cam_sample_primary(sc.cam, (Real)sx + delta, (Real)sy, d_ray_dx, cam_acc, d_screen_ptr);
-            d_cam_sample_primary(sc.cam, (Real)sx, (Real)sy + delta, d_ray_dy, cam_acc, d_screen_ptr);
-            if (ka.screen_grad) {
-                atomicAdd(&ka.screen_grad[2 * (size_t)w.pixel + 0], (float)d_screen.x);
-                atomicAdd(&ka.screen_grad[2 * (size_t)w.pixel + 1], (float)d_screen.y);
-            }
+            if (w.valid && s < rp.spp) backward_sample(sc, ka, w.pixel, w.px, w.py, s, recs, cam_acc);
         }
     }
-    block_reduce_camera(cam_smem, ds.cam_accum);
+    block_reduce_camera(cam_smem, ka.ds.cam_accum);
 }
 
 // ------------------------------------------------------------------------------------------------ primary edges
-// Projection of an edge in double (the +-1e-6 offsets across the edge need more than fp32 screen coordinates).
-struct D2 {
-    double x, y;
-};
-RB_D D3 w2c_point(const DevCamera& cam, D3 p) {
-    const double* W = cam.w2c;
-    double x = W[0] * p.x + W[1] * p.y + W[2] * p.z + W[3];
-    double y = W[4] * p.x + W[5] * p.y + W[6] * p.z + W[7];
-    double z = W[8] * p.x + W[9] * p.y + W[10] * p.z + W[11];
-    double w = W[12] * p.x + W[13] * p.y + W[14] * p.z + W[15];
-    double iw = 1.0 / w;
-    return d3(x * iw, y * iw, z * iw);
-}
-RB_D D2 cam_to_screen_d(const DevCamera& cam, D3 p) {
-    const double* K = cam.intr;
-    double aspect = double(cam.width) / double(cam.height);
-    double ix = K[0] * p.x + K[1] * p.y + K[2] * p.z, iy = K[3] * p.x + K[4] * p.y + K[5] * p.z, iz = K[6] * p.x + K[7] * p.y + K[8] * p.z;
-    D2 r;
-    if (cam.type == RB_CAMERA_PERSPECTIVE) {
-        r.x = (ix / iz + 1.0) * 0.5;
-        r.y = (-(iy / iz) * aspect + 1.0) * 0.5;
-    } else {
-        r.x = (ix + 1.0) * 0.5;
-        r.y = (-iy * aspect + 1.0) * 0.5;
-    }
-    return r;
-}
-RB_D bool cam_project_d(const DevCamera& cam, D3 p0, D3 p1, D2& q0, D2& q1) {
-    D3 a = w2c_point(cam, p0), b = w2c_point(cam, p1);
-    double cn = cam.clip_near;
-    if (a.z < cn && b.z < cn) return false;
-    if (a.z < cn) {
-        D3 dir = d3(a.x - b.x, a.y - b.y, a.z - b.z);
-        double t = -(b.z - cn) / dir.z;
-        a = d3(b.x + t * dir.x, b.y + t * dir.y, b.z + t * dir.z);
-    } else if (b.z < cn) {
-        D3 dir = d3(b.x - a.x, b.y - a.y, b.z - a.z);
-        double t = -(a.z - cn) / dir.z;
-        b = d3(a.x + t * dir.x, a.y + t * dir.y, a.z + t * dir.z);
-    }
-    q0 = cam_to_screen_d(cam, a);
-    q1 = cam_to_screen_d(cam, b);
-    return true;
-}
-RB_D unsigned long long edge_draws_per_sample(const RenderParams& rp) { return (unsigned long long)(2 + 7 * rp.max_bounces); }
-
-// One thread per (edge sample i, spp sample s).  Reference: primary_edge_sampler src/edge.cpp:385-625, the sub-path
-// loop src/pathtracer.cpp:766-934 and primary_edge_derivatives_computer src/edge.cpp:700-783.
+// One thread per (edge sample i, spp sample s).
 __global__ void __launch_bounds__(RB_BLOCK) k_primary_edge(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka, int dim_base) {
     __shared__ float cam_smem[RB_CAM_ACC * RB_BLOCK];
     for (int k = 0; k < RB_CAM_ACC; k++) cam_smem[k * RB_BLOCK + threadIdx.x] = 0.f;
@@ -287,129 +137,22 @@ __global__ void __launch_bounds__(RB_BLOCK) k_primary_edge(const __grid_constant
     cam_acc.base = cam_smem + threadIdx.x;
     cam_acc.stride = RB_BLOCK;
     const RenderParams& rp = ka.rp;
-    const DevDScene& ds = ka.ds;
     const long long n_px = (long long)rp.vp_w * rp.vp_h;
     // samples of this device: i with i % num_parts == part
     const long long n_mine = (n_px - rp.part + rp.num_parts - 1) / rp.num_parts;
     const long long total = n_mine * rp.spp;
-    const Real weight = Real(1) / Real(rp.spp);
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        // consecutive threads share the edge-sample index and differ in the spp sample -> coherent edge picks per warp
+        // consecutive threads share the edge-sample index and differ in the spp sample
         long long i = (t / rp.spp) * rp.num_parts + rp.part;
         int s = (int)(t % rp.spp);
-        Sampler smp;
-        smp.init(rp.sampler_type, rp.seed + 131071ULL, (int)i, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * edge_draws_per_sample(rp));
-        smp.dim = dim_base;
-        double e_sel = smp.next(), e_t = smp.next();
-        int edge_id = cdf_pick(sc.prim_edge_cdf, sc.num_edges, e_sel);
-        double pmf = sc.prim_edge_pmf[edge_id];
-        const Edge edge = sc.edges[edge_id];
-        V3 v0 = edge_v0(sc.shapes, edge), v1 = edge_v1(sc.shapes, edge);
-        D2 q0, q1;
-        if (!cam_project_d(sc.cam, d3(v0.x, v0.y, v0.z), d3(v1.x, v1.y, v1.z), q0, q1)) continue;
-        if (pmf <= 0) continue;
-        D2 ept;
-        ept.x = q0.x + e_t * (q1.x - q0.x);
-        ept.y = q0.y + e_t * (q1.y - q0.y);
-        if (!cam_in_screen(sc.cam, mk2((Real)ept.x, (Real)ept.y))) continue;
-        // unit normal of the projected edge: get_normal(normalize(v0_ss - v1_ss)) = (d.y, -d.x)
-        double ddx = q0.x - q1.x, ddy = q0.y - q1.y;
-        double dl = sqrt(ddx * ddx + ddy * ddy);
-        double nx = ddy / dl, ny = -ddx / dl;
-        const double offset = 1e-6;
-        int vp_w = rp.vp_w;
-        int xi = rb_clampi(int(ept.x * sc.cam.width - sc.cam.vp_beg[0]), 0, sc.cam.vp_end[0] - sc.cam.vp_beg[0]);
-        int yi = rb_clampi(int(ept.y * sc.cam.height - sc.cam.vp_beg[1]), 0, sc.cam.vp_end[1] - sc.cam.vp_beg[1]);
-        const float* dpx = ka.d_image + (size_t)rp.nd * ((size_t)yi * vp_w + xi) + rp.rad_dim;
-        V3 d_color = mk3(dpx[0], dpx[1], dpx[2]);
-        V3 wgt = d_color / (Real)pmf;
-        // ray differential of the un-offset ray, shared by both sides (src/edge.cpp:594-608)
-        Ray cray;
-        RayDiff rd;
-        cam_primary_ray(sc.cam, ept.x, ept.y, cray, rd);
-        Real contrib = 0;
-        for (int side = 0; side < 2; side++) {
-            double sgn = side == 0 ? 1.0 : -1.0;
-            D3 o, d;
-            cam_sample_primary(sc.cam, ept.x + sgn * nx * offset, ept.y + sgn * ny * offset, o, d);
-            Ray ray = make_ray(o, d);
-            V3 thr = side == 0 ? wgt : -wgt;
-            Isect is = no_isect();
-            if (!closest_hit(sc, ray, is)) continue;
-            RayDiff rd_after;
-            SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
-            contrib += sum(weight * thr * hit_emission(sc, is, sp, -ray.dir));
-            Sampler sub = smp; // both sides consume the same light / bsdf samples (src/pathtracer.cpp:871-886)
-            V3 Lb = trace_bounces<false>(sc, sub, ray, rd, is, thr, Real(0), 0, rp.max_bounces, nullptr, 0, nullptr);
-            contrib += sum(weight * Lb);
-        }
-        if (contrib == 0) continue;
-        // Eq. 8: gradients of the edge equation w.r.t. the projected end points
-        Real d0x = (Real)(q1.y - ept.y) * contrib, d0y = (Real)(ept.x - q1.x) * contrib;
-        Real d1x = (Real)(ept.y - q0.y) * contrib, d1y = (Real)(q0.x - ept.x) * contrib;
-        V3 d_v0 = zero3(), d_v1 = zero3();
-        d_cam_project(sc.cam, v0, v1, d0x, d0y, d1x, d1y, cam_acc, d_v0, d_v1);
-        float* dv = ds.shapes[edge.shape_id].vertices;
-        if (dv) {
-            agg_add3(dv + 3 * (size_t)edge.v0, d_v0);
-            agg_add3(dv + 3 * (size_t)edge.v1, d_v1);
-        }
-        if (ka.screen_grad) {
-            Real dex = (Real)(q0.y - q1.y) * contrib, dey = (Real)(q1.x - q0.x) * contrib;
-            size_t pix = (size_t)yi * vp_w + xi;
-            atomicAdd(&ka.screen_grad[2 * pix + 0], (float)dex);
-            atomicAdd(&ka.screen_grad[2 * pix + 1], (float)dey);
-        }
+        primary_edge_sample(sc, ka, i, s, dim_base, cam_acc);
     }
-    block_reduce_camera(cam_smem, ds.cam_accum);
+    block_reduce_camera(cam_smem, ka.ds.cam_accum);
 }
 
-// ------------------------------------------------------------------------------------------------ camera finish
-// Turns the reduced matrix gradients into the user-facing camera gradients (one thread; everything is linear in the
-// accumulated matrices): d_project's world_to_cam term (src/camera.h:811-829) and d_look_at_matrix (src/transform.h:29-71).
 __global__ void k_finish_camera(DevCamera cam, const double* acc, rb_dcamera out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double C[4][4], W[4][4], Dw[4][4];
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) {
-            C[i][j] = acc[4 * i + j];
-            Dw[i][j] = acc[16 + 4 * i + j];
-            W[i][j] = cam.w2c[4 * i + j];
-        }
-    // d_cam_to_world += -W^T * d_W * W^T
-    double tmp[4][4];
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) {
-            double s = 0;
-            for (int k = 0; k < 4; k++) s += W[k][i] * Dw[k][j];
-            tmp[i][j] = s;
-        }
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) {
-            double s = 0;
-            for (int k = 0; k < 4; k++) s += tmp[i][k] * W[j][k];
-            C[i][j] -= s;
-        }
-    if (cam.use_look_at) {
-        M4 d_m;
-        for (int i = 0; i < 4; i++)
-            for (int j = 0; j < 4; j++) d_m.m[i][j] = (Real)C[i][j];
-        V3 pos = mk3((Real)cam.position[0], (Real)cam.position[1], (Real)cam.position[2]);
-        V3 look = mk3((Real)cam.look[0], (Real)cam.look[1], (Real)cam.look[2]);
-        V3 up = mk3((Real)cam.up[0], (Real)cam.up[1], (Real)cam.up[2]);
-        V3 d_p = zero3(), d_l = zero3(), d_u = zero3();
-        d_look_at_matrix(pos, look, up, d_m, d_p, d_l, d_u);
-        if (out.position) { out.position[0] += (float)d_p.x; out.position[1] += (float)d_p.y; out.position[2] += (float)d_p.z; }
-        if (out.look) { out.look[0] += (float)d_l.x; out.look[1] += (float)d_l.y; out.look[2] += (float)d_l.z; }
-        if (out.up) { out.up[0] += (float)d_u.x; out.up[1] += (float)d_u.y; out.up[2] += (float)d_u.z; }
-    } else if (out.cam_to_world) {
-        for (int i = 0; i < 4; i++)
-            for (int j = 0; j < 4; j++) out.cam_to_world[4 * i + j] += (float)C[i][j];
-    }
-    if (out.intrinsic_mat_inv)
-        for (int k = 0; k < 9; k++) out.intrinsic_mat_inv[k] += (float)acc[32 + k];
-    if (out.intrinsic_mat)
-        for (int k = 0; k < 9; k++) out.intrinsic_mat[k] += (float)acc[41 + k];
+    finish_camera(cam, acc, out);
 }
 
 // ------------------------------------------------------------------------------------------------ driver

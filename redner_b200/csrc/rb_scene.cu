@@ -10,8 +10,8 @@
 #include <string>
 #include <vector>
 
-#include "rb_edge.cuh"
 #include "rb_scene.cuh"
+#include "rb_scene_host.hpp"
 
 static thread_local std::string g_last_error;
 void rb_set_error(const std::string& msg) { g_last_error = msg; }
@@ -197,7 +197,7 @@ __global__ void k_refit(int T, BVHNode* nodes, const int* parent_inner, const in
         nodes[node].lo_z_hi_z = make_float4(l[2], l[5], r[2], r[5]);
         for (int k = 0; k < 3; k++) {
             inner_box[6 * (size_t)node + k] = fminf(l[k], r[k]);
-            inner_box[6 * (size_t)node + 3 + k] = fmaxf(l[k], r[k]);
+            inner_box[6 * (size_t)node + 3 + k] = fmaxf(l[3 + k], r[3 + k]);
         }
         node = parent_inner[node];
     }
@@ -252,20 +252,16 @@ int rb_build_bvh(rb_scene* sc, cudaStream_t stream) {
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ lights
-// Host mirrors of the geometry (needed for the serial double-precision CDFs the reference builds, and for edges).
-struct HostMesh {
-    std::vector<float> vertices, normals;
-    std::vector<int> indices;
-};
-static int fetch_mesh(const rb_shape& s, HostMesh& m, bool want_normals, cudaStream_t stream) {
+// ------------------------------------------------------------------------------------------------ lights + edges
+// The distributions themselves are computed on the host from mirrors of the (small) light meshes / the topology
+// (rb_scene_host.hpp, shared with the debug emulator); here we only move data.
+static int fetch_mesh(const rb_shape& s, HostMesh& m, cudaStream_t stream) {
     m.vertices.resize(3 * (size_t)s.num_vertices);
     m.indices.resize(3 * (size_t)s.num_triangles);
     if (s.num_vertices > 0)
         RB_CUDA_OK(cudaMemcpyAsync(m.vertices.data(), s.vertices, m.vertices.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
     if (s.num_triangles > 0)
         RB_CUDA_OK(cudaMemcpyAsync(m.indices.data(), s.indices, m.indices.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    (void)want_normals;
     return 0;
 }
 
@@ -280,51 +276,18 @@ int rb_build_lights(rb_scene* sc, cudaStream_t stream) {
     sc->dev.num_lights = L;
     sc->dev.lights = nullptr;
     if (L == 0) return 0;
-    auto& meshes = host_meshes(sc);
-    std::vector<double> pmf(L), cdf(L), areas(L), pool;
-    std::vector<int> offsets(L);
-    double total = 0;
-    for (int l = 0; l < L; l++) {
-        const DevLight& light = sc->lights[l];
-        const HostMesh& m = meshes[light.shape_id];
-        int T = (int)m.indices.size() / 3;
-        offsets[l] = (int)pool.size();
-        std::vector<double> a(T);
-        double sum_area = 0; // serial sum in triangle order == thrust::reduce on the CPP backend (src/scene.cpp:43-45)
-        for (int t = 0; t < T; t++) {
-            const int* id = &m.indices[3 * (size_t)t];
-            double v[3][3];
-            for (int k = 0; k < 3; k++)
-                for (int c = 0; c < 3; c++) v[k][c] = m.vertices[3 * (size_t)id[k] + c];
-            double e1[3] = {v[1][0] - v[0][0], v[1][1] - v[0][1], v[1][2] - v[0][2]};
-            double e2[3] = {v[2][0] - v[0][0], v[2][1] - v[0][1], v[2][2] - v[0][2]};
-            double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
-            a[t] = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
-            sum_area += a[t];
-        }
-        double run = 0;
-        for (int t = 0; t < T; t++) { // exclusive scan, then normalise
-            pool.push_back(run / sum_area);
-            run += a[t];
-        }
-        areas[l] = sum_area;
-        double lum = 0.212671f * (double)light.intensity[0] + 0.715160f * (double)light.intensity[1] + 0.072169f * (double)light.intensity[2];
-        pmf[l] = sum_area * lum * double(M_PI);
-        total += pmf[l];
-    }
-    if (!(total > 0)) {
-        rb_set_error("rb_scene_create: total light importance is not positive (src/scene.cpp:243)");
+    HostLightTables t;
+    std::string err;
+    if (!host_build_lights(sc->lights, host_meshes(sc), t, err)) {
+        rb_set_error(err);
         return 1;
     }
-    for (int l = 0; l < L; l++) pmf[l] /= total;
-    cdf[0] = 0;
-    for (int l = 1; l < L; l++) cdf[l] = cdf[l - 1] + pmf[l - 1];
     DevLight* d_lights;
     double *d_pmf, *d_cdf, *d_areas, *d_pool;
     int* d_off;
-    if (dev_upload(sc, &d_lights, sc->lights.data(), L, stream) || dev_upload(sc, &d_pmf, pmf.data(), L, stream) ||
-        dev_upload(sc, &d_cdf, cdf.data(), L, stream) || dev_upload(sc, &d_areas, areas.data(), L, stream) ||
-        dev_upload(sc, &d_pool, pool.data(), pool.size(), stream) || dev_upload(sc, &d_off, offsets.data(), L, stream))
+    if (dev_upload(sc, &d_lights, sc->lights.data(), L, stream) || dev_upload(sc, &d_pmf, t.pmf.data(), L, stream) ||
+        dev_upload(sc, &d_cdf, t.cdf.data(), L, stream) || dev_upload(sc, &d_areas, t.areas.data(), L, stream) ||
+        dev_upload(sc, &d_pool, t.pool.data(), t.pool.size(), stream) || dev_upload(sc, &d_off, t.offsets.data(), L, stream))
         return 1;
     RB_CUDA_OK(cudaStreamSynchronize(stream)); // host vectors go out of scope
     sc->dev.lights = d_lights;
@@ -336,127 +299,22 @@ int rb_build_lights(rb_scene* sc, cudaStream_t stream) {
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ edges
-static bool pos_less(const float* a, const float* b) { // strict lexicographic order on positions
-    if (a[0] != b[0]) return a[0] < b[0];
-    if (a[1] != b[1]) return a[1] < b[1];
-    return a[2] < b[2];
-}
-static bool pos_eq(const float* a, const float* b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
-
 int rb_build_edges(rb_scene* sc, cudaStream_t stream) {
     sc->dev.edges = nullptr;
     sc->dev.num_edges = 0;
     sc->dev.prim_edge_pmf = sc->dev.prim_edge_cdf = nullptr;
     if (!sc->dev.use_primary_edge && !sc->dev.use_secondary_edge) return 0;
-    auto& meshes = host_meshes(sc);
-    int S = (int)sc->shapes.size();
-    // host-addressable shape table for the shared RB_HD helpers
-    std::vector<rb_shape> hs(sc->shapes);
-    for (int s = 0; s < S; s++) {
-        hs[s].vertices = meshes[s].vertices.data();
-        hs[s].indices = meshes[s].indices.data();
-        // `normals` is only tested for null-ness by edge_is_silhouette
-    }
-    std::vector<Edge> edges;
-    for (int s = 0; s < S; s++) {
-        const HostMesh& m = meshes[s];
-        int T = (int)m.indices.size() / 3;
-        std::vector<Edge> he(3 * (size_t)T);
-        for (int t = 0; t < T; t++) {
-            const int* id = &m.indices[3 * (size_t)t];
-            for (int k = 0; k < 3; k++) {
-                int a = id[k], b = id[(k + 1) % 3];
-                Edge e;
-                e.shape_id = s;
-                e.v0 = std::min(a, b);
-                e.v1 = std::max(a, b);
-                e.f0 = t;
-                e.f1 = -1;
-                he[3 * (size_t)t + k] = e;
-            }
-        }
-        std::stable_sort(he.begin(), he.end(), [](const Edge& x, const Edge& y) { return x.v0 != y.v0 ? x.v0 < y.v0 : x.v1 < y.v1; });
-        // merge runs of equal (v0, v1): f0 of the first, f1 = f0 of the last (src/edge.cpp:86-90, :266-273)
-        std::vector<Edge> merged;
-        for (size_t i = 0; i < he.size();) {
-            size_t j = i + 1;
-            while (j < he.size() && he[j].v0 == he[i].v0 && he[j].v1 == he[i].v1) j++;
-            Edge e = he[i];
-            if (j - i >= 2) e.f1 = he[j - 1].f0;
-            merged.push_back(e);
-            i = j;
-        }
-        // seam repair: sort by end-point POSITIONS and pair up unmatched duplicates (src/edge.cpp:103-166, :280-288)
-        const float* V = m.vertices.data();
-        auto key = [&](const Edge& e, const float*& lo, const float*& hi) {
-            lo = V + 3 * (size_t)e.v0;
-            hi = V + 3 * (size_t)e.v1;
-            if (pos_less(hi, lo)) std::swap(lo, hi);
-        };
-        std::stable_sort(merged.begin(), merged.end(), [&](const Edge& x, const Edge& y) {
-            const float *xl, *xh, *yl, *yh;
-            key(x, xl, xh);
-            key(y, yl, yh);
-            if (!pos_eq(xl, yl)) return pos_less(xl, yl);
-            if (!pos_eq(xh, yh)) return pos_less(xh, yh);
-            return false;
-        });
-        std::vector<int> new_f1(merged.size());
-        for (size_t i = 0; i < merged.size(); i++) {
-            new_f1[i] = merged[i].f1;
-            if (merged[i].f1 != -1) continue;
-            const float *l, *h, *cl, *ch;
-            key(merged[i], l, h);
-            if (i > 0) {
-                key(merged[i - 1], cl, ch);
-                if (pos_eq(l, cl) && pos_eq(h, ch)) new_f1[i] = merged[i - 1].f0;
-            }
-            if (i + 1 < merged.size()) {
-                key(merged[i + 1], cl, ch);
-                if (pos_eq(l, cl) && pos_eq(h, ch)) new_f1[i] = merged[i + 1].f0;
-            }
-        }
-        for (size_t i = 0; i < merged.size(); i++) {
-            merged[i].f1 = new_f1[i];
-            edges.push_back(merged[i]);
-        }
-    }
-    // drop edges between coplanar faces (src/edge.cpp:293-296)
-    std::vector<Edge> kept;
-    for (const Edge& e : edges)
-        if (!edge_is_flat(hs.data(), e)) kept.push_back(e);
-    edges.swap(kept);
-    int E = (int)edges.size();
+    HostEdgeTables t;
+    host_build_edges(sc->shapes, host_meshes(sc), sc->dev.cam, sc->dev.use_primary_edge != 0, t);
+    int E = (int)t.edges.size();
     sc->dev.num_edges = E;
     if (E == 0) return 0;
     Edge* d_edges;
-    if (dev_upload(sc, &d_edges, edges.data(), E, stream)) return 1;
+    if (dev_upload(sc, &d_edges, t.edges.data(), E, stream)) return 1;
     sc->dev.edges = d_edges;
     if (sc->dev.use_primary_edge) {
-        // screen-space length of camera silhouettes -> PMF / CDF (src/edge.cpp:186-214, :298-331)
-        std::vector<double> pmf(E), cdf(E);
-        const DevCamera& cam = sc->dev.cam;
-        double iw = 1.0 / cam.c2w[15];
-        V3 org = mk3((Real)(cam.c2w[3] * iw), (Real)(cam.c2w[7] * iw), (Real)(cam.c2w[11] * iw));
-        double total = 0;
-        for (int i = 0; i < E; i++) {
-            const Edge& e = edges[i];
-            V3 v0 = edge_v0(hs.data(), e), v1 = edge_v1(hs.data(), e);
-            V2 p0, p1, c0, c1;
-            double w = 0;
-            if (cam_project(cam, v0, v1, p0, p1) && clip_line_unit(p0, p1, c0, c1) && edge_is_silhouette(hs.data(), org, e)) w = length(c1 - c0);
-            pmf[i] = w;
-            total += w;
-        }
-        double run = 0;
-        for (int i = 0; i < E; i++) {
-            pmf[i] = total > 0 ? pmf[i] / total : 0.0;
-            cdf[i] = run;
-            run += pmf[i];
-        }
         double *d_pmf, *d_cdf;
-        if (dev_upload(sc, &d_pmf, pmf.data(), E, stream) || dev_upload(sc, &d_cdf, cdf.data(), E, stream)) return 1;
+        if (dev_upload(sc, &d_pmf, t.prim_pmf.data(), E, stream) || dev_upload(sc, &d_cdf, t.prim_cdf.data(), E, stream)) return 1;
         sc->dev.prim_edge_pmf = d_pmf;
         sc->dev.prim_edge_cdf = d_cdf;
     }
@@ -489,58 +347,6 @@ static int get_tables(int device, DeviceTables& out) {
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
-static double lookat_d[16];
-static void host_look_at(const float* pos, const float* look, const float* up, double* m) {
-    auto norm = [](double* v) {
-        double l = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-        if (l > 0) { v[0] /= l; v[1] /= l; v[2] /= l; } else { v[0] = v[1] = v[2] = 0; }
-    };
-    auto crs = [](const double* a, const double* b, double* c) {
-        c[0] = a[1] * b[2] - a[2] * b[1];
-        c[1] = a[2] * b[0] - a[0] * b[2];
-        c[2] = a[0] * b[1] - a[1] * b[0];
-    };
-    double d[3] = {(double)look[0] - pos[0], (double)look[1] - pos[1], (double)look[2] - pos[2]};
-    norm(d);
-    double u[3] = {up[0], up[1], up[2]};
-    norm(u);
-    double r[3];
-    crs(d, u, r);
-    norm(r);
-    double nu[3];
-    crs(r, d, nu);
-    norm(nu);
-    double out[16] = {r[0], nu[0], d[0], pos[0], r[1], nu[1], d[1], pos[1], r[2], nu[2], d[2], pos[2], 0, 0, 0, 1};
-    memcpy(m, out, sizeof(out));
-    (void)lookat_d;
-}
-static void host_inverse4(const double* m, double* o) {
-    M4 a;
-    // use a double Gauss-Jordan elimination
-    double A[4][8];
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) {
-            A[i][j] = m[4 * i + j];
-            A[i][4 + j] = (i == j) ? 1.0 : 0.0;
-        }
-    for (int c = 0; c < 4; c++) {
-        int piv = c;
-        for (int r = c + 1; r < 4; r++)
-            if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
-        for (int k = 0; k < 8; k++) std::swap(A[c][k], A[piv][k]);
-        double d = A[c][c];
-        for (int k = 0; k < 8; k++) A[c][k] /= d;
-        for (int r = 0; r < 4; r++)
-            if (r != c) {
-                double f = A[r][c];
-                for (int k = 0; k < 8; k++) A[r][k] -= f * A[c][k];
-            }
-    }
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) o[4 * i + j] = A[i][4 + j];
-    (void)a;
-}
-
 extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
     if (!desc || !out) {
         rb_set_error("rb_scene_create: null argument");
@@ -584,35 +390,8 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
         return 1;
     };
     // camera (double copies, src/camera.h:44-55)
-    DevCamera& dc = sc->dev.cam;
     memset(&sc->dev, 0, sizeof(DevScene));
-    dc.width = c.width;
-    dc.height = c.height;
-    dc.use_look_at = c.use_look_at;
-    for (int i = 0; i < 3; i++) {
-        dc.position[i] = c.position[i];
-        dc.look[i] = c.look[i];
-        dc.up[i] = c.up[i];
-    }
-    if (c.use_look_at) {
-        host_look_at(c.position, c.look, c.up, dc.c2w);
-        host_inverse4(dc.c2w, dc.w2c);
-    } else {
-        for (int i = 0; i < 16; i++) {
-            dc.c2w[i] = c.cam_to_world[i];
-            dc.w2c[i] = c.world_to_cam[i];
-        }
-    }
-    for (int i = 0; i < 9; i++) {
-        dc.intr_inv[i] = c.intrinsic_mat_inv[i];
-        dc.intr[i] = c.intrinsic_mat[i];
-    }
-    dc.clip_near = c.clip_near;
-    dc.type = c.camera_type;
-    dc.vp_beg[0] = c.viewport_beg[0];
-    dc.vp_beg[1] = c.viewport_beg[1];
-    dc.vp_end[0] = c.viewport_end[0];
-    dc.vp_end[1] = c.viewport_end[1];
+    host_setup_camera(c, sc->dev.cam);
 
     sc->shapes.assign(desc->shapes, desc->shapes + desc->num_shapes);
     sc->materials.assign(desc->materials, desc->materials + desc->num_materials);
@@ -672,7 +451,7 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
     std::vector<char> need(sc->shapes.size(), need_edges ? 1 : 0);
     for (const DevLight& l : sc->lights) need[l.shape_id] = 1;
     for (size_t s = 0; s < sc->shapes.size(); s++)
-        if (need[s] && fetch_mesh(sc->shapes[s], meshes[s], false, stream)) return fail();
+        if (need[s] && fetch_mesh(sc->shapes[s], meshes[s], stream)) return fail();
     if (cudaStreamSynchronize(stream) != cudaSuccess) {
         rb_set_error("rb_scene_create: device-to-host geometry copy failed (are the shape buffers device pointers?)");
         return fail();
@@ -725,26 +504,4 @@ extern "C" int rb_scene_last_stats(const rb_scene* sc, int* launches, float* ms)
 }
 
 // compute_num_channels, src/channels.cpp:42-113
-extern "C" int rb_compute_num_channels(const int* channels, int n, int max_generic) {
-    int total = 0;
-    for (int i = 0; i < n; i++) {
-        switch (channels[i]) {
-            case RB_CH_RADIANCE: case RB_CH_POSITION: case RB_CH_GEOMETRY_NORMAL: case RB_CH_SHADING_NORMAL:
-            case RB_CH_DIFFUSE_REFLECTANCE: case RB_CH_SPECULAR_REFLECTANCE: case RB_CH_VERTEX_COLOR:
-                total += 3;
-                break;
-            case RB_CH_ALPHA: case RB_CH_DEPTH: case RB_CH_ROUGHNESS: case RB_CH_SHAPE_ID: case RB_CH_TRIANGLE_ID: case RB_CH_MATERIAL_ID:
-                total += 1;
-                break;
-            case RB_CH_UV: case RB_CH_BARYCENTRIC:
-                total += 2;
-                break;
-            case RB_CH_GENERIC_TEXTURE:
-                total += max_generic;
-                break;
-            default:
-                return -1;
-        }
-    }
-    return total;
-}
+extern "C" int rb_compute_num_channels(const int* channels, int n, int max_generic) { return host_compute_num_channels(channels, n, max_generic); }

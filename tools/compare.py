@@ -81,13 +81,20 @@ def main():
     ap.add_argument("--sampler", default="sobol")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--lib", default=None, help="alternative libredner_b200 (e.g. the f64 validation build)")
+    ap.add_argument("--emu", action="store_true", help="debug only: run the host-compiled emulator (tools/cpu_emu) instead of the GPU")
+    ap.add_argument("--edges-ref", type=int, default=None, help="edge-sampling flags for the reference run (default: same)")
     a = ap.parse_args()
-    if a.lib:
-        os.environ["REDNER_B200_LIB"] = a.lib
+    from redner_b200 import _lib
+    dev = torch.device("cuda:0")
+    if a.emu:
+        _lib._lib = _lib._bind(__import__("ctypes").CDLL(os.path.join(ROOT, "tools", "cpu_emu", "libredner_b200_emu.so")))
+        dev = torch.device("cpu")
+    elif a.lib:
+        _lib._lib = _lib.load(a.lib)
     from redner_b200 import redner as rb
     ref = ref_loader.load()
-    img_r, g_r, t_r = run(ref, torch.device("cpu"), a.scene, a.res, a.spp, a.mb, a.edges, a.sampler, a.seed)
-    img_c, g_c, t_c = run(rb, torch.device("cuda:0"), a.scene, a.res, a.spp, a.mb, a.edges, a.sampler, a.seed)
+    img_r, g_r, t_r = run(ref, torch.device("cpu"), a.scene, a.res, a.spp, a.mb, a.edges if a.edges_ref is None else a.edges_ref, a.sampler, a.seed)
+    img_c, g_c, t_c = run(rb, dev, a.scene, a.res, a.spp, a.mb, a.edges, a.sampler, a.seed)
     print("scene=%s res=%d spp=%d mb=%d edges=%d sampler=%s" % (a.scene, a.res, a.spp, a.mb, a.edges, a.sampler))
     print("time ref fwd %.3fs bwd %.3fs | cuda fwd %.3fs bwd %.3fs (incl. scene build, first call)" % (t_r + t_c))
     print("image  relL2 = %.3e   (mean ref %.5f, mean cuda %.5f)" % (rel(img_c, img_r), img_r.mean().item(), img_c.cpu().mean().item()))
