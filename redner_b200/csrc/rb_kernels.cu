@@ -297,7 +297,7 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         launches++;
         if (scene->dev.use_primary_edge && scene->dev.num_edges > 0 && scene->dev.prim_edge_cdf != nullptr) {
             int grid_e = pick_grid((const void*)k_primary_edge, scene->device, nullptr);
-            int dim_base = 0;
+            int dim_base = primary_edge_dim_base(scene->dev, rp);
             k_primary_edge<<<grid_e, RB_BLOCK, 0, stream>>>(scene->dev, ka, dim_base);
             launches++;
         }

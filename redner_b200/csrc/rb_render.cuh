@@ -7,6 +7,7 @@
 #pragma once
 #include "rb_edge.cuh"
 #include "rb_path.cuh"
+#include "rb_secondary.cuh"
 
 struct KernelArgs {
     RenderParams rp;
@@ -23,7 +24,21 @@ struct KernelArgs {
 RB_HD unsigned long long main_draws_per_sample(const RenderParams& rp) {
     return (unsigned long long)((rp.sample_pixel_center ? 0 : 2) + 7 * rp.max_bounces);
 }
-RB_HD unsigned long long edge_draws_per_sample(const RenderParams& rp) { return (unsigned long long)(2 + 7 * rp.max_bounces); }
+// Edge-sampler dimension layout per sample, in the order of the reference's next_* calls on `edge_sampler`
+// (src/pathtracer.cpp:505, :630-641 inside the reverse depth loop, then :788, :871-882):
+//   for depth = mb-1 .. 0:  secondary edge (4) + 7 per remaining bounce of its two sub-paths
+//   primary edge (2) + 7 per bounce of its two sub-paths
+RB_HD int secondary_edge_dim_base(const RenderParams& rp, int depth) {
+    int off = 0;
+    for (int d = rp.max_bounces - 1; d > depth; d--) off += 4 + 7 * (rp.max_bounces - 1 - d);
+    return off;
+}
+RB_HD int primary_edge_dim_base(const DevScene& sc, const RenderParams& rp) {
+    return (sc.use_secondary_edge && sc.num_lights > 0) ? secondary_edge_dim_base(rp, -1) : 0;
+}
+RB_HD unsigned long long edge_draws_per_sample(const DevScene& sc, const RenderParams& rp) {
+    return (unsigned long long)(primary_edge_dim_base(sc, rp) + 2 + 7 * rp.max_bounces);
+}
 
 // Camera sample -> primary ray (px, py are viewport-relative pixel coordinates), src/camera.cpp:8-43.
 RB_D void primary_ray_for(const DevScene& sc, const RenderParams& rp, int px, int py, Sampler& smp, double& sx, double& sy, Ray& ray, RayDiff& rd) {
@@ -80,6 +95,14 @@ RB_D void backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, i
         VertexRec cur = recs[d];
         VertexRec nxt = recs[d + 1];
         adj = d_vertex(sc, ds, cur, &nxt, d_contrib, adj);
+        if (sc.use_secondary_edge && sc.num_edges > 0) {
+            // boundary term of the visibility at this vertex (src/pathtracer.cpp:500-707)
+            Sampler es;
+            es.init(rp.sampler_type, rp.seed + 131071ULL, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS,
+                    (unsigned long long)s * edge_draws_per_sample(sc, rp));
+            es.skip(secondary_edge_dim_base(rp, d));
+            secondary_edge_sample(sc, ds, rp, cur, d, es, mk3(dpx[0], dpx[1], dpx[2]), adj.d_point.position);
+        }
     }
     // first vertex: emission adjoint (src/primary_contribution.cpp:449-466) ...
     RayDiff rd_after;
@@ -171,8 +194,9 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
     const DevDScene& ds = ka.ds;
     const Real weight = Real(1) / Real(rp.spp);
     Sampler smp;
-    smp.init(rp.sampler_type, rp.seed + 131071ULL, (int)i, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * edge_draws_per_sample(rp));
-    smp.dim = dim_base;
+    smp.init(rp.sampler_type, rp.seed + 131071ULL, (int)i, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS,
+             (unsigned long long)s * edge_draws_per_sample(sc, rp));
+    smp.skip(dim_base);
     double e_sel = smp.next(), e_t = smp.next();
     int edge_id = cdf_pick(sc.prim_edge_cdf, sc.num_edges, e_sel);
     double pmf = sc.prim_edge_pmf[edge_id];

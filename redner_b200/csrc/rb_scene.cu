@@ -318,6 +318,17 @@ int rb_build_edges(rb_scene* sc, cudaStream_t stream) {
         sc->dev.prim_edge_pmf = d_pmf;
         sc->dev.prim_edge_cdf = d_cdf;
     }
+    if (sc->dev.use_secondary_edge) {
+        HostEdgeTree tree;
+        host_build_edge_tree(sc->shapes, host_meshes(sc), t.edges, sc->dev.cam, tree);
+        EdgeNode* d_nodes;
+        if (dev_upload(sc, &d_nodes, tree.nodes.data(), tree.nodes.size(), stream)) return 1;
+        RB_CUDA_OK(cudaStreamSynchronize(stream));
+        sc->dev.edge_nodes = d_nodes;
+        sc->dev.edge_root_cs = tree.root_cs;
+        sc->dev.edge_root_ncs = tree.root_ncs;
+        sc->dev.edge_bounds_expand = tree.expand;
+    }
     RB_CUDA_OK(cudaStreamSynchronize(stream));
     return 0;
 }
@@ -440,6 +451,7 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
     sc->dev.ltc_table = tabs.ltc;
     sc->dev.edge_nodes = nullptr;
     sc->dev.edge_root_cs = sc->dev.edge_root_ncs = -1;
+    sc->dev.edge_bounds_expand = 0.f;
 
     auto t0 = std::chrono::high_resolution_clock::now();
     if (rb_build_bvh(sc, stream)) return fail();

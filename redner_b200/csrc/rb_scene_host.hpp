@@ -180,6 +180,417 @@ inline void host_build_edges(const std::vector<rb_shape>& shapes, const std::vec
     }
 }
 
+// ---- secondary-edge hierarchy (host build) ----
+// The hierarchical edge sampler's expectation depends on the tree when a scene has few edges (an edge that receives
+// more than one of the 16 stochastic descents is still only counted once, src/edge.cpp:1173-1190), so gradient parity
+// with the oracle on small scenes needs the SAME tree.  This is therefore a step-by-step restatement of
+// EdgeTree::EdgeTree (src/edge_tree.cpp:724-882) in index form:
+//   partition into camera silhouettes / rest (:749-756), 6-D edge bounds with the Hough transform (:23-66),
+//   billboard size from the mean absolute deviation (:763-773), Morton codes (:166-266), stable sort (:795, :846),
+//   Karras radix tree with the reference's tie break (:282-376), bottom-up bounds and weighted lengths (:391-445)
+//   and the treelet (<= 7 leaves) SAH re-optimisation (:464-711) including its quirks.
+// The result is flattened into the 64-byte EdgeNode array the kernels traverse.
+struct HostEdgeTree {
+    std::vector<EdgeNode> nodes;
+    int root_cs = -1, root_ncs = -1;
+    float expand = 0.f;
+};
+struct HNode { // node of the reference-shaped tree (double precision like the reference's Real)
+    double pmin[3], pmax[3], dmin[3], dmax[3];
+    double wlen;
+    int parent;
+    int child[2];
+    int edge_id;
+    double cost;
+};
+inline int host_clz64(unsigned long long x) { return x == 0 ? 64 : __builtin_clzll(x); }
+inline unsigned long long host_expand21(unsigned long long x) {
+    x &= 0x1fffffULL;
+    x = (x | x << 32) & 0x1f00000000ffffULL;
+    x = (x | x << 16) & 0x1f0000ff0000ffULL;
+    x = (x | x << 8) & 0x100f00f00f00f00fULL;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+inline unsigned long long host_expand10(unsigned long long x) { // 5 zeros before each bit of a 10-bit integer
+    unsigned long long r = 0;
+    for (int b = 0; b < 10; b++) r |= ((x >> b) & 1ULL) << (5 * b);
+    return r;
+}
+struct HostTreeBuilder {
+    bool six;
+    std::vector<HNode> n; // [0, L-1) internal, [L-1, 2L-1) leaves (leaf j at L-1+j)
+    int L = 0;
+    static void merge_into(HNode& o, const HNode& a, const HNode& b) {
+        for (int k = 0; k < 3; k++) {
+            o.pmin[k] = std::min(a.pmin[k], b.pmin[k]);
+            o.pmax[k] = std::max(a.pmax[k], b.pmax[k]);
+            o.dmin[k] = std::min(a.dmin[k], b.dmin[k]);
+            o.dmax[k] = std::max(a.dmax[k], b.dmax[k]);
+        }
+    }
+    double area(const HNode& a) const {
+        double dx = a.pmax[0] - a.pmin[0], dy = a.pmax[1] - a.pmin[1], dz = a.pmax[2] - a.pmin[2];
+        double s = dx * dy + dx * dz + dy * dz;
+        if (six) {
+            double ex = a.dmax[0] - a.dmin[0], ey = a.dmax[1] - a.dmin[1], ez = a.dmax[2] - a.dmin[2];
+            s += ex * ey + ex * ez + ey * ez;
+        }
+        return 2 * s;
+    }
+    void refresh(int i) { // bounds, weighted length and SAH cost of an internal node from its children
+        HNode &o = n[i];
+        const HNode &a = n[o.child[0]], &b = n[o.child[1]];
+        merge_into(o, a, b);
+        o.wlen = a.wlen + b.wlen;
+        o.cost = area(o) + a.cost + b.cost;
+    }
+    // src/edge_tree.cpp:491-500: NOTE the union always starts from leaf 0, also for subsets that do not contain it
+    double subset_area(int cnt, const int* lv, unsigned s) const {
+        HNode t = n[lv[0]];
+        for (int i = 1; i < cnt; i++)
+            if ((s >> i) & 1u) merge_into(t, t, n[lv[i]]);
+        return area(t);
+    }
+    void propagate_cost(int root, const int* lv, int cnt) { // src/edge_tree.cpp:546-579
+        for (int i = 0; i < cnt; i++) {
+            int cur = lv[i];
+            while (cur != root) {
+                if (n[cur].cost < 0) {
+                    if (n[n[cur].child[0]].cost >= 0 && n[n[cur].child[1]].cost >= 0) refresh(cur); else break;
+                }
+                cur = n[cur].parent;
+            }
+        }
+        refresh(root);
+    }
+    void restruct(int parent, int child_index, const int* lv, const int* inner, unsigned char partition, const unsigned char* optimal, int& index,
+                  int cnt) { // src/edge_tree.cpp:586-626
+        struct Entry { unsigned char partition, child; int parent; } stack[8];
+        int sp = 0;
+        stack[sp++] = Entry{partition, (unsigned char)child_index, parent};
+        while (sp > 0) {
+            Entry e = stack[--sp];
+            if (__builtin_popcount(e.partition) == 1) {
+                int leaf = lv[__builtin_ffs(e.partition) - 1];
+                n[e.parent].child[e.child] = leaf;
+                n[leaf].parent = e.parent;
+            } else {
+                int node = inner[index++];
+                n[node].cost = -1;
+                n[e.parent].child[e.child] = node;
+                n[node].parent = e.parent;
+                unsigned char lp = optimal[e.partition];
+                unsigned char rp = (unsigned char)((~lp) & e.partition);
+                stack[sp++] = Entry{lp, 0, node};
+                stack[sp++] = Entry{rp, 1, node};
+            }
+        }
+        propagate_cost(parent, lv, cnt);
+    }
+    void treelet_optimize(int root) { // src/edge_tree.cpp:627-684
+        if (n[root].edge_id != -1) return;
+        int lv[7], inner[5];
+        int cnt = 0, icnt = 0;
+        lv[cnt++] = n[root].child[0];
+        lv[cnt++] = n[root].child[1];
+        int max_idx = 0;
+        while (cnt < 7 && max_idx != -1) {
+            max_idx = -1;
+            double max_area = -1;
+            for (int i = 0; i < cnt; i++)
+                if (n[lv[i]].edge_id == -1) {
+                    double a = area(n[lv[i]]);
+                    if (a > max_area) {
+                        max_area = a;
+                        max_idx = i;
+                    }
+                }
+            if (max_idx != -1) {
+                int tmp = lv[max_idx];
+                inner[icnt++] = tmp;
+                lv[max_idx] = lv[cnt - 1];
+                lv[cnt - 1] = n[tmp].child[0];
+                lv[cnt] = n[tmp].child[1];
+                cnt++;
+            }
+        }
+        // Algorithm 2 of Karras & Aila 2013 (src/edge_tree.cpp:502-544)
+        unsigned char optimal[128];
+        double a[128], c_opt[128];
+        unsigned num_subsets = (1u << cnt) - 1;
+        for (unsigned s = 1; s <= num_subsets; s++) a[s] = subset_area(cnt, lv, s);
+        for (int i = 0; i < cnt; i++) c_opt[1u << i] = n[lv[i]].cost;
+        for (int k = 2; k <= cnt; k++)
+            for (unsigned s = 1; s <= num_subsets; s++)
+                if (__builtin_popcount(s) == k) {
+                    double c_s = INFINITY;
+                    unsigned p_s = 0;
+                    unsigned d = (s - 1u) & s;
+                    unsigned p = (0u - d) & s;
+                    do {
+                        double c = c_opt[p] + c_opt[s ^ p];
+                        if (c < c_s) {
+                            c_s = c;
+                            p_s = p;
+                        }
+                        p = (p - d) & s;
+                    } while (p != 0);
+                    c_opt[s] = a[s] + c_s;
+                    optimal[s] = (unsigned char)p_s;
+                }
+        unsigned char mask = (unsigned char)((1u << cnt) - 1);
+        int index = 0;
+        unsigned char left = optimal[mask];
+        restruct(root, 0, lv, inner, left, optimal, index, cnt);
+        unsigned char right = (unsigned char)((~left) & mask);
+        restruct(root, 1, lv, inner, right, optimal, index, cnt);
+        refresh(root);
+    }
+    void optimize_postorder(int root) {
+        // every internal node is optimised after both of its (already optimised) child subtrees, which is the order the
+        // reference's atomic-counter walk guarantees (src/edge_tree.cpp:685-707)
+        std::vector<std::pair<int, int>> st;
+        st.push_back({root, 0});
+        while (!st.empty()) {
+            auto& top = st.back();
+            int i = top.first;
+            if (n[i].edge_id != -1) {
+                st.pop_back();
+                continue;
+            }
+            if (top.second == 0) {
+                top.second = 1;
+                st.push_back({n[i].child[0], 0});
+            } else if (top.second == 1) {
+                top.second = 2;
+                st.push_back({n[i].child[1], 0});
+            } else {
+                st.pop_back();
+                treelet_optimize(i);
+            }
+        }
+    }
+    // returns the root index in `n` (or -1)
+    int build(const std::vector<HNode>& leaf_nodes, const std::vector<unsigned long long>& codes, const std::vector<int>& ids) {
+        L = (int)ids.size();
+        if (L == 0) return -1;
+        n.assign(std::max(L - 1, 1) + L, HNode());
+        for (auto& x : n) {
+            x.parent = -1;
+            x.child[0] = x.child[1] = -1;
+            x.edge_id = -1;
+            x.cost = 0;
+            x.wlen = 0;
+            for (int k = 0; k < 3; k++) {
+                x.pmin[k] = x.dmin[k] = INFINITY;
+                x.pmax[k] = x.dmax[k] = -INFINITY;
+            }
+        }
+        int LB = std::max(L - 1, 1); // leaf base
+        for (int j = 0; j < L; j++) {
+            n[LB + j] = leaf_nodes[ids[j]];
+            n[LB + j].parent = -1;
+            n[LB + j].cost = area(n[LB + j]);
+        }
+        if (L == 1) {
+            n[0] = n[LB]; // src/edge_tree.cpp:303-308
+            return 0;
+        }
+        auto lcp = [&](int i, int j) -> int {
+            if (i < 0 || i >= L || j < 0 || j >= L) return -1;
+            unsigned long long a = codes[ids[i]], b = codes[ids[j]];
+            if (a == b) return host_clz64(a ^ b) + host_clz64((unsigned long long)ids[i] ^ (unsigned long long)ids[j]);
+            return host_clz64(a ^ b);
+        };
+        for (int i = 0; i < L - 1; i++) {
+            int d = (lcp(i, i + 1) - lcp(i, i - 1)) >= 0 ? 1 : -1;
+            int dmin = lcp(i, i - d);
+            int lmax = 2;
+            while (lcp(i, i + lmax * d) > dmin) lmax *= 2;
+            int l = 0;
+            for (int t = lmax / 2; t >= 1; t /= 2)
+                if (lcp(i, i + (l + t) * d) > dmin) l += t;
+            int j = i + l * d;
+            int dnode = lcp(i, j);
+            int s = 0, div = 2;
+            for (int t = (l + (div - 1)) / div; t >= 1;) {
+                if (lcp(i, i + (s + t) * d) > dnode) s += t;
+                if (t == 1) break;
+                div *= 2;
+                t = (l + (div - 1)) / div;
+            }
+            int gamma = i + s * d + std::min(d, 0);
+            int c0 = (std::min(i, j) == gamma) ? LB + gamma : gamma;
+            int c1 = (std::max(i, j) == gamma + 1) ? LB + gamma + 1 : gamma + 1;
+            n[i].child[0] = c0;
+            n[i].child[1] = c1;
+            n[c0].parent = i;
+            n[c1].parent = i;
+        }
+        // bottom-up bounds / weighted lengths (costs of internal nodes are set by the optimiser)
+        {
+            std::vector<int> order; // post-order over internal nodes
+            std::vector<std::pair<int, int>> st;
+            st.push_back({0, 0});
+            while (!st.empty()) {
+                auto& top = st.back();
+                int i = top.first;
+                if (n[i].edge_id != -1 || i >= LB) { st.pop_back(); continue; }
+                if (top.second == 0) { top.second = 1; st.push_back({n[i].child[0], 0}); }
+                else if (top.second == 1) { top.second = 2; st.push_back({n[i].child[1], 0}); }
+                else { st.pop_back(); order.push_back(i); }
+            }
+            for (int i : order) {
+                merge_into(n[i], n[n[i].child[0]], n[n[i].child[1]]);
+                n[i].wlen = n[n[i].child[0]].wlen + n[n[i].child[1]].wlen;
+            }
+        }
+        optimize_postorder(0);
+        return 0;
+    }
+};
+inline V3 host_edge_normal(const rb_shape* hs, const Edge& e, int which) {
+    V3 v0 = edge_v0(hs, e), v1 = edge_v1(hs, e);
+    V3 n;
+    if (which == 0) {
+        V3 o = edge_opposite0(hs, e);
+        n = cross(v0 - o, v1 - o);
+    } else {
+        V3 o = edge_opposite1(hs, e);
+        n = cross(v1 - o, v0 - o);
+    }
+    Real l2 = length_sq(n);
+    if (l2 < Real(1e-20)) return zero3();
+    return n / std::sqrt(l2);
+}
+inline void host_build_edge_tree(const std::vector<rb_shape>& shapes, const std::vector<HostMesh>& meshes, const std::vector<Edge>& edges,
+                                 const DevCamera& cam, HostEdgeTree& out) {
+    out.nodes.clear();
+    out.root_cs = out.root_ncs = -1;
+    out.expand = 0.f;
+    int E = (int)edges.size();
+    if (E == 0) return;
+    std::vector<rb_shape> hs(shapes);
+    for (size_t s = 0; s < shapes.size(); s++) {
+        hs[s].vertices = meshes[s].vertices.data();
+        hs[s].indices = meshes[s].indices.data();
+    }
+    double iw = 1.0 / cam.c2w[15];
+    double co[3] = {cam.c2w[3] * iw, cam.c2w[7] * iw, cam.c2w[11] * iw};
+    V3 cam_org = mk3((Real)co[0], (Real)co[1], (Real)co[2]);
+    std::vector<HNode> leaves(E);
+    std::vector<int> ids_cs, ids_ncs;
+    double mean[3] = {0, 0, 0};
+    for (int i = 0; i < E; i++) {
+        const Edge& e = edges[i];
+        V3 v0 = edge_v0(hs.data(), e), v1 = edge_v1(hs.data(), e);
+        for (int k = 0; k < 3; k++) mean[k] += (double)v0[k] + (double)v1[k];
+        HNode n;
+        V3 n0 = host_edge_normal(hs.data(), e, 0);
+        V3 n1 = e.f1 == -1 ? -n0 : host_edge_normal(hs.data(), e, 1);
+        double p[3], p0d = 0, p1d = 0;
+        for (int k = 0; k < 3; k++) p[k] = 0.5 * ((double)v0[k] + (double)v1[k]) - co[k];
+        for (int k = 0; k < 3; k++) {
+            p0d += p[k] * (double)n0[k];
+            p1d += p[k] * (double)n1[k];
+        }
+        for (int k = 0; k < 3; k++) {
+            double h0 = (double)n0[k] * p0d, h1 = (double)n1[k] * p1d;
+            n.pmin[k] = std::min((double)v0[k], (double)v1[k]);
+            n.pmax[k] = std::max((double)v0[k], (double)v1[k]);
+            n.dmin[k] = std::min(h0, h1);
+            n.dmax[k] = std::max(h0, h1);
+        }
+        double ext = M_PI;
+        if (e.f1 != -1) ext = std::acos(std::min(1.0, std::max(-1.0, (double)dot(n0, n1))));
+        n.wlen = (double)length(v1 - v0) * ext;
+        n.parent = -1;
+        n.child[0] = n.child[1] = -1;
+        n.edge_id = i;
+        n.cost = 0;
+        leaves[i] = n;
+        (edge_is_silhouette(hs.data(), cam_org, e) ? ids_cs : ids_ncs).push_back(i);
+    }
+    for (int k = 0; k < 3; k++) mean[k] /= 2.0 * E;
+    double mad[3] = {0, 0, 0};
+    for (int i = 0; i < E; i++) {
+        V3 v0 = edge_v0(hs.data(), edges[i]), v1 = edge_v1(hs.data(), edges[i]);
+        for (int k = 0; k < 3; k++) mad[k] += std::fabs((double)v0[k] - mean[k]) + std::fabs((double)v1[k] - mean[k]);
+    }
+    for (int k = 0; k < 3; k++) mad[k] /= E;
+    out.expand = (float)(0.01 * std::sqrt(mad[0] * mad[0] + mad[1] * mad[1] + mad[2] * mad[2]));
+    auto build = [&](std::vector<int>& ids, bool six) -> int {
+        if (ids.empty()) return -1;
+        double lo[6], hi[6];
+        for (int k = 0; k < 6; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+        for (int id : ids)
+            for (int k = 0; k < 3; k++) {
+                lo[k] = std::min(lo[k], leaves[id].pmin[k]);
+                hi[k] = std::max(hi[k], leaves[id].pmax[k]);
+                lo[3 + k] = std::min(lo[3 + k], leaves[id].dmin[k]);
+                hi[3 + k] = std::max(hi[3 + k], leaves[id].dmax[k]);
+            }
+        std::vector<unsigned long long> codes(E, 0);
+        for (int id : ids) {
+            double q[6];
+            for (int k = 0; k < 3; k++) {
+                double cp = 0.5 * (leaves[id].pmin[k] + leaves[id].pmax[k]), cd = 0.5 * (leaves[id].dmin[k] + leaves[id].dmax[k]);
+                q[k] = hi[k] - lo[k] <= 0 ? 0.5 : (cp - lo[k]) / (hi[k] - lo[k]);
+                q[3 + k] = hi[3 + k] - lo[3 + k] <= 0 ? 0.5 : (cd - lo[3 + k]) / (hi[3 + k] - lo[3 + k]);
+            }
+            if (!six) {
+                double sc = (1 << 21) - 1;
+                codes[id] = (host_expand21((unsigned long long)(q[0] * sc)) << 2) | (host_expand21((unsigned long long)(q[1] * sc)) << 1) |
+                            host_expand21((unsigned long long)(q[2] * sc));
+            } else {
+                unsigned long long c = 0;
+                for (int k = 0; k < 6; k++) c |= host_expand10((unsigned long long)(q[k] * 1023)) << (5 - k);
+                codes[id] = c;
+            }
+        }
+        std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return codes[a] < codes[b]; });
+        HostTreeBuilder tb;
+        tb.six = six;
+        int root = tb.build(leaves, codes, ids);
+        // flatten (depth-first) into EdgeNode
+        int base = (int)out.nodes.size();
+        std::vector<int> map(tb.n.size(), -1);
+        std::vector<int> st;
+        st.push_back(root);
+        std::vector<int> order;
+        while (!st.empty()) {
+            int i = st.back();
+            st.pop_back();
+            map[i] = base + (int)order.size();
+            order.push_back(i);
+            if (tb.n[i].edge_id == -1) {
+                st.push_back(tb.n[i].child[1]);
+                st.push_back(tb.n[i].child[0]);
+            }
+        }
+        for (int i : order) {
+            const HNode& h = tb.n[i];
+            EdgeNode en;
+            for (int k = 0; k < 3; k++) {
+                en.pmin[k] = (float)h.pmin[k];
+                en.pmax[k] = (float)h.pmax[k];
+                en.dmin[k] = (float)h.dmin[k];
+                en.dmax[k] = (float)h.dmax[k];
+            }
+            en.wlen = (float)h.wlen;
+            en.edge_id = h.edge_id;
+            en.left = h.edge_id == -1 ? map[h.child[0]] : -1;
+            en.right = h.edge_id == -1 ? map[h.child[1]] : -1;
+            out.nodes.push_back(en);
+        }
+        return base;
+    };
+    out.root_cs = build(ids_cs, false);
+    out.root_ncs = build(ids_ncs, true);
+}
+
 inline void host_look_at(const float* pos, const float* look, const float* up, double* m) {
     auto norm = [](double* v) {
         double l = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);

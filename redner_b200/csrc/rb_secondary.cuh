@@ -1,0 +1,508 @@
+// Secondary (shadow / interreflection) edge sampling at one path vertex.
+//   secondary_edge_sampler                    src/edge.cpp:826-1773  (ltc_bound :838-875, importance :885-917,
+//                                             leaf_importance :943-1067, sample_edge_h :1115-1237, sample_edge_l :1239-1364,
+//                                             operator() :1366-1744)
+//   get_ltc_matrix                            src/edge.cpp:803-814
+//   secondary_edge_weights_updater            src/edge.cpp:1856-1972 (intersect_jacobian :1829-1853)
+//   secondary_edge_derivatives_accumulator    src/edge.cpp:2001-2043
+// The estimator is the reference's; the hierarchy it walks is our own flat, balanced tree (EdgeNode, built in
+// rb_scene_host.hpp) instead of the treelet-optimised pointer LBVH of src/edge_tree.cpp, so individual samples
+// differ from the reference's while the expectation is the same (edge-sampling parity is statistical).
+// Every path keeps its traversal state in a <= 24-entry stack: each stack item carries at least one of the 16
+// stochastic descents, so the hierarchical sampler never holds more than 16 items; the gather variant holds at
+// most two per level of the balanced tree.
+#pragma once
+#include "rb_edge.cuh"
+#include "rb_path.cuh"
+
+#define RB_EDGE_H_SAMPLES 16
+#define RB_EDGE_STACK_H 24
+#define RB_EDGE_STACK_L 64
+
+RB_HD M3 m3_rows(V3 a, V3 b, V3 c) {
+    M3 r;
+    r.m[0][0] = a.x; r.m[0][1] = a.y; r.m[0][2] = a.z;
+    r.m[1][0] = b.x; r.m[1][1] = b.y; r.m[1][2] = b.z;
+    r.m[2][0] = c.x; r.m[2][1] = c.y; r.m[2][2] = c.z;
+    return r;
+}
+RB_HD M3 m3_mul(const M3& a, const M3& b) {
+    M3 r;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+    return r;
+}
+RB_HD M3 m3_inverse(const M3& m) {
+    Real det = m.m[0][0] * (m.m[1][1] * m.m[2][2] - m.m[2][1] * m.m[1][2]) - m.m[0][1] * (m.m[1][0] * m.m[2][2] - m.m[1][2] * m.m[2][0]) +
+               m.m[0][2] * (m.m[1][0] * m.m[2][1] - m.m[1][1] * m.m[2][0]);
+    Real id = 1 / det;
+    M3 r;
+    r.m[0][0] = (m.m[1][1] * m.m[2][2] - m.m[2][1] * m.m[1][2]) * id;
+    r.m[0][1] = (m.m[0][2] * m.m[2][1] - m.m[0][1] * m.m[2][2]) * id;
+    r.m[0][2] = (m.m[0][1] * m.m[1][2] - m.m[0][2] * m.m[1][1]) * id;
+    r.m[1][0] = (m.m[1][2] * m.m[2][0] - m.m[1][0] * m.m[2][2]) * id;
+    r.m[1][1] = (m.m[0][0] * m.m[2][2] - m.m[0][2] * m.m[2][0]) * id;
+    r.m[1][2] = (m.m[1][0] * m.m[0][2] - m.m[0][0] * m.m[1][2]) * id;
+    r.m[2][0] = (m.m[1][0] * m.m[2][1] - m.m[2][0] * m.m[1][1]) * id;
+    r.m[2][1] = (m.m[2][0] * m.m[0][1] - m.m[0][0] * m.m[2][1]) * id;
+    r.m[2][2] = (m.m[0][0] * m.m[1][1] - m.m[1][0] * m.m[0][1]) * id;
+    return r;
+}
+
+struct EdgeCtx { // per-vertex constants of the sampler
+    const DevScene* sc;
+    SurfacePoint p;
+    M3 m, m_inv;
+    V3 cam_org;
+};
+
+RB_HD Real min_abs_bound(Real lo, Real hi) {
+    if (lo <= 0 && hi >= 0) return 0;
+    if (lo <= 0 && hi <= 0) return hi;
+    return lo;
+}
+RB_HD bool node_contains(const EdgeNode& n, V3 p) {
+    return p.x >= n.pmin[0] && p.x <= n.pmax[0] && p.y >= n.pmin[1] && p.y <= n.pmax[1] && p.z >= n.pmin[2] && p.z <= n.pmax[2];
+}
+// Upper bound of the (linearly transformed) cosine lobe over a position box, src/edge.cpp:838-875
+RB_D Real ltc_bound(const EdgeNode& n, const EdgeCtx& c) {
+    V3 dir = mk3(0, 0, 1);
+    if (!node_contains(n, c.p.position)) {
+        V3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+        for (int i = 0; i < 8; i++) {
+            V3 corner = mk3((i & 1) ? n.pmax[0] : n.pmin[0], (i & 2) ? n.pmax[1] : n.pmin[1], (i & 4) ? n.pmax[2] : n.pmin[2]);
+            V3 q = mul(c.m_inv, corner - c.p.position);
+            lo = mk3(rb_min(lo.x, q.x), rb_min(lo.y, q.y), rb_min(lo.z, q.z));
+            hi = mk3(rb_max(hi.x, q.x), rb_max(hi.y, q.y), rb_max(hi.z, q.z));
+        }
+        if (hi.z < 0) return 0;
+        dir = mk3(min_abs_bound(lo.x, hi.x), min_abs_bound(lo.y, hi.y), hi.z);
+        Real l = length(dir);
+        dir = l <= 0 ? mk3(0, 0, 1) : dir / l;
+    }
+    V3 max_dir = normalize(mul(c.m, dir));
+    V3 local = mul(c.m_inv, max_dir);
+    if (local.z <= 0) return 0;
+    return local.z / rb_sq(length_sq(local));
+}
+// Olson & Zhang: an edge of the non-camera-silhouette set can only be a silhouette from p if the sphere with
+// diameter (cam_org, p) touches its Hough-space box; src/edge.cpp:906-911, box/sphere test src/aabb.h:155-171
+RB_HD bool hough_may_be_silhouette(const EdgeNode& n, V3 p, V3 cam_org) {
+    V3 center = Real(0.5) * (p - cam_org);
+    Real r2 = rb_sq(Real(0.5) * length(p - cam_org));
+    Real d = 0;
+    for (int i = 0; i < 3; i++) {
+        if (center[i] < n.dmin[i]) d += rb_sq(center[i] - n.dmin[i]);
+        else if (center[i] > n.dmax[i]) d += rb_sq(center[i] - n.dmax[i]);
+        if (d <= r2) return true;
+    }
+    return false;
+}
+RB_D Real node_importance(const EdgeNode& n, bool is6d, const EdgeCtx& c) {
+    if (is6d && !hough_may_be_silhouette(n, c.p.position, c.cam_org)) return 0;
+    Real brdf = ltc_bound(n, c);
+    V3 center = Real(0.5) * (mk3(n.pmin[0], n.pmin[1], n.pmin[2]) + mk3(n.pmax[0], n.pmax[1], n.pmax[2]));
+    return brdf * n.wlen / rb_max(length(center - c.p.position), Real(1e-3));
+}
+// Integral of the transformed cosine along the (clipped) edge, src/edge.cpp:951-983
+RB_D Real edge_ltc_integral(V3 v0, V3 v1, const EdgeCtx& c) {
+    if (!(length_sq(v1 - v0) > Real(1e-10))) return 0;
+    V3 a = mul(c.m_inv, v0 - c.p.position), b = mul(c.m_inv, v1 - c.p.position);
+    if (!(a.z > 0 || b.z > 0)) return 0;
+    if (a.z < 0) a = (a * b.z - b * a.z) / (b.z - a.z);
+    if (b.z < 0) b = (a * b.z - b * a.z) / (b.z - a.z);
+    V3 wt = normalize(b - a);
+    Real l0 = dot(a, wt), l1 = dot(b, wt);
+    V3 vo = a - l0 * wt;
+    Real d = length(vo);
+    auto I = [&](Real l) { return (l / (d * (d * d + l * l)) + atan(l / d) / (d * d)) * vo.z + (l * l / (d * (d * d + l * l))) * wt.z; };
+    return rb_max(I(l1) - I(l0), Real(0));
+}
+RB_D Real leaf_importance_h(const Edge& e, const EdgeCtx& c) {
+    if (!edge_is_silhouette(c.sc->shapes, c.p.position, e)) return 0;
+    return edge_ltc_integral(edge_v0(c.sc->shapes, e), edge_v1(c.sc->shapes, e), c);
+}
+// gather variant: the edge must also be a silhouette seen from the light point and its "billboard" must be hit
+// by the shadow ray, src/edge.cpp:998-1067
+RB_D Real leaf_importance_l(const Edge& e, const EdgeCtx& c, const Ray& nee, Real billboard) {
+    if (!edge_is_silhouette(c.sc->shapes, c.p.position, e)) return 0;
+    V3 nee_pt = nee.org + nee.tmax * nee.dir;
+    if (!edge_is_silhouette(c.sc->shapes, nee_pt, e)) return 0;
+    V3 v0 = edge_v0(c.sc->shapes, e), v1 = edge_v1(c.sc->shapes, e);
+    Real t = -(dot(nee.org, nee.dir) - dot(v0, nee.dir)) / dot(nee.dir, nee.dir);
+    V3 ip = nee.org + nee.dir * t;
+    V3 v0_p = v0 - ip;
+    V3 ed = normalize(v1 - v0);
+    V3 ept = ip + v0_p - dot(v0_p, ed) * ed;
+    if (length_sq(ept - ip) > rb_sq(billboard)) return 0;
+    return edge_ltc_integral(v0, v1, c);
+}
+// pbrt-style slab test with the box grown by `expand`, src/aabb.h:172-195
+RB_HD bool node_hit_by_ray(const EdgeNode& n, const Ray& r, Real expand) {
+    Real t0 = r.tmin, t1 = r.tmax;
+    for (int i = 0; i < 3; i++) {
+        Real inv = 1 / r.dir[i];
+        Real tn = (n.pmin[i] - expand - r.org[i]) * inv, tf = (n.pmax[i] + expand - r.org[i]) * inv;
+        if (tn > tf) {
+            Real tmp = tn;
+            tn = tf;
+            tf = tmp;
+        }
+        tf *= (1 + Real(1e-6));
+        t0 = tn > t0 ? tn : t0;
+        t1 = tf < t1 ? tf : t1;
+        if (t0 > t1) return false;
+    }
+    return true;
+}
+
+struct StackH {
+    int node;
+    short num;
+    short is6d;
+    Real pmf;
+};
+// Split `num` stochastic descents between two children proportionally to their importance.
+RB_D void split_samples(int num, Real prob0, Real& u, int& n0, int& n1) {
+    Real e0 = num * prob0, e1 = num * (1 - prob0);
+    n0 = (int)floor(e0);
+    n1 = (int)floor(e1);
+    if (n0 + n1 < num) {
+        Real prob = e0 - n0;
+        if (u < prob) {
+            n0++;
+            u /= prob;
+        } else {
+            n1++;
+            u = (u - prob) / (1 - prob);
+        }
+    }
+}
+// 16 correlated stochastic descents through both trees followed by reservoir resampling among the reached leaves.
+RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sample_weight) {
+    const DevScene& sc = *c.sc;
+    StackH stack[RB_EDGE_STACK_H];
+    int sp = 0;
+    int selected = -1;
+    Real edge_weight = 0, wsum = 0;
+    Real imp_cs = sc.edge_root_cs >= 0 ? Real(1) : Real(0), imp_ncs = sc.edge_root_ncs >= 0 ? Real(1) : Real(0);
+    if (imp_cs <= 0 && imp_ncs <= 0) return -1;
+    Real prob_cs = imp_cs / (imp_cs + imp_ncs);
+    int n_cs, n_ncs;
+    split_samples(RB_EDGE_H_SAMPLES, prob_cs, u, n_cs, n_ncs);
+    if (n_cs > 0) { stack[sp].node = sc.edge_root_cs; stack[sp].num = (short)n_cs; stack[sp].is6d = 0; stack[sp].pmf = prob_cs; sp++; }
+    if (n_ncs > 0) { stack[sp].node = sc.edge_root_ncs; stack[sp].num = (short)n_ncs; stack[sp].is6d = 1; stack[sp].pmf = 1 - prob_cs; sp++; }
+    while (sp > 0) {
+        StackH it = stack[--sp];
+        const EdgeNode& n = sc.edge_nodes[it.node];
+        if (n.edge_id >= 0) {
+            Real w = it.num * leaf_importance_h(sc.edges[n.edge_id], c) / it.pmf;
+            if (w > 0) {
+                Real prev = wsum;
+                wsum += w;
+                Real nw = w / wsum;
+                if (resample_u <= nw || prev == 0) {
+                    selected = n.edge_id;
+                    edge_weight = w * it.pmf;
+                    resample_u /= nw;
+                } else {
+                    resample_u = (resample_u - nw) / (1 - nw);
+                }
+            }
+        } else {
+            Real i0, i1;
+            if (node_contains(n, c.p.position)) {
+                i0 = i1 = 1;
+            } else {
+                i0 = node_importance(sc.edge_nodes[n.left], it.is6d != 0, c);
+                i1 = node_importance(sc.edge_nodes[n.right], it.is6d != 0, c);
+            }
+            if (i0 > 0 || i1 > 0) {
+                Real p0 = i0 / (i0 + i1);
+                int n0, n1;
+                split_samples(it.num, p0, u, n0, n1);
+                if (n0 > 0 && sp < RB_EDGE_STACK_H) { stack[sp].node = n.left; stack[sp].num = (short)n0; stack[sp].is6d = it.is6d; stack[sp].pmf = it.pmf * p0; sp++; }
+                if (n1 > 0 && sp < RB_EDGE_STACK_H) { stack[sp].node = n.right; stack[sp].num = (short)n1; stack[sp].is6d = it.is6d; stack[sp].pmf = it.pmf * (1 - p0); sp++; }
+            }
+        }
+    }
+    if (edge_weight <= 0 || wsum <= 0) return -1;
+    sample_weight = 1 / (edge_weight * RB_EDGE_H_SAMPLES / wsum);
+    return selected;
+}
+// Gather all silhouette edges whose billboard the shadow ray crosses and pick one by reservoir resampling.
+RB_D int sample_edge_gather(const EdgeCtx& c, const Ray& nee, const Isect& lis, const SurfacePoint& lp, Real resample_u, Real& sample_weight,
+                            V3& edge_pt, V3& mwt) {
+    const DevScene& sc = *c.sc;
+    int stack[RB_EDGE_STACK_L];
+    int sp = 0;
+    int n_cs_items = 0; // entries below this index on the stack belong to ... (we tag 6D nodes with the sign bit instead)
+    (void)n_cs_items;
+    int selected = -1;
+    Real edge_weight = 0, wsum = 0;
+    Real expand = sc.edge_bounds_expand;
+    // encode the tree kind in bit 30
+    if (sc.edge_root_cs >= 0) stack[sp++] = sc.edge_root_cs;
+    if (sc.edge_root_ncs >= 0) stack[sp++] = sc.edge_root_ncs | (1 << 30);
+    while (sp > 0) {
+        int item = stack[--sp];
+        bool is6d = (item & (1 << 30)) != 0;
+        const EdgeNode& n = sc.edge_nodes[item & ~(1 << 30)];
+        if (n.edge_id >= 0) {
+            Real w = leaf_importance_l(sc.edges[n.edge_id], c, nee, expand);
+            if (w > 0) {
+                Real prev = wsum;
+                wsum += w;
+                Real nw = w / wsum;
+                if (resample_u <= nw || prev == 0) {
+                    selected = n.edge_id;
+                    edge_weight = w;
+                    resample_u /= nw;
+                } else {
+                    resample_u = (resample_u - nw) / (1 - nw);
+                }
+            }
+        } else {
+            for (int k = 0; k < 2; k++) {
+                int ci = k == 0 ? n.left : n.right;
+                const EdgeNode& ch = sc.edge_nodes[ci];
+                bool ok = true;
+                if (is6d) ok = hough_may_be_silhouette(ch, c.p.position, c.cam_org) && hough_may_be_silhouette(ch, lp.position, c.cam_org);
+                if (ok && node_hit_by_ray(ch, nee, expand) && sp < RB_EDGE_STACK_L) stack[sp++] = ci | (is6d ? (1 << 30) : 0);
+            }
+        }
+    }
+    if (selected == -1) return -1;
+    Real pmf = edge_weight / wsum;
+    const Edge& e = sc.edges[selected];
+    V3 v0 = edge_v0(sc.shapes, e), v1 = edge_v1(sc.shapes, e);
+    Real t = -(dot(nee.org, nee.dir) - dot(v0, nee.dir)) / dot(nee.dir, nee.dir);
+    if (t < nee.tmin || t > nee.tmax) return -1;
+    V3 ip = nee.org + nee.dir * t;
+    V3 nn = lp.geom_normal;
+    V3 omega = ip - nee.org;
+    Real tau = dot(lp.position - nee.org, nn) / dot(omega, nn);
+    Real jac = length(tau * ((v1 - v0) - omega * (dot(v1 - v0, nn) / dot(omega, nn))));
+    const rb_shape& lshape = sc.shapes[lis.shape_id];
+    Real pdf_nee = (Real)(sc.light_pmf[lshape.light_id] / sc.light_areas[lshape.light_id]);
+    if (pmf <= 0 || jac <= 0 || pdf_nee <= 0) return -1;
+    sample_weight = 1 / (2 * expand * pmf * jac * pdf_nee);
+    V3 v0_p = v0 - ip;
+    V3 ed = normalize(v1 - v0);
+    edge_pt = ip + v0_p - dot(v0_p, ed) * ed - nee.org;
+    mwt = v1 - v0;
+    return selected;
+}
+
+// d(intersection point)/d(line parameter), src/edge.cpp:1829-1853
+RB_HD V3 intersect_jacobian(V3 org, V3 dir, V3 p, V3 n, V3 l) {
+    Real dn = dot(dir, n);
+    if (fabs(dn) < Real(1e-10)) return zero3();
+    Real t = -(dot(org, n) - dot(p, n)) / dn;
+    if (t <= 0) return zero3();
+    return t * (l - dir * (dot(l, n) / dn));
+}
+
+// Samples one silhouette edge as seen from path vertex `cur` (depth `depth`), traces the two sub-paths on either side
+// of it and accumulates the boundary-term gradient into the shading point position (d_position) and the two edge
+// vertices.  `smp` is the edge sampler positioned at this depth's first dimension; `d_color` is the raw d_image pixel.
+RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const VertexRec& cur, int depth, Sampler smp,
+                                V3 d_color, V3& d_position) {
+    const Real weight = Real(1) / Real(rp.spp);
+    double s_edge_sel = smp.next(), s_resample = smp.next(), s_component = smp.next(), s_t = smp.next();
+    Real min_rough = cur.min_rough;
+    // secondary edges are only sampled until the first rough bounce (src/edge.cpp:1396-1401)
+    if (min_rough > Real(1e-2)) return;
+    const rb_shape& shape = sc.shapes[cur.isect.shape_id];
+    const rb_material& mat = sc.materials[shape.material_id];
+    RayDiff rd;
+    SurfacePoint sp = make_surface_point(shape, cur.isect.tri_id, cur.ray, cur.rd_in, rd);
+    V3 wi = -cur.ray.dir;
+    // shadow ray of this vertex with its true length (src/edge.cpp:1377-1385)
+    const rb_shape& lshape = sc.shapes[cur.light.isect.shape_id];
+    SurfacePoint lp = sample_light_triangle(lshape, cur.light.isect.tri_id, cur.light.uv);
+    Ray nee;
+    nee.org = sp.position;
+    nee.dir = normalize(lp.position - sp.position);
+    nee.tmin = Real(1e-3);
+    nee.tmax = length(lp.position - sp.position);
+
+    V3 kd = mat_diffuse(mat, sp), ks = mat_specular(mat, sp);
+    Real wd = luminance(kd), ws = luminance(ks), wsum = wd + ws;
+    if (wsum <= 0) return;
+    Real pd = wd / wsum, ps = ws / wsum;
+    V3 n = sp.shading_frame.n;
+    if (mat.two_sided && dot(wi, n) < 0) n = -n;
+    V3 fx = normalize(wi - n * dot(wi, n));
+    V3 fy = cross(n, fx);
+    if (dot(wi, n) > 1 - Real(1e-6)) coordinate_system(n, fx, fy);
+    EdgeCtx c;
+    c.sc = &sc;
+    c.p = sp;
+    {
+        double iw = 1.0 / sc.cam.c2w[15];
+        c.cam_org = mk3((Real)(sc.cam.c2w[3] * iw), (Real)(sc.cam.c2w[7] * iw), (Real)(sc.cam.c2w[11] * iw));
+    }
+    Real roughness = rb_max(mat_roughness(mat, sp), min_rough);
+    Real m_pmf;
+    bool diffuse_lobe = s_component <= (double)pd;
+    if (diffuse_lobe) {
+        c.m_inv = m3_rows(fx, fy, n);
+        c.m = m3_inverse(c.m_inv);
+        m_pmf = pd;
+    } else {
+        // LTC fitted to the Blinn-Phong lobe, src/edge.cpp:803-814
+        Real theta = acos(dot(wi, sp.shading_frame.n));
+        int rid = rb_clampi(int(roughness * 127), 0, 127);
+        int tid = rb_clampi(int((theta / (RB_PI / 2)) * 127), 0, 127);
+        const float* t = sc.ltc_table + 9 * (rid + tid * 128);
+        M3 ltc;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) ltc.m[i][j] = t[3 * i + j];
+        c.m_inv = m3_mul(m3_inverse(ltc), m3_rows(fx, fy, n));
+        c.m = m3_inverse(c.m_inv);
+        m_pmf = ps;
+    }
+    int edge_id = -1;
+    Real edge_weight = 0;
+    V3 sample_p = zero3(), mwt = zero3();
+    Real edge_sel = (Real)s_edge_sel;
+    bool use_nee = false;
+    Real nee_pmf = 1;
+    bool diffuse_or_glossy = diffuse_lobe || roughness > Real(0.1);
+    if (diffuse_or_glossy) {
+        use_nee = s_edge_sel < 0.5;
+        if (roughness > Real(0.1)) nee_pmf = Real(0.5);
+        else nee_pmf = use_nee ? pd * Real(0.5) : 1 - pd * Real(0.5);
+    }
+    if (!use_nee) {
+        if (diffuse_or_glossy) edge_sel = (Real)((s_edge_sel - 0.5) * 2);
+        edge_id = sample_edge_hier(c, edge_sel, (Real)s_resample, edge_weight);
+        if (edge_id == -1 || edge_weight <= 0) return;
+        const Edge& e = sc.edges[edge_id];
+        if (!edge_is_silhouette(sc.shapes, sp.position, e)) return;
+        V3 a = mul(c.m_inv, edge_v0(sc.shapes, e) - sp.position), b = mul(c.m_inv, edge_v1(sc.shapes, e) - sp.position);
+        if (a.z <= 0 && b.z <= 0) return;
+        if (a.z < 0) a = (a * b.z - b * a.z) / (b.z - a.z);
+        if (b.z < 0) b = (a * b.z - b * a.z) / (b.z - a.z);
+        V3 wt = normalize(b - a);
+        Real l0 = dot(a, wt), l1 = dot(b, wt);
+        V3 vo = a - l0 * wt;
+        Real d = length(vo);
+        auto I = [&](Real l) { return (l / (d * (d * d + l * l)) + atan(l / d) / (d * d)) * vo.z + (l * l / (d * (d * d + l * l))) * wt.z; };
+        Real Il0 = I(l0), Il1 = I(l1);
+        Real norm = Il1 - Il0;
+        auto line_pdf = [&](Real l) {
+            Real ds2 = d * d + l * l;
+            return 2 * d * (vo + l * wt).z / (norm * ds2 * ds2);
+        };
+        // invert the line CDF by bisection-safeguarded Newton, src/edge.cpp:1618-1643
+        Real lb = l0, ub = l1;
+        if (lb > ub) {
+            Real tmp = lb;
+            lb = ub;
+            ub = tmp;
+        }
+        Real l = Real(0.5) * (lb + ub);
+        for (int it = 0; it < 20; it++) {
+            if (!(l >= lb && l <= ub)) l = Real(0.5) * (lb + ub);
+            Real value = (I(l) - Il0) / norm - (Real)s_t;
+            if (fabs(value) < Real(1e-5) || it == 19) break;
+            if (value > 0) ub = l; else lb = l;
+            l -= value / line_pdf(l);
+        }
+        Real lpdf = line_pdf(l);
+        if (!(lpdf > 0)) return;
+        sample_p = mul(c.m, vo + l * wt);
+        edge_weight /= (m_pmf * lpdf);
+        mwt = mul(c.m, wt);
+    } else {
+        edge_id = sample_edge_gather(c, nee, cur.light.isect, lp, (Real)s_resample, edge_weight, sample_p, mwt);
+        if (edge_id == -1 || edge_weight <= 0) return;
+    }
+    const Edge edge = sc.edges[edge_id];
+    V3 v0 = edge_v0(sc.shapes, edge), v1 = edge_v1(sc.shapes, edge);
+    V3 hpn = normalize(cross(v0 - sp.position, v1 - sp.position));
+    Real plen = length(sample_p);
+    Real offset = Real(1e-5) / plen;
+    V3 sdir = normalize(sample_p);
+    V3 f = bsdf_eval(mat, sp, wi, sdir, min_rough);
+    if (sum(f) < Real(1e-6)) return;
+    // ray differential of the two edge rays (src/edge.cpp:1703-1733)
+    RayDiff rd_e;
+    rd_e.org_dx = rd.org_dx;
+    rd_e.org_dy = rd.org_dy;
+    if (diffuse_lobe) {
+        rd_e.dir_dx = rd_e.dir_dy = mk3(Real(0.03), Real(0.03), Real(0.03));
+    } else {
+        V3 h = normalize(wi + sdir);
+        Real hz = dot(h, sp.shading_frame.n);
+        V3 dmdx = sp.dn_dx * hz, dmdy = sp.dn_dy * hz;
+        // (elementwise products, as in the reference: src/edge.cpp:1724-1730)
+        V3 ddn_dx = rd.dir_dx * h - wi * dmdx, ddn_dy = rd.dir_dy * h - wi * dmdy;
+        rd_e.dir_dx = rd.dir_dx - 2 * (-dot(wi, h) * sp.dn_dx + ddn_dx * h);
+        rd_e.dir_dy = rd.dir_dy - 2 * (-dot(wi, h) * sp.dn_dy + ddn_dy * h);
+    }
+    V3 nt = cur.thr * f * d_color * (edge_weight / nee_pmf);
+    // advance the sampler past this depth's 4 dimensions: both edge rays share the following light/bsdf samples
+    Isect eis[2];
+    SurfacePoint esp[2];
+    Ray eray[2];
+    bool hit[2];
+    int light_id[2] = {-1, -1};
+    for (int k = 0; k < 2; k++) {
+        eray[k].org = sp.position;
+        eray[k].dir = normalize(k == 0 ? sdir + offset * hpn : sdir - offset * hpn);
+        eray[k].tmin = Real(1e-3) * plen;
+        eray[k].tmax = INFINITY;
+        eis[k] = no_isect();
+        hit[k] = closest_hit(sc, eray[k], eis[k]);
+        if (hit[k]) {
+            RayDiff tmp;
+            esp[k] = make_surface_point(sc.shapes[eis[k].shape_id], eis[k].tri_id, eray[k], rd_e, tmp);
+            light_id[k] = sc.shapes[eis[k].shape_id].light_id;
+        }
+    }
+    bool hit_light = light_id[0] != -1 || light_id[1] != -1;
+    Real scale = 1;
+    if (use_nee) {
+        scale = hit_light ? Real(0.5) : Real(0);
+    } else if (hit_light && diffuse_or_glossy) {
+        scale = Real(0.5);
+    }
+    if (scale == 0) return;
+    V3 dp = zero3(), dv0 = zero3(), dv1 = zero3();
+    for (int k = 0; k < 2; k++) {
+        if (!hit[k]) continue;
+        V3 thr = (k == 0 ? nt : -nt) * scale;
+        // geometry term and Jacobians (Eq. 15-18), src/edge.cpp:1857-1898
+        V3 dir = esp[k].position - sp.position;
+        Real dist_sq = length_sq(dir);
+        if (dist_sq < Real(1e-8)) continue;
+        V3 ndir = dir / sqrt(dist_sq);
+        Real G = fabs(dot(esp[k].geom_normal, ndir)) / dist_sq;
+        V3 ij = intersect_jacobian(sp.position, sample_p, esp[k].position, esp[k].geom_normal, mwt);
+        Real line_jac = length(ij) / length(cross(esp[k].geom_normal, hpn));
+        Real dirac_jac = length(cross(v0 - sp.position, v1 - sp.position));
+        thr *= G * (line_jac / dirac_jac);
+        if (!finite3(thr)) continue;
+        // radiance carried by this side: emission at the hit + the remaining bounces
+        Real contrib = sum(weight * thr * hit_emission(sc, eis[k], esp[k], -eray[k].dir));
+        Sampler sub = smp;
+        V3 Lb = trace_bounces<false>(sc, sub, eray[k], rd_e, eis[k], thr, min_rough, depth + 1, rp.max_bounces, nullptr, 0, nullptr);
+        contrib += sum(weight * Lb);
+        if (contrib == 0) continue;
+        // Eq. 16 (with the errata), src/edge.cpp:2020-2033
+        V3 x = esp[k].position, p = sp.position;
+        V3 d0 = v0 - p, d1 = v1 - p;
+        dp += (cross(d1, d0) + cross(x - p, d1) + cross(d0, x - p)) * contrib;
+        dv0 += cross(d1, x - p) * contrib;
+        dv1 += cross(x - p, d0) * contrib;
+    }
+    d_position += dp;
+    float* dv = ds.shapes[edge.shape_id].vertices;
+    if (dv) {
+        agg_add3(dv + 3 * (size_t)edge.v0, dv0);
+        agg_add3(dv + 3 * (size_t)edge.v1, dv1);
+    }
+}

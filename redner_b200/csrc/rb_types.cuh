@@ -96,8 +96,16 @@ struct DevLight {
     int two_sided, directly_visible;
 };
 
-// Secondary-edge tree node (own layout; see rb_edge_tree.cuh)
-struct EdgeNode;
+// Secondary-edge tree node (own flat layout, 64 B; replaces the pointer-linked BVHNode3 / BVHNode6 of
+// src/edge_tree.h:14-30).  The camera-silhouette tree only uses the position box, the other tree also the box in
+// Hough space (src/edge_tree.cpp:23-66).  Leaf <=> edge_id >= 0.
+struct __align__(16) EdgeNode {
+    float pmin[3], pmax[3];
+    float dmin[3], dmax[3];
+    float wlen; // sum of length * exterior dihedral angle below this node
+    int left, right;
+    int edge_id;
+};
 
 struct DevScene {
     DevCamera cam;

@@ -106,7 +106,7 @@ def glossy_room(device, resolution=(128, 128), grad=True, textured=True):
     return api.Scene(cam, [floor, back, side, ball, l1, l2], [m_floor, m_wall, m_ball, m_light], lights)
 
 
-def random_soup(device, num_tris=2000, resolution=(256, 256), seed=3):
+def random_soup(device, num_tris=2000, resolution=(256, 256), seed=3, grad=False):
     """Random triangle soup under one light: BVH / traversal stress (many shapes' worth of edges, deep tree)."""
     g = torch.Generator().manual_seed(seed)
     c = (torch.rand(num_tris, 1, 3, generator=g) - 0.5) * torch.tensor([4.0, 2.5, 3.0]) + torch.tensor([0.0, 1.3, 0.5])
@@ -122,4 +122,4 @@ def random_soup(device, num_tris=2000, resolution=(256, 256), seed=3):
     return api.Scene(cam, [soup, floor, light], [m, m_l], [api.AreaLight(2, torch.tensor([30.0, 30.0, 30.0]))])
 
 
-SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room}
+SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup}

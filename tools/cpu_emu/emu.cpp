@@ -23,6 +23,8 @@ struct rb_scene {
     std::vector<DevLight> lights;
     HostLightTables lt;
     HostEdgeTables et;
+    HostEdgeTree tree;
+    std::vector<float> ltc;
     std::vector<BVHNode> nodes;
     std::vector<BVHTri> tris;
     std::vector<unsigned long long> sobol;
@@ -87,6 +89,7 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
     for (const rb_material& m : sc->materials)
         if (m.generic_texture.num_levels > 0) sc->max_generic = std::max(sc->max_generic, m.generic_texture.channels);
     DevScene& d = sc->dev;
+    d.edge_root_cs = d.edge_root_ncs = -1;
     d.shapes = sc->shapes.data();
     d.num_shapes = (int)sc->shapes.size();
     d.materials = sc->materials.data();
@@ -157,6 +160,20 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
         d.num_edges = (int)sc->et.edges.size();
         d.prim_edge_pmf = sc->et.prim_pmf.data();
         d.prim_edge_cdf = sc->et.prim_cdf.data();
+        d.edge_root_cs = d.edge_root_ncs = -1;
+        if (d.use_secondary_edge) {
+            host_build_edge_tree(sc->shapes, meshes, sc->et.edges, d.cam, sc->tree);
+            d.edge_nodes = sc->tree.nodes.data();
+            d.edge_root_cs = sc->tree.root_cs;
+            d.edge_root_ncs = sc->tree.root_ncs;
+            d.edge_bounds_expand = sc->tree.expand;
+            FILE* fl = fopen(RB_DATA_DIR "/ltc_blinn_phong_128x128x9_f32.bin", "rb");
+            if (!fl) { g_err = "emu: ltc table not found"; return 1; }
+            sc->ltc.resize(128 * 128 * 9);
+            if (fread(sc->ltc.data(), 4, sc->ltc.size(), fl) != sc->ltc.size()) { g_err = "emu: short ltc table"; return 1; }
+            fclose(fl);
+            d.ltc_table = sc->ltc.data();
+        }
     }
     *out = sc;
     return 0;
@@ -227,7 +244,7 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
             long long n_px = (long long)rp.vp_w * rp.vp_h;
             for (long long i = 0; i < n_px; i++)
                 for (int s = 0; s < rp.spp; s++) {
-                    primary_edge_sample(sc, ka, i, s, 0, acc);
+                    primary_edge_sample(sc, ka, i, s, primary_edge_dim_base(sc, rp), acc);
                     for (int k = 0; k < RB_CAM_ACC; k++) { cam_accum[k] += cam_f[k]; cam_f[k] = 0.f; }
                 }
         }
