@@ -188,6 +188,14 @@ int rb_scene_set_partition(rb_scene* scene, int part, int num_parts, int rows_pe
  * the render stream) spent inside the traced kernels. */
 int rb_scene_last_stats(const rb_scene* scene, int* num_kernel_launches, float* kernel_ms);
 
+/* Per-kernel device times of the last rb_render (CUDA events on the render stream), in launch order
+ * { k_forward, k_backward, k_primary_edge, k_finish_camera } (0 for kernels that did not run), the number of path
+ * vertices at which the last backward pass formed a radiance estimate and its number of primary hits (mean executed
+ * bounces per sample = path_vertices / (W*H*spp)). */
+int rb_scene_last_stage_stats(const rb_scene* scene, float* stage_ms4, double* path_vertices, double* primary_hits);
+/* Host wall-clock milliseconds rb_scene_create spent in { BVH build, light tables, edge list + edge tree }. */
+int rb_scene_build_ms(const rb_scene* scene, float* bvh_lights_edges3);
+
 const char* rb_last_error(void);
 const char* rb_version(void);
 

@@ -118,12 +118,28 @@ __global__ void __launch_bounds__(RB_BLOCK) k_backward(const __grid_constant__ D
     long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int nb = (rp.spp + L - 1) / L;
     VertexRec* recs = ka.records + (size_t)gtid * ka.rec_per_thread;
+    int n_vertices = 0, n_hits = 0;
     for (long long g = warp; g < groups; g += nwarps) {
         WorkItem w = warp_work(rp, L, ka.owned_rows, g);
         for (int b = 0; b < nb; b++) {
             int s = b * L + w.sample_lane;
-            if (w.valid && s < rp.spp) backward_sample(sc, ka, w.pixel, w.px, w.py, s, recs, cam_acc);
+            if (w.valid && s < rp.spp) {
+                int nv = backward_sample(sc, ka, w.pixel, w.px, w.py, s, recs, cam_acc);
+                if (nv >= 0) {
+                    n_hits++;
+                    n_vertices += nv;
+                }
+            }
         }
+    }
+    // statistics for the roofline accounting (mean executed bounces per sample)
+    for (int off = 16; off > 0; off >>= 1) {
+        n_vertices += __shfl_xor_sync(0xffffffffu, n_vertices, off);
+        n_hits += __shfl_xor_sync(0xffffffffu, n_hits, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&ka.ds.cam_accum[RB_CAM_ACC], (double)n_vertices);
+        atomicAdd(&ka.ds.cam_accum[RB_CAM_ACC + 1], (double)n_hits);
     }
     block_reduce_camera(cam_smem, ka.ds.cam_accum);
 }
@@ -237,22 +253,27 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
     RB_CUDA_OK(cudaGetDevice(&prev));
     RB_CUDA_OK(cudaSetDevice(scene->device));
     cudaStream_t stream = (cudaStream_t)stream_;
-    cudaEvent_t ev0, ev1;
-    RB_CUDA_OK(cudaEventCreate(&ev0));
-    RB_CUDA_OK(cudaEventCreate(&ev1));
+    // per-kernel CUDA events on the render stream: [0] start, [1] after k_forward, [2] after k_backward,
+    // [3] after k_primary_edge, [4] after k_finish_camera
+    cudaEvent_t ev[5];
+    for (int i = 0; i < 5; i++) RB_CUDA_OK(cudaEventCreate(&ev[i]));
     int launches = 0;
+    double host_stats[2] = {0, 0};
     std::vector<void*> temps;
     auto cleanup = [&]() {
         for (void* p : temps) cudaFreeAsync(p, stream);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
+        for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
         cudaSetDevice(prev);
     };
-    RB_CUDA_OK(cudaEventRecord(ev0, stream));
+    RB_CUDA_OK(cudaEventRecord(ev[0], stream));
     if (image != nullptr) {
         int grid = pick_grid((const void*)k_forward, scene->device, nullptr);
         k_forward<<<grid, RB_BLOCK, 0, stream>>>(scene->dev, ka);
         launches++;
+    }
+    RB_CUDA_OK(cudaEventRecord(ev[1], stream));
+    if (d_image == nullptr) {
+        for (int i = 2; i < 5; i++) RB_CUDA_OK(cudaEventRecord(ev[i], stream));
     }
     if (d_image != nullptr) {
         // device copies of the gradient descriptor
@@ -274,14 +295,14 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         temps.push_back(d_mats);
         RB_CUDA_OK(cudaMallocAsync((void**)&d_lights, nb_lights, stream));
         temps.push_back(d_lights);
-        RB_CUDA_OK(cudaMallocAsync((void**)&cam_accum, RB_CAM_ACC * sizeof(double), stream));
+        RB_CUDA_OK(cudaMallocAsync((void**)&cam_accum, (RB_CAM_ACC + 2) * sizeof(double), stream));
         temps.push_back(cam_accum);
         if (d_scene->num_shapes) RB_CUDA_OK(cudaMemcpyAsync(d_shapes, d_scene->shapes, d_scene->num_shapes * sizeof(rb_dshape), cudaMemcpyHostToDevice, stream));
         if (d_scene->num_materials)
             RB_CUDA_OK(cudaMemcpyAsync(d_mats, d_scene->materials, d_scene->num_materials * sizeof(rb_material), cudaMemcpyHostToDevice, stream));
         if (d_scene->num_lights)
             RB_CUDA_OK(cudaMemcpyAsync(d_lights, d_scene->light_intensity, d_scene->num_lights * sizeof(float*), cudaMemcpyHostToDevice, stream));
-        RB_CUDA_OK(cudaMemsetAsync(cam_accum, 0, RB_CAM_ACC * sizeof(double), stream));
+        RB_CUDA_OK(cudaMemsetAsync(cam_accum, 0, (RB_CAM_ACC + 2) * sizeof(double), stream));
         ka.ds.shapes = d_shapes;
         ka.ds.materials = d_mats;
         ka.ds.light_intensity = d_lights;
@@ -295,22 +316,31 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         ka.records = recs;
         k_backward<<<grid, RB_BLOCK, 0, stream>>>(scene->dev, ka);
         launches++;
+        RB_CUDA_OK(cudaEventRecord(ev[2], stream));
         if (scene->dev.use_primary_edge && scene->dev.num_edges > 0 && scene->dev.prim_edge_cdf != nullptr) {
             int grid_e = pick_grid((const void*)k_primary_edge, scene->device, nullptr);
             int dim_base = primary_edge_dim_base(scene->dev, rp);
             k_primary_edge<<<grid_e, RB_BLOCK, 0, stream>>>(scene->dev, ka, dim_base);
             launches++;
         }
+        RB_CUDA_OK(cudaEventRecord(ev[3], stream));
         k_finish_camera<<<1, 32, 0, stream>>>(scene->dev.cam, cam_accum, d_scene->camera);
         launches++;
+        RB_CUDA_OK(cudaEventRecord(ev[4], stream));
+        RB_CUDA_OK(cudaMemcpyAsync(host_stats, cam_accum + RB_CAM_ACC, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
-    RB_CUDA_OK(cudaEventRecord(ev1, stream));
     cudaError_t err = cudaStreamSynchronize(stream);
     if (err == cudaSuccess) err = cudaGetLastError();
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventElapsedTime(&ms, ev[0], ev[4]);
     scene->last_launches = launches;
     scene->last_kernel_ms = ms;
+    for (int i = 0; i < 4; i++) {
+        scene->last_stage_ms[i] = 0.f;
+        if (err == cudaSuccess) cudaEventElapsedTime(&scene->last_stage_ms[i], ev[i], ev[i + 1]);
+    }
+    scene->last_path_vertices = host_stats[0];
+    scene->last_primary_hits = host_stats[1];
     cleanup();
     if (err != cudaSuccess) {
         rb_set_error(std::string("rb_render: kernel failure: ") + cudaGetErrorString(err));

@@ -73,7 +73,8 @@ RB_D V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, in
 }
 
 // Adjoint of one pixel sample.  `recs` is this thread's private record array (max_bounces + 2 entries).
-RB_D void backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, int px, int py, int s, VertexRec* recs, CamAcc& cam_acc) {
+// Returns the number of path vertices at which a radiance estimate was formed (-1 if the primary ray missed).
+RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, int px, int py, int s, VertexRec* recs, CamAcc& cam_acc) {
     const RenderParams& rp = ka.rp;
     const DevDScene& ds = ka.ds;
     const Real weight = Real(1) / Real(rp.spp);
@@ -84,7 +85,7 @@ RB_D void backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, i
     RayDiff rd;
     primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd);
     Isect is = no_isect();
-    if (!closest_hit(sc, ray, is)) return;
+    if (!closest_hit(sc, ray, is)) return -1;
     const float* dpx = ka.d_image + (size_t)rp.nd * pixel + rp.rad_dim;
     V3 d_contrib = weight * mk3(dpx[0], dpx[1], dpx[2]);
     int nrec = 0;
@@ -140,6 +141,7 @@ RB_D void backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, i
         rb_red_add(&ka.screen_grad[2 * (size_t)pixel + 0], (float)d_screen.x);
         rb_red_add(&ka.screen_grad[2 * (size_t)pixel + 1], (float)d_screen.y);
     }
+    return nrec;
 }
 
 // ---- primary edges ----

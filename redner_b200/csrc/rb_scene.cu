@@ -515,5 +515,21 @@ extern "C" int rb_scene_last_stats(const rb_scene* sc, int* launches, float* ms)
     return 0;
 }
 
+extern "C" int rb_scene_last_stage_stats(const rb_scene* sc, float* stage_ms4, double* path_vertices, double* primary_hits) {
+    if (!sc) return 1;
+    if (stage_ms4)
+        for (int i = 0; i < 4; i++) stage_ms4[i] = sc->last_stage_ms[i];
+    if (path_vertices) *path_vertices = sc->last_path_vertices;
+    if (primary_hits) *primary_hits = sc->last_primary_hits;
+    return 0;
+}
+extern "C" int rb_scene_build_ms(const rb_scene* sc, float* bvh_lights_edges3) {
+    if (!sc || !bvh_lights_edges3) return 1;
+    bvh_lights_edges3[0] = sc->build_ms_bvh;
+    bvh_lights_edges3[1] = sc->build_ms_lights;
+    bvh_lights_edges3[2] = sc->build_ms_edges;
+    return 0;
+}
+
 // compute_num_channels, src/channels.cpp:42-113
 extern "C" int rb_compute_num_channels(const int* channels, int n, int max_generic) { return host_compute_num_channels(channels, n, max_generic); }

@@ -342,6 +342,18 @@ class Scene:  # src/redner.cpp:62-73, src/scene.cpp:63-307
         self._lib.rb_scene_last_stats(self._handle, C.byref(n), C.byref(ms))
         return n.value, ms.value
 
+    def last_stage_stats(self):
+        """({kernel name: ms}, path_vertices, primary_hits) of the last render on this scene."""
+        ms = (C.c_float * 4)()
+        v, h = C.c_double(0), C.c_double(0)
+        self._lib.rb_scene_last_stage_stats(self._handle, ms, C.byref(v), C.byref(h))
+        return dict(zip(("k_forward", "k_backward", "k_primary_edge", "k_finish_camera"), list(ms))), v.value, h.value
+
+    def build_ms(self):
+        ms = (C.c_float * 3)()
+        self._lib.rb_scene_build_ms(self._handle, ms)
+        return dict(zip(("bvh", "lights", "edges"), list(ms)))
+
     def __del__(self):
         try:
             if self._handle is not None and self._handle.value:

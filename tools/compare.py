@@ -62,7 +62,7 @@ def run(backend, device, name, res, spp, mb, edges, sampler, seed, do_backward=T
         torch.cuda.synchronize()
     t1 = time.time()
     g = {}
-    if do_backward:
+    if do_backward and img.requires_grad:
         img.pow(2).sum().backward()
         if device.type == "cuda":
             torch.cuda.synchronize()

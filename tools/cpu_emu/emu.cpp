@@ -185,6 +185,13 @@ extern "C" int rb_scene_set_partition(rb_scene* sc, int part, int num_parts, int
     sc->part = part; sc->num_parts = num_parts; sc->rps = rps;
     return 0;
 }
+extern "C" int rb_scene_last_stage_stats(const rb_scene*, float* ms, double* v, double* h) {
+    if (ms) for (int i = 0; i < 4; i++) ms[i] = 0;
+    if (v) *v = 0;
+    if (h) *h = 0;
+    return 0;
+}
+extern "C" int rb_scene_build_ms(const rb_scene*, float* ms) { ms[0] = ms[1] = ms[2] = 0; return 0; }
 extern "C" int rb_scene_last_stats(const rb_scene*, int* n, float* ms) {
     if (n) *n = 0;
     if (ms) *ms = 0;
