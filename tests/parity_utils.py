@@ -1,0 +1,78 @@
+"""Shared helpers of the parity tests and the golden generator: the list of golden cases and one function that
+renders a case (image + gradients of loss = sum(img^2)) with ANY module exposing the `redner` surface."""
+import os
+
+import numpy as np
+import torch
+
+import scenes
+from redner_b200 import api
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# edges: bit 0 primary edge sampling, bit 1 secondary edge sampling
+CASES = {
+    # C1 geometry (tests/test_single_triangle.py), primary-edge gradients are sample-exact
+    "c1_single_triangle_sobol": dict(scene="single_triangle", res=64, spp=4, mb=1, sampler="sobol", edges=1, seed=1),
+    "c1_single_triangle_pcg": dict(scene="single_triangle", res=48, spp=4, mb=1, sampler="independent", edges=0, seed=3),
+    # C2 geometry (tests/test_shadow_blocker.py) without edge sampling: every gradient is sample-exact
+    "c2_shadow_blocker_sobol": dict(scene="shadow_blocker", res=96, spp=16, mb=1, sampler="sobol", edges=0, seed=2),
+    # glossy textured room: specular lobe, shading normals, uvs, mip-mapped textures, two lights, 2 bounces
+    "glossy_room_sobol_mb2": dict(scene="glossy_room", res=48, spp=8, mb=2, sampler="sobol", edges=0, seed=5),
+    "glossy_room_pcg_mb3": dict(scene="glossy_room", res=32, spp=4, mb=3, sampler="independent", edges=0, seed=7),
+}
+STAT_CASES = {
+    # secondary-edge (shadow) gradient of the blocker: mean over seeds +- standard error
+    "c2_shadow_blocker_secondary_stat": dict(scene="shadow_blocker", res=64, spp=64, mb=1, sampler="sobol", edges=3, seeds=list(range(1, 9)),
+                                             keys=["shape1.vertices"]),
+    "glossy_room_secondary_stat": dict(scene="glossy_room", res=32, spp=32, mb=2, sampler="sobol", edges=3, seeds=list(range(1, 7)),
+                                       keys=["shape3.vertices"]),
+}
+
+
+def collect_grads(scene):
+    out = {}
+    cam = scene.camera
+    for k in ("position", "look_at", "up"):
+        t = getattr(cam, k)
+        if t is not None and t.grad is not None:
+            out["cam." + k] = t.grad.detach().cpu().clone()
+    for i, s in enumerate(scene.shapes):
+        for k in ("vertices", "uvs", "normals", "colors"):
+            t = getattr(s, k)
+            if t is not None and t.grad is not None:
+                out["shape%d.%s" % (i, k)] = t.grad.detach().cpu().clone()
+    for i, m in enumerate(scene.materials):
+        for k in ("diffuse_reflectance", "specular_reflectance", "roughness"):
+            t = getattr(m, k)
+            if t is not None and t.texels.grad is not None:
+                out["mat%d.%s" % (i, k)] = t.texels.grad.detach().cpu().clone()
+    for i, l in enumerate(scene.area_lights):
+        if l.intensity.grad is not None:
+            out["light%d.intensity" % i] = l.intensity.grad.detach().cpu().clone()
+    return out
+
+
+def render_case(backend, device, cfg, seed, backward=True):
+    sc = scenes.SCENES[cfg["scene"]](device, resolution=(cfg["res"], cfg["res"]))
+    st = backend.SamplerType.sobol if cfg["sampler"] == "sobol" else backend.SamplerType.independent
+    args = api.RenderFunction.serialize_scene(sc, cfg["spp"], cfg["mb"], sampler_type=st, device=device, backend=backend,
+                                              use_primary_edge_sampling=bool(cfg["edges"] & 1),
+                                              use_secondary_edge_sampling=bool(cfg["edges"] & 2))
+    img = api.RenderFunction.apply(seed, *args)
+    grads = {}
+    if backward and img.requires_grad:
+        img.pow(2).sum().backward()
+        grads = collect_grads(sc)
+    return img.detach().cpu(), grads
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    n = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / n) if n > 0 else float(np.linalg.norm(a - b))
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
