@@ -20,7 +20,7 @@ RB_D void rb_red_add(float* addr, float v) { atomicAdd(addr, v); }
 // Combine `n` consecutive floats (n <= 9) across the lanes of the current convergence group that
 // have the same `addr`, then the group leader adds them to addr[0..n).
 template <int N>
-RB_D void warp_agg_add(float* addr, const float (&val)[N]) {
+RB_DFN void warp_agg_add(float* addr, const float (&val)[N]) {
     unsigned active = __activemask();
     unsigned peers = __match_any_sync(active, (unsigned long long)addr);
     int lane = threadIdx.x & 31;

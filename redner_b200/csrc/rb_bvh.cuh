@@ -65,7 +65,7 @@ RB_D float box_test(const BoxRay& r, float lox, float hix, float loy, float hiy,
 }
 
 template <bool ANY_HIT>
-RB_D bool bvh_trace(const DevScene& sc, const Ray& ray, int& shape_id, int& tri_id, float& t_hit) {
+RB_DFN bool bvh_trace(const DevScene& sc, const Ray& ray, int& shape_id, int& tri_id, float& t_hit) {
     shape_id = -1;
     tri_id = -1;
     float tnear = (float)ray.tmin, tfar = (float)ray.tmax;

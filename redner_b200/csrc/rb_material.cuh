@@ -39,7 +39,7 @@ RB_HD Real tex_level(const rb_texture& t, V2 du, V2 dv, Real& fu, Real& fv) {
     return log2(rb_max(rb_max(fu, fv), Real(1e-8)));
 }
 // out[0..nch)
-RB_HD void tex_eval(const rb_texture& t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, Real* out) {
+RB_FN void tex_eval(const rb_texture& t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, Real* out) {
     if (tex_is_constant(t)) {
         for (int c = 0; c < nch; c++) out[c] = t.texels[0][c];
         return;
@@ -73,7 +73,7 @@ RB_D void d_bilerp(const float* tex, float* d_tex, int nch, int c, const BilerpT
     d_u += d_val * (-ff * (1 - b.v) + cf * (1 - b.v) - fc * b.v + cc * b.v);
     d_v += d_val * (-ff * (1 - b.u) - cf * b.u + fc * (1 - b.u) + cc * b.u);
 }
-RB_D void d_tex_eval(const rb_texture& t, const rb_texture& d_t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, const Real* d_out, V2& d_uv_,
+RB_DFN void d_tex_eval(const rb_texture& t, const rb_texture& d_t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, const Real* d_out, V2& d_uv_,
                      V2& d_du_dxy_, V2& d_dv_dxy_) {
     if (tex_is_constant(t)) {
         if (nch == 3) {
@@ -154,7 +154,7 @@ RB_HD bool mat_has_normal_map(const rb_material& m) { return m.normal_map.num_le
 RB_HD Real roughness_to_phong(Real r) { return rb_max(2 / r - 2, Real(0)); }
 RB_HD Real d_roughness_to_phong(Real r, Real d_e) { return (r > 0 && r <= 1) ? -2 * d_e / rb_sq(r) : Real(0); }
 
-RB_HD Frame perturb_shading_frame(const rb_material& m, const SurfacePoint& p) {
+RB_FN Frame perturb_shading_frame(const rb_material& m, const SurfacePoint& p) {
     V3 n_local = 2 * mat_normal_tex(m, p) - mk3(1, 1, 1);
     V3 pn = normalize(to_world(p.shading_frame, n_local));
     V3 px = normalize(p.dpdu - pn * dot(pn, p.dpdu));
@@ -195,7 +195,7 @@ RB_HD Real smith_g1(V3 v, V3 n, Real roughness) {
     return (Real(3.535) * a + Real(2.181) * a2) / (1 + Real(2.276) * a + Real(2.577) * a2);
 }
 
-RB_HD V3 bsdf_eval(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough) {
+RB_FN V3 bsdf_eval(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough) {
     BsdfCtx c = bsdf_ctx(m, p);
     Real geom_wi = dot(c.geom_n, wi), geom_wo = dot(c.geom_n, wo);
     Real sh_wi = fabs(dot(c.frame.n, wi)), sh_wo = fabs(dot(c.frame.n, wo));
@@ -223,7 +223,7 @@ RB_HD V3 bsdf_eval(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, Re
     return diffuse + spec;
 }
 
-RB_HD Real bsdf_pdf(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough) {
+RB_FN Real bsdf_pdf(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough) {
     BsdfCtx c = bsdf_ctx(m, p);
     Real geom_wi = dot(c.geom_n, wi), geom_wo = dot(c.geom_n, wo);
     Real sh_wo = fabs(dot(c.frame.n, wo));
@@ -258,7 +258,7 @@ RB_HD Real bsdf_pdf(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, R
 
 // Returns the sampled direction (zero vector when sampling fails).  `w_sel` is the lobe-selection sample kept in
 // double so that the decision agrees with the reference's double comparison.
-RB_HD V3 bsdf_sample_dir(const rb_material& m, const SurfacePoint& p, V3 wi, V2 suv, double w_sel, Real min_rough, const RayDiff& wi_diff,
+RB_FN V3 bsdf_sample_dir(const rb_material& m, const SurfacePoint& p, V3 wi, V2 suv, double w_sel, Real min_rough, const RayDiff& wi_diff,
                          RayDiff& wo_diff, Real& next_min_rough) {
     next_min_rough = min_rough;
     BsdfCtx c = bsdf_ctx(m, p);
@@ -310,7 +310,7 @@ RB_HD V3 bsdf_sample_dir(const rb_material& m, const SurfacePoint& p, V3 wi, V2 
 }
 
 // Adjoint of bsdf_eval with respect to material textures, the shading point, wi and wo.
-RB_D void d_bsdf_eval(const rb_material& m, const rb_material& d_m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough, V3 d_out,
+RB_DFN void d_bsdf_eval(const rb_material& m, const rb_material& d_m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough, V3 d_out,
                       SurfacePoint& d_p, V3& d_wi, V3& d_wo) {
     BsdfCtx c = bsdf_ctx(m, p);
     const V3 n = c.frame.n;

@@ -21,6 +21,10 @@ typedef float Real;
 
 #define RB_HD __host__ __device__ __forceinline__
 #define RB_D __device__ __forceinline__
+// Out-of-line functions: the differentiable path tracer is far larger than the SM instruction caches (L0 6 KB / L1.5 32 KB),
+// so the big building blocks are real calls that every kernel and every call site shares instead of being inlined N times.
+#define RB_FN inline __host__ __device__ __noinline__
+#define RB_DFN inline __device__ __noinline__
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846

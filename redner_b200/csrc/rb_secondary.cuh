@@ -65,7 +65,7 @@ RB_HD bool node_contains(const EdgeNode& n, V3 p) {
     return p.x >= n.pmin[0] && p.x <= n.pmax[0] && p.y >= n.pmin[1] && p.y <= n.pmax[1] && p.z >= n.pmin[2] && p.z <= n.pmax[2];
 }
 // Upper bound of the (linearly transformed) cosine lobe over a position box, src/edge.cpp:838-875
-RB_D Real ltc_bound(const EdgeNode& n, const EdgeCtx& c) {
+RB_DFN Real ltc_bound(const EdgeNode& n, const EdgeCtx& c) {
     V3 dir = mk3(0, 0, 1);
     if (!node_contains(n, c.p.position)) {
         V3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
@@ -105,7 +105,7 @@ RB_D Real node_importance(const EdgeNode& n, bool is6d, const EdgeCtx& c) {
     return brdf * n.wlen / rb_max(length(center - c.p.position), Real(1e-3));
 }
 // Integral of the transformed cosine along the (clipped) edge, src/edge.cpp:951-983
-RB_D Real edge_ltc_integral(V3 v0, V3 v1, const EdgeCtx& c) {
+RB_DFN Real edge_ltc_integral(V3 v0, V3 v1, const EdgeCtx& c) {
     if (!(length_sq(v1 - v0) > Real(1e-10))) return 0;
     V3 a = mul(c.m_inv, v0 - c.p.position), b = mul(c.m_inv, v1 - c.p.position);
     if (!(a.z > 0 || b.z > 0)) return 0;
@@ -179,7 +179,7 @@ RB_D void split_samples(int num, Real prob0, Real& u, int& n0, int& n1) {
     }
 }
 // 16 correlated stochastic descents through both trees followed by reservoir resampling among the reached leaves.
-RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sample_weight) {
+RB_DFN int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sample_weight) {
     const DevScene& sc = *c.sc;
     StackH stack[RB_EDGE_STACK_H];
     int sp = 0;
@@ -231,7 +231,7 @@ RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sampl
     return selected;
 }
 // Gather all silhouette edges whose billboard the shadow ray crosses and pick one by reservoir resampling.
-RB_D int sample_edge_gather(const EdgeCtx& c, const Ray& nee, const Isect& lis, const SurfacePoint& lp, Real resample_u, Real& sample_weight,
+RB_DFN int sample_edge_gather(const EdgeCtx& c, const Ray& nee, const Isect& lis, const SurfacePoint& lp, Real resample_u, Real& sample_weight,
                             V3& edge_pt, V3& mwt) {
     const DevScene& sc = *c.sc;
     int stack[RB_EDGE_STACK_L];
@@ -306,7 +306,7 @@ RB_HD V3 intersect_jacobian(V3 org, V3 dir, V3 p, V3 n, V3 l) {
 // Samples one silhouette edge as seen from path vertex `cur` (depth `depth`), traces the two sub-paths on either side
 // of it and accumulates the boundary-term gradient into the shading point position (d_position) and the two edge
 // vertices.  `smp` is the edge sampler positioned at this depth's first dimension; `d_color` is the raw d_image pixel.
-RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const VertexRec& cur, int depth, Sampler smp,
+RB_DFN void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const VertexRec& cur, int depth, Sampler smp,
                                 V3 d_color, V3& d_position) {
     const Real weight = Real(1) / Real(rp.spp);
     double s_edge_sel = smp.next(), s_resample = smp.next(), s_component = smp.next(), s_t = smp.next();
