@@ -10,30 +10,27 @@
 #ifdef RB_CPU_EMU
 // host-compiled debug emulator (tools/cpu_emu): single "lane", plain adds
 RB_D void rb_red_add(float* addr, float v) { *addr += v; }
-template <int N>
-RB_D void warp_agg_add(float* addr, const float (&val)[N]) {
-    for (int i = 0; i < N; i++) addr[i] += val[i];
-}
+RB_D void warp_agg_add3(float* addr, float x, float y, float z) { addr[0] += x; addr[1] += y; addr[2] += z; }
 #else
-RB_D void rb_red_add(float* addr, float v) { atomicAdd(addr, v); }
+RB_D void rb_red_add(float* addr, float v) { atomicAdd(addr, v); } // result unused -> RED.E.ADD.F32 (fire and forget)
+// (A per-block shared-memory cache in front of the REDs was tried and measured 1.4x - 4.6x SLOWER on the backward kernel:
+//  the 64-bit CAS + shared atomic per scalar costs more than a fire-and-forget L2 reduction; see DESIGN.md.)
 
-// Combine `n` consecutive floats (n <= 9) across the lanes of the current convergence group that
-// have the same `addr`, then the group leader adds them to addr[0..n).
-template <int N>
-RB_DFN void warp_agg_add(float* addr, const float (&val)[N]) {
+// Combine up to three consecutive floats across the lanes of the current convergence group that target the same `addr`;
+// the group leader issues the reductions.  Must stay INLINE: inside a real function the callers' lanes are not
+// reconverged, __activemask() degenerates to single lanes and every lane issues its own atomics (measured: 7x slower).
+RB_D void warp_agg_add3(float* addr, float x, float y, float z) {
     unsigned active = __activemask();
     unsigned peers = __match_any_sync(active, (unsigned long long)addr);
     int lane = threadIdx.x & 31;
-    float v[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) v[i] = val[i];
     int n = __popc(peers);
     if (n > 1) {
         if (peers == 0xffffffffu) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-                for (int i = 0; i < N; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+                x += __shfl_xor_sync(0xffffffffu, x, off);
+                y += __shfl_xor_sync(0xffffffffu, y, off);
+                z += __shfl_xor_sync(0xffffffffu, z, off);
             }
         } else {
             int rank = __popc(peers & ((1u << lane) - 1u));
@@ -41,30 +38,24 @@ RB_DFN void warp_agg_add(float* addr, const float (&val)[N]) {
                 int src_rank = rank + off;
                 bool take = (src_rank < n) && ((rank & (2 * off - 1)) == 0);
                 int src_lane = take ? (int)__fns(peers, 0, src_rank + 1) : lane;
-#pragma unroll
-                for (int i = 0; i < N; i++) {
-                    float o = __shfl_sync(peers, v[i], src_lane);
-                    if (take) v[i] += o;
+                float ox = __shfl_sync(peers, x, src_lane), oy = __shfl_sync(peers, y, src_lane), oz = __shfl_sync(peers, z, src_lane);
+                if (take) {
+                    x += ox;
+                    y += oy;
+                    z += oz;
                 }
             }
         }
     }
     if (lane == __ffs(peers) - 1) {
-#pragma unroll
-        for (int i = 0; i < N; i++)
-            if (v[i] != 0.f) rb_red_add(addr + i, v[i]);
+        if (x != 0.f) rb_red_add(addr, x);
+        if (y != 0.f) rb_red_add(addr + 1, y);
+        if (z != 0.f) rb_red_add(addr + 2, z);
     }
 }
 #endif // RB_CPU_EMU
-RB_D void agg_add3(float* addr, V3 v) {
-    float a[3] = {(float)v.x, (float)v.y, (float)v.z};
-    warp_agg_add<3>(addr, a);
-}
-RB_D void agg_add2(float* addr, V2 v) {
-    float a[2] = {(float)v.x, (float)v.y};
-    warp_agg_add<2>(addr, a);
-}
-RB_D void agg_add1(float* addr, Real v) {
-    float a[1] = {(float)v};
-    warp_agg_add<1>(addr, a);
-}
+// NOTE: a zero component is never written, so the 1- and 2-component variants may pass 0 for the unused lanes of the
+// triple without touching memory beyond their target.
+RB_D void agg_add3(float* addr, V3 v) { warp_agg_add3(addr, (float)v.x, (float)v.y, (float)v.z); }
+RB_D void agg_add2(float* addr, V2 v) { warp_agg_add3(addr, (float)v.x, (float)v.y, 0.f); }
+RB_D void agg_add1(float* addr, Real v) { warp_agg_add3(addr, (float)v, 0.f, 0.f); }

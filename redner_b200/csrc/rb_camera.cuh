@@ -21,7 +21,7 @@ RB_HD D3 d3_normalize(D3 v) {
     return d3(v.x / l, v.y / l, v.z / l);
 }
 
-RB_FN void cam_sample_primary(const DevCamera& cam, double sx, double sy, D3& org, D3& dir) {
+RB_HD void cam_sample_primary(const DevCamera& cam, double sx, double sy, D3& org, D3& dir) {
     const double* C = cam.c2w;
     const double* I = cam.intr_inv;
     double aspect = double(cam.width) / double(cam.height);
@@ -115,7 +115,7 @@ struct CamAcc {
 
 // Adjoint of cam_sample_primary w.r.t. camera parameters (screen-position gradients are only needed for
 // distortion / screen_gradient_image; the latter is accumulated by the caller through d_screen).
-RB_DFN void d_cam_sample_primary(const DevCamera& cam, Real sx, Real sy, const DRay& d_ray, CamAcc& acc, V2* d_screen) {
+RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx, Real sy, const DRay& d_ray, CamAcc& acc, V2* d_screen) {
     M4 C = cam_m4(cam.c2w);
     M3 I = cam_m3(cam.intr_inv);
     Real aspect = Real(cam.width) / Real(cam.height);
@@ -210,7 +210,7 @@ RB_D void d_cam_to_screen(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc&
     acc.add_intr(d_K);
     d_pt += mul_t(d_ip, K);
 }
-RB_DFN void d_cam_project(const DevCamera& cam, V3 p0, V3 p1, Real dp0x, Real dp0y, Real dp1x, Real dp1y, CamAcc& acc, V3& d_p0,
+RB_D void d_cam_project(const DevCamera& cam, V3 p0, V3 p1, Real dp0x, Real dp0y, Real dp1x, Real dp1y, CamAcc& acc, V3& d_p0,
                         V3& d_p1) {
     M4 W = cam_m4(cam.w2c);
     V3 a = xfm_point(W, p0), b = xfm_point(W, p1);

@@ -29,7 +29,7 @@ RB_HD V3 edge_opposite1(const rb_shape* shapes, const Edge& e) {
     }
     return b;
 }
-RB_FN bool edge_is_silhouette(const rb_shape* shapes, V3 p, const Edge& e) {
+RB_HD bool edge_is_silhouette(const rb_shape* shapes, V3 p, const Edge& e) {
     V3 v0 = edge_v0(shapes, e), v1 = edge_v1(shapes, e);
     if (e.f0 == -1 || e.f1 == -1) {
         if (e.f0 != -1) {

@@ -22,6 +22,12 @@
 #include "rb_scene.cuh"
 
 #define RB_BLOCK 128
+#ifndef RB_MIN_BLOCKS_FWD
+#define RB_MIN_BLOCKS_FWD 4
+#endif
+#ifndef RB_MIN_BLOCKS_BWD
+#define RB_MIN_BLOCKS_BWD 4
+#endif
 
 // j-th owned row -> viewport row, for the round-robin stripe partition
 RB_D int owned_row_to_row(const RenderParams& rp, int j) {
@@ -59,7 +65,7 @@ RB_D WorkItem warp_work(const RenderParams& rp, int L, int owned_rows, long long
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(RB_BLOCK) k_forward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_FWD) k_forward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     const RenderParams& rp = ka.rp;
     const int L = ka.lanes_per_pixel;
     const int P = 32 / L;
@@ -102,7 +108,7 @@ RB_D void block_reduce_camera(float* cam_smem, double* cam_accum) {
     }
 }
 
-__global__ void __launch_bounds__(RB_BLOCK) k_backward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_BWD) k_backward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     __shared__ float cam_smem[RB_CAM_ACC * RB_BLOCK];
     for (int k = 0; k < RB_CAM_ACC; k++) cam_smem[k * RB_BLOCK + threadIdx.x] = 0.f;
     CamAcc cam_acc;
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(RB_BLOCK) k_backward(const __grid_constant__ D
 
 // ------------------------------------------------------------------------------------------------ primary edges
 // One thread per (edge sample i, spp sample s).
-__global__ void __launch_bounds__(RB_BLOCK) k_primary_edge(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka, int dim_base) {
+__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_BWD) k_primary_edge(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka, int dim_base) {
     __shared__ float cam_smem[RB_CAM_ACC * RB_BLOCK];
     for (int k = 0; k < RB_CAM_ACC; k++) cam_smem[k * RB_BLOCK + threadIdx.x] = 0.f;
     CamAcc cam_acc;

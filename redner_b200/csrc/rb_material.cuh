@@ -38,12 +38,13 @@ RB_HD Real tex_level(const rb_texture& t, V2 du, V2 dv, Real& fu, Real& fv) {
     fv = length(dv) * t.height[0];
     return log2(rb_max(rb_max(fu, fv), Real(1e-8)));
 }
-// out[0..nch)
-RB_FN void tex_eval(const rb_texture& t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, Real* out) {
-    if (tex_is_constant(t)) {
-        for (int c = 0; c < nch; c++) out[c] = t.texels[0][c];
-        return;
-    }
+// Mip-mapped (trilinear) fetch; out of line: ~15 inlined copies per kernel otherwise.  out[0..nch)
+#ifndef RB_INLINE_TEX
+#define RB_TEX_FN RB_FN
+#else
+#define RB_TEX_FN RB_HD
+#endif
+RB_TEX_FN void tex_eval_mip(const rb_texture& t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, Real* out) {
     Real sx = t.uv_scale[0], sy = t.uv_scale[1];
     V2 uv = mk2(uv_.x * sx, uv_.y * sy);
     V2 du = du_dxy_ * sx, dv = dv_dxy_ * sy;
@@ -63,6 +64,13 @@ RB_FN void tex_eval(const rb_texture& t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_
         }
     }
 }
+RB_HD void tex_eval(const rb_texture& t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, Real* out) {
+    if (tex_is_constant(t)) {
+        for (int c = 0; c < nch; c++) out[c] = t.texels[0][c];
+        return;
+    }
+    tex_eval_mip(t, nch, uv_, du_dxy_, dv_dxy_, out);
+}
 // Adjoint of one bilinear tap: scatters into the gradient mip level and returns d(u), d(v).
 RB_D void d_bilerp(const float* tex, float* d_tex, int nch, int c, const BilerpTap& b, Real d_val, Real& d_u, Real& d_v) {
     Real ff = tex[nch * b.i_ff + c], cf = tex[nch * b.i_cf + c], fc = tex[nch * b.i_fc + c], cc = tex[nch * b.i_cc + c];
@@ -73,16 +81,12 @@ RB_D void d_bilerp(const float* tex, float* d_tex, int nch, int c, const BilerpT
     d_u += d_val * (-ff * (1 - b.v) + cf * (1 - b.v) - fc * b.v + cc * b.v);
     d_v += d_val * (-ff * (1 - b.u) - cf * b.u + fc * (1 - b.u) + cc * b.u);
 }
-RB_DFN void d_tex_eval(const rb_texture& t, const rb_texture& d_t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, const Real* d_out, V2& d_uv_,
-                     V2& d_du_dxy_, V2& d_dv_dxy_) {
-    if (tex_is_constant(t)) {
-        if (nch == 3) {
-            agg_add3(d_t.texels[0], mk3(d_out[0], d_out[1], d_out[2]));
-        } else {
-            for (int c = 0; c < nch; c++) agg_add1(&d_t.texels[0][c], d_out[c]);
-        }
-        return;
-    }
+struct TexAdjoint { // returned by value so that the caller's SurfacePoint adjoint can stay in registers
+    V2 d_uv, d_du_dxy, d_dv_dxy;
+};
+RB_D TexAdjoint d_tex_eval_mip(const rb_texture& t, const rb_texture& d_t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, Real d0, Real d1, Real d2) {
+    Real d_out[3] = {d0, d1, d2};
+    V2 d_uv_ = zero2(), d_du_dxy_ = zero2(), d_dv_dxy_ = zero2();
     Real sx = t.uv_scale[0], sy = t.uv_scale[1];
     V2 uv = mk2(uv_.x * sx, uv_.y * sy);
     V2 du = du_dxy_ * sx, dv = dv_dxy_ * sy;
@@ -127,6 +131,26 @@ RB_DFN void d_tex_eval(const rb_texture& t, const rb_texture& d_t, int nch, V2 u
     d_dv_dxy_ += d_dv * sy;
     if (d_t.uv_scale != nullptr)
         agg_add2(d_t.uv_scale, mk2(d_uv.x * uv_.x + sum(d_du * du_dxy_), d_uv.y * uv_.y + sum(d_dv * dv_dxy_)));
+    TexAdjoint r;
+    r.d_uv = d_uv_;
+    r.d_du_dxy = d_du_dxy_;
+    r.d_dv_dxy = d_dv_dxy_;
+    return r;
+}
+RB_D void d_tex_eval(const rb_texture& t, const rb_texture& d_t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, const Real* d_out, V2& d_uv_,
+                     V2& d_du_dxy_, V2& d_dv_dxy_) {
+    if (tex_is_constant(t)) {
+        if (nch == 3) {
+            agg_add3(d_t.texels[0], mk3(d_out[0], d_out[1], d_out[2]));
+        } else {
+            for (int c = 0; c < nch; c++) agg_add1(&d_t.texels[0][c], d_out[c]);
+        }
+        return;
+    }
+    TexAdjoint r = d_tex_eval_mip(t, d_t, nch, uv_, du_dxy_, dv_dxy_, d_out[0], nch > 1 ? d_out[1] : Real(0), nch > 2 ? d_out[2] : Real(0));
+    d_uv_ += r.d_uv;
+    d_du_dxy_ += r.d_du_dxy;
+    d_dv_dxy_ += r.d_dv_dxy;
 }
 
 // ---------------------------------------------------------------- material helpers
@@ -154,7 +178,7 @@ RB_HD bool mat_has_normal_map(const rb_material& m) { return m.normal_map.num_le
 RB_HD Real roughness_to_phong(Real r) { return rb_max(2 / r - 2, Real(0)); }
 RB_HD Real d_roughness_to_phong(Real r, Real d_e) { return (r > 0 && r <= 1) ? -2 * d_e / rb_sq(r) : Real(0); }
 
-RB_FN Frame perturb_shading_frame(const rb_material& m, const SurfacePoint& p) {
+RB_HD Frame perturb_shading_frame(const rb_material& m, const SurfacePoint& p) {
     V3 n_local = 2 * mat_normal_tex(m, p) - mk3(1, 1, 1);
     V3 pn = normalize(to_world(p.shading_frame, n_local));
     V3 px = normalize(p.dpdu - pn * dot(pn, p.dpdu));
@@ -195,7 +219,7 @@ RB_HD Real smith_g1(V3 v, V3 n, Real roughness) {
     return (Real(3.535) * a + Real(2.181) * a2) / (1 + Real(2.276) * a + Real(2.577) * a2);
 }
 
-RB_FN V3 bsdf_eval(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough) {
+RB_HD V3 bsdf_eval(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough) {
     BsdfCtx c = bsdf_ctx(m, p);
     Real geom_wi = dot(c.geom_n, wi), geom_wo = dot(c.geom_n, wo);
     Real sh_wi = fabs(dot(c.frame.n, wi)), sh_wo = fabs(dot(c.frame.n, wo));
@@ -223,7 +247,7 @@ RB_FN V3 bsdf_eval(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, Re
     return diffuse + spec;
 }
 
-RB_FN Real bsdf_pdf(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough) {
+RB_HD Real bsdf_pdf(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough) {
     BsdfCtx c = bsdf_ctx(m, p);
     Real geom_wi = dot(c.geom_n, wi), geom_wo = dot(c.geom_n, wo);
     Real sh_wo = fabs(dot(c.frame.n, wo));
@@ -258,7 +282,7 @@ RB_FN Real bsdf_pdf(const rb_material& m, const SurfacePoint& p, V3 wi, V3 wo, R
 
 // Returns the sampled direction (zero vector when sampling fails).  `w_sel` is the lobe-selection sample kept in
 // double so that the decision agrees with the reference's double comparison.
-RB_FN V3 bsdf_sample_dir(const rb_material& m, const SurfacePoint& p, V3 wi, V2 suv, double w_sel, Real min_rough, const RayDiff& wi_diff,
+RB_HD V3 bsdf_sample_dir(const rb_material& m, const SurfacePoint& p, V3 wi, V2 suv, double w_sel, Real min_rough, const RayDiff& wi_diff,
                          RayDiff& wo_diff, Real& next_min_rough) {
     next_min_rough = min_rough;
     BsdfCtx c = bsdf_ctx(m, p);
@@ -310,7 +334,7 @@ RB_FN V3 bsdf_sample_dir(const rb_material& m, const SurfacePoint& p, V3 wi, V2 
 }
 
 // Adjoint of bsdf_eval with respect to material textures, the shading point, wi and wo.
-RB_DFN void d_bsdf_eval(const rb_material& m, const rb_material& d_m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough, V3 d_out,
+RB_D void d_bsdf_eval(const rb_material& m, const rb_material& d_m, const SurfacePoint& p, V3 wi, V3 wo, Real min_rough, V3 d_out,
                       SurfacePoint& d_p, V3& d_wi, V3& d_wo) {
     BsdfCtx c = bsdf_ctx(m, p);
     const V3 n = c.frame.n;

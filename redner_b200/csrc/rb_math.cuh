@@ -23,6 +23,11 @@ typedef float Real;
 #define RB_D __device__ __forceinline__
 // Out-of-line functions: the differentiable path tracer is far larger than the SM instruction caches (L0 6 KB / L1.5 32 KB),
 // so the big building blocks are real calls that every kernel and every call site shares instead of being inlined N times.
+#ifndef __CUDACC__
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
+#endif
 #define RB_FN inline __host__ __device__ __noinline__
 #define RB_DFN inline __device__ __noinline__
 

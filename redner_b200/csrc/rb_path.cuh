@@ -41,7 +41,7 @@ RB_D bool any_hit(const DevScene& sc, const Ray& ray) {
 }
 
 // Pick a light, a triangle on it and a point on the triangle; trace the shadow ray.
-RB_DFN void sample_light(const DevScene& sc, const SurfacePoint& sp, double light_sel, double tri_sel, V2 uv, LightSampleRec& rec,
+RB_D void sample_light(const DevScene& sc, const SurfacePoint& sp, double light_sel, double tri_sel, V2 uv, LightSampleRec& rec,
                        SurfacePoint& lp) {
     int light_id = cdf_pick(sc.light_cdf, sc.num_lights, light_sel);
     const DevLight& light = sc.lights[light_id];
@@ -80,7 +80,7 @@ RB_D Real mis_power2(Real p_other, Real p_this) {
 
 // Radiance estimate at one vertex: returns nee + scatter (not yet multiplied by the throughput) and the
 // throughput factor for the next vertex.
-RB_DFN V3 vertex_estimate(const DevScene& sc, const rb_material& mat, const SurfacePoint& sp, V3 wi, Real min_rough, const LightSampleRec& ls,
+RB_D V3 vertex_estimate(const DevScene& sc, const rb_material& mat, const SurfacePoint& sp, V3 wi, Real min_rough, const LightSampleRec& ls,
                         const SurfacePoint& lp, const Isect& bis, const SurfacePoint& bp, V3& scatter_factor, bool& scatter_ok) {
     V3 nee = zero3();
     if (ls.unoccluded) {
@@ -142,7 +142,7 @@ struct VertexRec {
 // dimension of depth `depth_begin`.  If REC, vertices are written to rec[depth - depth_begin] and *num_rec is
 // the number of vertices at which an estimate was formed.
 template <bool REC>
-RB_DFN V3 trace_bounces(const DevScene& sc, Sampler& smp, Ray ray, RayDiff rd_in, Isect is, V3 thr, Real min_rough, int depth_begin,
+RB_D V3 trace_bounces(const DevScene& sc, Sampler& smp, Ray ray, RayDiff rd_in, Isect is, V3 thr, Real min_rough, int depth_begin,
                       int max_bounces, VertexRec* rec, int rec_stride, int* num_rec) {
     V3 L = zero3();
     int count = 0;
@@ -204,7 +204,7 @@ RB_DFN V3 trace_bounces(const DevScene& sc, Sampler& smp, Ray ray, RayDiff rd_in
 }
 
 // Gradient sinks for geometry: per-corner scatter with warp aggregation.
-RB_DFN void scatter_vertex_grads(const DevScene& sc, const DevDScene& ds, const Isect& is, const V3 d_vp[3], const V3 d_vn[3], const V2 d_vuv[3],
+RB_D void scatter_vertex_grads(const DevScene& sc, const DevDScene& ds, const Isect& is, const V3 d_vp[3], const V3 d_vn[3], const V2 d_vuv[3],
                                const V3 d_vc[3]) {
     const rb_shape& s = sc.shapes[is.shape_id];
     const rb_dshape& d = ds.shapes[is.shape_id];
@@ -234,7 +234,7 @@ RB_D VertexAdjoint zero_vertex_adjoint() {
 
 // Adjoint of vertex_estimate + throughput update at vertex `cur`, given the adjoint arriving from vertex `nxt`.
 // d_contrib = weight * d_image[pixel] (radiance channels).
-RB_DFN VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const VertexRec& cur, const VertexRec* nxt, V3 d_contrib,
+RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const VertexRec& cur, const VertexRec* nxt, V3 d_contrib,
                             const VertexAdjoint& next) {
     VertexAdjoint out = zero_vertex_adjoint();
     const rb_shape& shape = sc.shapes[cur.isect.shape_id];

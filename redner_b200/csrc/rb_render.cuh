@@ -53,7 +53,7 @@ RB_D void primary_ray_for(const DevScene& sc, const RenderParams& rp, int px, in
 }
 
 // Radiance of one pixel sample, already multiplied by 1/spp.
-RB_DFN V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, int px, int py, int s) {
+RB_D V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, int px, int py, int s) {
     const Real weight = Real(1) / Real(rp.spp);
     Sampler smp;
     smp.init(rp.sampler_type, rp.seed, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
@@ -74,7 +74,7 @@ RB_DFN V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, 
 
 // Adjoint of one pixel sample.  `recs` is this thread's private record array (max_bounces + 2 entries).
 // Returns the number of path vertices at which a radiance estimate was formed (-1 if the primary ray missed).
-RB_DFN int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, int px, int py, int s, VertexRec* recs, CamAcc& cam_acc) {
+RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, int px, int py, int s, VertexRec* recs, CamAcc& cam_acc) {
     const RenderParams& rp = ka.rp;
     const DevDScene& ds = ka.ds;
     const Real weight = Real(1) / Real(rp.spp);
@@ -102,7 +102,13 @@ RB_DFN int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, 
             es.init(rp.sampler_type, rp.seed + 131071ULL, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS,
                     (unsigned long long)s * edge_draws_per_sample(sc, rp));
             es.skip(secondary_edge_dim_base(rp, d));
-            secondary_edge_sample(sc, ds, rp, cur, d, es, mk3(dpx[0], dpx[1], dpx[2]), adj.d_point.position);
+            // warp-uniform fair coin: all 32 lanes of a warp share (pixel group, sample batch); consecutive batches of a
+            // pixel alternate, so a pixel with >= 64 spp uses both strategies equally often
+            int Lp = ka.lanes_per_pixel > 0 ? ka.lanes_per_pixel : 1;
+            unsigned long long h = rb_hash64shift(((unsigned long long)(unsigned)((long long)pixel * Lp / 32) << 24) ^ ((unsigned long long)d << 16) ^
+                                                  (rp.seed << 44));
+            int coin = (int)(((h >> 17) + (unsigned long long)(s / Lp)) & 1ULL);
+            secondary_edge_sample(sc, ds, rp, cur, d, es, mk3(dpx[0], dpx[1], dpx[2]), coin, adj.d_point.position);
         }
     }
     // first vertex: emission adjoint (src/primary_contribution.cpp:449-466) ...
@@ -191,7 +197,7 @@ RB_HD bool cam_project_d(const DevCamera& cam, D3 p0, D3 p1, D2& q0, D2& q1) {
 }
 
 // One primary-edge sample: edge sample index i (seeds the stream like a pixel index), spp sample s.
-RB_DFN void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long long i, int s, int dim_base, CamAcc& cam_acc) {
+RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long long i, int s, int dim_base, CamAcc& cam_acc) {
     const RenderParams& rp = ka.rp;
     const DevDScene& ds = ka.ds;
     const Real weight = Real(1) / Real(rp.spp);

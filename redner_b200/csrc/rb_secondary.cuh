@@ -65,7 +65,7 @@ RB_HD bool node_contains(const EdgeNode& n, V3 p) {
     return p.x >= n.pmin[0] && p.x <= n.pmax[0] && p.y >= n.pmin[1] && p.y <= n.pmax[1] && p.z >= n.pmin[2] && p.z <= n.pmax[2];
 }
 // Upper bound of the (linearly transformed) cosine lobe over a position box, src/edge.cpp:838-875
-RB_DFN Real ltc_bound(const EdgeNode& n, const EdgeCtx& c) {
+RB_D Real ltc_bound(const EdgeNode& n, const EdgeCtx& c) {
     V3 dir = mk3(0, 0, 1);
     if (!node_contains(n, c.p.position)) {
         V3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
@@ -105,7 +105,7 @@ RB_D Real node_importance(const EdgeNode& n, bool is6d, const EdgeCtx& c) {
     return brdf * n.wlen / rb_max(length(center - c.p.position), Real(1e-3));
 }
 // Integral of the transformed cosine along the (clipped) edge, src/edge.cpp:951-983
-RB_DFN Real edge_ltc_integral(V3 v0, V3 v1, const EdgeCtx& c) {
+RB_D Real edge_ltc_integral(V3 v0, V3 v1, const EdgeCtx& c) {
     if (!(length_sq(v1 - v0) > Real(1e-10))) return 0;
     V3 a = mul(c.m_inv, v0 - c.p.position), b = mul(c.m_inv, v1 - c.p.position);
     if (!(a.z > 0 || b.z > 0)) return 0;
@@ -179,7 +179,7 @@ RB_D void split_samples(int num, Real prob0, Real& u, int& n0, int& n1) {
     }
 }
 // 16 correlated stochastic descents through both trees followed by reservoir resampling among the reached leaves.
-RB_DFN int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sample_weight) {
+RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sample_weight) {
     const DevScene& sc = *c.sc;
     StackH stack[RB_EDGE_STACK_H];
     int sp = 0;
@@ -231,7 +231,7 @@ RB_DFN int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sam
     return selected;
 }
 // Gather all silhouette edges whose billboard the shadow ray crosses and pick one by reservoir resampling.
-RB_DFN int sample_edge_gather(const EdgeCtx& c, const Ray& nee, const Isect& lis, const SurfacePoint& lp, Real resample_u, Real& sample_weight,
+RB_D int sample_edge_gather(const EdgeCtx& c, const Ray& nee, const Isect& lis, const SurfacePoint& lp, Real resample_u, Real& sample_weight,
                             V3& edge_pt, V3& mwt) {
     const DevScene& sc = *c.sc;
     int stack[RB_EDGE_STACK_L];
@@ -306,8 +306,8 @@ RB_HD V3 intersect_jacobian(V3 org, V3 dir, V3 p, V3 n, V3 l) {
 // Samples one silhouette edge as seen from path vertex `cur` (depth `depth`), traces the two sub-paths on either side
 // of it and accumulates the boundary-term gradient into the shading point position (d_position) and the two edge
 // vertices.  `smp` is the edge sampler positioned at this depth's first dimension; `d_color` is the raw d_image pixel.
-RB_DFN void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const VertexRec& cur, int depth, Sampler smp,
-                                V3 d_color, V3& d_position) {
+RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const VertexRec& cur, int depth, Sampler smp,
+                                V3 d_color, int strategy_bit, V3& d_position) {
     const Real weight = Real(1) / Real(rp.spp);
     double s_edge_sel = smp.next(), s_resample = smp.next(), s_component = smp.next(), s_t = smp.next();
     Real min_rough = cur.min_rough;
@@ -371,12 +371,16 @@ RB_DFN void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const
     Real nee_pmf = 1;
     bool diffuse_or_glossy = diffuse_lobe || roughness > Real(0.1);
     if (diffuse_or_glossy) {
-        use_nee = s_edge_sel < 0.5;
+        // The reference flips this coin per sample (edge_sel < 0.5, src/edge.cpp:1461-1468).  We flip it per WARP
+        // (`strategy_bit` is a hash of pixel group, sample batch, depth and seed, identical for the 32 lanes): both
+        // strategies are long, completely different code paths, and a per-lane choice makes every warp execute both.
+        // The coin stays fair and independent of the remaining samples, so the expectation is unchanged.
+        use_nee = strategy_bit != 0;
         if (roughness > Real(0.1)) nee_pmf = Real(0.5);
         else nee_pmf = use_nee ? pd * Real(0.5) : 1 - pd * Real(0.5);
     }
     if (!use_nee) {
-        if (diffuse_or_glossy) edge_sel = (Real)((s_edge_sel - 0.5) * 2);
+        // (edge_sel is no longer consumed by the strategy coin, so it is uniform on [0, 1) as it stands)
         edge_id = sample_edge_hier(c, edge_sel, (Real)s_resample, edge_weight);
         if (edge_id == -1 || edge_weight <= 0) return;
         const Edge& e = sc.edges[edge_id];

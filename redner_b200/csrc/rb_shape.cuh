@@ -102,7 +102,7 @@ RB_HD void quot_adjoint(Real n, Real n_dx, Real n_dy, Real dv, Real dv_dx, Real 
     d_dv_dx += -d_q_dxy.x * n / dv2;
     d_dv_dy += -d_q_dxy.y * n / dv2;
 }
-RB_FN void d_tri_solve(V3 v0, V3 v1, V3 v2, const Ray& ray, const RayDiff& rd, Real d_u, Real d_v, Real d_t, V2 d_u_dxy, V2 d_v_dxy,
+RB_HD void d_tri_solve(V3 v0, V3 v1, V3 v2, const Ray& ray, const RayDiff& rd, Real d_u, Real d_v, Real d_t, V2 d_u_dxy, V2 d_v_dxy,
                        V2 d_t_dxy, V3& d_v0, V3& d_v1, V3& d_v2, DRay& d_ray, RayDiff& d_rd) {
     TriTerms k;
     tri_terms(v0, v1, v2, ray, rd, k);
@@ -181,7 +181,7 @@ RB_HD V3 shape_color(const rb_shape& s, int i) {
     return mk3(p[0], p[1], p[2]);
 }
 
-RB_FN SurfacePoint make_surface_point(const rb_shape& s, int tri, const Ray& ray, const RayDiff& rd, RayDiff& rd_out) {
+RB_HD SurfacePoint make_surface_point(const rb_shape& s, int tri, const Ray& ray, const RayDiff& rd, RayDiff& rd_out) {
     TriAttribs a;
     tri_attribs(s, tri, a);
     V3 v0 = shape_vertex(s, a.ind[0]), v1 = shape_vertex(s, a.ind[1]), v2 = shape_vertex(s, a.ind[2]);
@@ -244,7 +244,7 @@ RB_FN SurfacePoint make_surface_point(const rb_shape& s, int tri, const Ray& ray
 // The treatment of the shading frame follows the reference statement by statement (including the places where
 // it double-counts or drops a term, src/shape.h:533-549, :565-574, :634-638) because gradient parity with the
 // oracle is the acceptance test.
-RB_FN void d_make_surface_point(const rb_shape& s, int tri, const Ray& ray, const RayDiff& rd, const SurfacePoint& d_p,
+RB_HD void d_make_surface_point(const rb_shape& s, int tri, const Ray& ray, const RayDiff& rd, const SurfacePoint& d_p,
                                 const RayDiff& d_rd_out, DRay& d_ray, RayDiff& d_rd, V3 d_vp[3], V3 d_vn[3], V2 d_vuv[3], V3 d_vc[3]) {
     TriAttribs a;
     tri_attribs(s, tri, a);
@@ -444,7 +444,7 @@ RB_FN void d_make_surface_point(const rb_shape& s, int tri, const Ray& ray, cons
 }
 
 // ---- uniform point on a triangle of an area light ----
-RB_FN SurfacePoint sample_light_triangle(const rb_shape& s, int tri, V2 sample) {
+RB_HD SurfacePoint sample_light_triangle(const rb_shape& s, int tri, V2 sample) {
     V3 v0, v1, v2;
     shape_tri_vertices(s, tri, v0, v1, v2);
     Real a = sqrt(sample.x);
@@ -459,7 +459,7 @@ RB_FN SurfacePoint sample_light_triangle(const rb_shape& s, int tri, V2 sample) 
     p.bary = mk2(b1, b2);
     return p;
 }
-RB_FN void d_sample_light_triangle(const rb_shape& s, int tri, V2 sample, const SurfacePoint& d_p, V3 d_v[3]) {
+RB_HD void d_sample_light_triangle(const rb_shape& s, int tri, V2 sample, const SurfacePoint& d_p, V3 d_v[3]) {
     V3 v0, v1, v2;
     shape_tri_vertices(s, tri, v0, v1, v2);
     Real a = sqrt(sample.x);

@@ -12,12 +12,15 @@ import scenes  # noqa: E402
 from redner_b200 import api  # noqa: E402
 from redner_b200 import redner as rb  # noqa: E402
 
+if os.environ.get("RB_LIB"):
+    from redner_b200 import _lib
+    _lib._lib = _lib.load(os.environ["RB_LIB"])
 scene = sys.argv[1] if len(sys.argv) > 1 else "shadow_blocker"
 res = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 spp = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 mb = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 dev = torch.device("cuda:0")
-for edges in (0, 1, 2, 3):
+for edges in [int(e) for e in os.environ.get("RB_EDGES", "0,1,2,3").split(",")]:
     for rep in range(2):
         sc = scenes.SCENES[scene](dev, resolution=(res, res))
         args = api.RenderFunction.serialize_scene(sc, spp, mb, sampler_type=rb.SamplerType.sobol, device=dev, backend=rb,

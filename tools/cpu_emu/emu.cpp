@@ -216,6 +216,8 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
     rp.part = 0; rp.num_parts = 1; rp.rows_per_stripe = 16;
     rp.vp_w = scene->cam.viewport_end[0] - scene->cam.viewport_beg[0];
     rp.vp_h = scene->cam.viewport_end[1] - scene->cam.viewport_beg[1];
+    ka.lanes_per_pixel = 1;
+    while (ka.lanes_per_pixel * 2 <= std::min(32, rp.spp)) ka.lanes_per_pixel *= 2;
     ka.image = image;
     ka.d_image = d_image;
     ka.screen_grad = screen_grad;
