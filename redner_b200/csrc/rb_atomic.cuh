@@ -19,32 +19,27 @@ RB_D void rb_red_add(float* addr, float v) { atomicAdd(addr, v); } // result unu
 // Combine up to three consecutive floats across the lanes of the current convergence group that target the same `addr`;
 // the group leader issues the reductions.  Must stay INLINE: inside a real function the callers' lanes are not
 // reconverged, __activemask() degenerates to single lanes and every lane issues its own atomics (measured: 7x slower).
+// The peers of one address form a linked list in lane order; pointer doubling turns every lane's value into the
+// suffix sum of its list in ceil(log2 n) rounds, so the lowest lane ends with the group total.  One code path for
+// every group shape and no __fns(): the previous rank-based tree made this helper ~45% of k_backward's 1.6 MB of
+// SASS, which then ran instruction-fetch bound (profiles/r01_ncu_k_backward_summary.txt).
 RB_D void warp_agg_add3(float* addr, float x, float y, float z) {
     unsigned active = __activemask();
     unsigned peers = __match_any_sync(active, (unsigned long long)addr);
     int lane = threadIdx.x & 31;
+    unsigned above = peers & (0xfffffffeu << lane);
+    int nxt = above ? __ffs(above) - 1 : -1;
     int n = __popc(peers);
-    if (n > 1) {
-        if (peers == 0xffffffffu) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                x += __shfl_xor_sync(0xffffffffu, x, off);
-                y += __shfl_xor_sync(0xffffffffu, y, off);
-                z += __shfl_xor_sync(0xffffffffu, z, off);
-            }
-        } else {
-            int rank = __popc(peers & ((1u << lane) - 1u));
-            for (int off = 1; off < n; off <<= 1) {
-                int src_rank = rank + off;
-                bool take = (src_rank < n) && ((rank & (2 * off - 1)) == 0);
-                int src_lane = take ? (int)__fns(peers, 0, src_rank + 1) : lane;
-                float ox = __shfl_sync(peers, x, src_lane), oy = __shfl_sync(peers, y, src_lane), oz = __shfl_sync(peers, z, src_lane);
-                if (take) {
-                    x += ox;
-                    y += oy;
-                    z += oz;
-                }
-            }
+#pragma unroll 1
+    for (int span = 1; span < n; span <<= 1) {
+        int src = nxt >= 0 ? nxt : lane;
+        float ox = __shfl_sync(peers, x, src), oy = __shfl_sync(peers, y, src), oz = __shfl_sync(peers, z, src);
+        int nn = __shfl_sync(peers, nxt, src);
+        if (nxt >= 0) {
+            x += ox;
+            y += oy;
+            z += oz;
+            nxt = nn;
         }
     }
     if (lane == __ffs(peers) - 1) {

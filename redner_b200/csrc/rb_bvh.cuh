@@ -9,7 +9,8 @@
 //
 // The triangle test is a Pluecker edge-function test evaluated in fp32 with the same operation nesting as
 // Embree 3.6's robust-mode intersector (edge tests U, V, W with fused multiply-adds, inclusive zero), because
-// parity with the reference means agreeing with Embree's hit/miss decisions on silhouette pixels.
+// parity with the reference means agreeing with Embree's hit/miss decisions on silhouette pixels
+// (including its one-ulp edge tolerance).
 #pragma once
 #include "rb_types.cuh"
 
@@ -35,7 +36,10 @@ RB_D bool tri_test(F3 O, F3 D, float tnear, float tfar, const BVHTri& tri, float
     float V = f3_dot(f3_cross(f3_add(v0, v1), e1), D);
     float W = f3_dot(f3_cross(f3_add(v1, v2), e2), D);
     float mn = fminf(U, fminf(V, W)), mx = fmaxf(U, fmaxf(V, W));
-    if (!(mn >= 0.0f || mx <= 0.0f)) return false;
+    // edge tolerance of one ulp of the summed edge functions, as in Embree's robust intersector (without it, 5 of
+    // 16.8 M primary samples of the C2 image miss the floor edge that the reference hits)
+    float eps = 1.1920929e-7f * fabsf(U + V + W);
+    if (!(mn >= -eps || mx <= eps)) return false;
     F3 Ng = f3_cross(e2, e1);
     float den = 2.0f * f3_dot(Ng, D);
     if (den == 0.0f) return false;

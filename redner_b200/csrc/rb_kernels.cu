@@ -95,6 +95,60 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_FWD) k_forward(const _
     }
 }
 
+// G-buffer forward (any channel list): one warp per pixel group like k_forward, channels reduced with shuffles; id
+// channels take the value of the highest-numbered sample that hit (the reference overwrites them sample after sample).
+__global__ void __launch_bounds__(RB_BLOCK, 2) k_forward_channels(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+    const RenderParams& rp = ka.rp;
+    const int L = ka.lanes_per_pixel;
+    const int P = 32 / L;
+    long long n_px = (long long)ka.owned_rows * rp.vp_w;
+    long long groups = (n_px + P - 1) / P;
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int nb = (rp.spp + L - 1) / L;
+    const int nd = rp.nd < RB_MAX_ND ? rp.nd : RB_MAX_ND;
+    for (long long g = warp; g < groups; g += nwarps) {
+        WorkItem w = warp_work(rp, L, ka.owned_rows, g);
+        float acc[RB_MAX_ND];
+        for (int i = 0; i < nd; i++) acc[i] = 0.f;
+        int ids[3] = {-1, -1, -1};
+        int last = -1;
+        for (int b = 0; b < nb; b++) {
+            int s = b * L + w.sample_lane;
+            if (w.valid && s < rp.spp) {
+                int cur[3] = {-1, -1, -1};
+                if (forward_sample_channels(sc, rp, w.pixel, w.px, w.py, s, acc, cur)) {
+                    last = s;
+                    ids[0] = cur[0]; ids[1] = cur[1]; ids[2] = cur[2];
+                }
+            }
+        }
+        for (int off = L >> 1; off > 0; off >>= 1) {
+            for (int i = 0; i < nd; i++) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+            int ol = __shfl_xor_sync(0xffffffffu, last, off);
+            int o0 = __shfl_xor_sync(0xffffffffu, ids[0], off), o1 = __shfl_xor_sync(0xffffffffu, ids[1], off), o2 = __shfl_xor_sync(0xffffffffu, ids[2], off);
+            if (ol > last) { last = ol; ids[0] = o0; ids[1] = o1; ids[2] = o2; }
+        }
+        if (w.valid && w.sample_lane == 0) {
+            float* px = ka.image + (size_t)rp.nd * w.pixel;
+            int d = 0;
+            for (int c = 0; c < rp.num_channels; c++) {
+                int ch = rp.channels[c];
+                int width = (ch == RB_CH_RADIANCE || ch == RB_CH_POSITION || ch == RB_CH_GEOMETRY_NORMAL || ch == RB_CH_SHADING_NORMAL ||
+                             ch == RB_CH_DIFFUSE_REFLECTANCE || ch == RB_CH_SPECULAR_REFLECTANCE || ch == RB_CH_VERTEX_COLOR) ? 3
+                          : (ch == RB_CH_UV || ch == RB_CH_BARYCENTRIC) ? 2 : (ch == RB_CH_GENERIC_TEXTURE ? rp.max_generic : 1);
+                if (ch == RB_CH_SHAPE_ID || ch == RB_CH_TRIANGLE_ID || ch == RB_CH_MATERIAL_ID) {
+                    int v = ids[ch - RB_CH_SHAPE_ID];
+                    if (last >= 0 && d < nd) px[d] = (float)v;
+                } else {
+                    for (int i = 0; i < width && d + i < nd; i++) px[d + i] += acc[d + i];
+                }
+                d += width;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ backward (interior + first hit)
 RB_D void block_reduce_camera(float* cam_smem, double* cam_accum) {
     // cam_smem: [RB_CAM_ACC][blockDim.x]; reduce each row and add to the global double accumulators
@@ -221,8 +275,13 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         rb_set_error("rb_render: too many channels");
         return 1;
     }
+    bool only_radiance = opt->num_channels == 1 && opt->channels[0] == RB_CH_RADIANCE;
     for (int i = 0; i < opt->num_channels; i++) {
         rp.channels[i] = opt->channels[i];
+        if (opt->channels[i] < 0 || opt->channels[i] >= RB_CH_COUNT) {
+            rb_set_error("rb_render: unknown channel");
+            return 1;
+        }
         if (opt->channels[i] == RB_CH_RADIANCE) {
             if (rp.rad_dim != -1) {
                 rb_set_error("Duplicated radiance channel"); // src/channels.cpp:24-26
@@ -231,16 +290,17 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             // the reference stores the CHANNEL INDEX and uses it as a float offset (src/channels.cpp:27,
             // src/path_contribution.cpp:125-129); identical whenever radiance is the first channel
             rp.rad_dim = i;
-        } else {
-            rb_set_error("rb_render: only the radiance channel is implemented so far (G-buffer channels: SURVEY.md 8f rank 3)");
-            return 1;
         }
     }
-    if (rp.rad_dim < 0) {
-        rb_set_error("rb_render: the radiance channel is required");
+    if (d_image != nullptr && !only_radiance) {
+        rb_set_error("rb_render: the backward pass is implemented for channels == [radiance] only (G-buffer adjoints: SURVEY.md 8f rank 3)");
         return 1;
     }
     rp.nd = rb_compute_num_channels(opt->channels, opt->num_channels, rp.max_generic);
+    if (rp.nd > RB_MAX_ND) {
+        rb_set_error("rb_render: more than 64 image dimensions requested");
+        return 1;
+    }
     rp.part = scene->part;
     rp.num_parts = scene->num_parts;
     rp.rows_per_stripe = scene->rows_per_stripe;
@@ -273,8 +333,13 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
     };
     RB_CUDA_OK(cudaEventRecord(ev[0], stream));
     if (image != nullptr) {
-        int grid = pick_grid((const void*)k_forward, scene->device, nullptr);
-        k_forward<<<grid, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+        if (only_radiance) {
+            int grid = pick_grid((const void*)k_forward, scene->device, nullptr);
+            k_forward<<<grid, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+        } else {
+            int grid = pick_grid((const void*)k_forward_channels, scene->device, nullptr);
+            k_forward_channels<<<grid, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+        }
         launches++;
     }
     RB_CUDA_OK(cudaEventRecord(ev[1], stream));

@@ -71,21 +71,14 @@ RB_HD void tex_eval(const rb_texture& t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_
     }
     tex_eval_mip(t, nch, uv_, du_dxy_, dv_dxy_, out);
 }
-// Adjoint of one bilinear tap: scatters into the gradient mip level and returns d(u), d(v).
-RB_D void d_bilerp(const float* tex, float* d_tex, int nch, int c, const BilerpTap& b, Real d_val, Real& d_u, Real& d_v) {
-    Real ff = tex[nch * b.i_ff + c], cf = tex[nch * b.i_cf + c], fc = tex[nch * b.i_fc + c], cc = tex[nch * b.i_cc + c];
-    agg_add1(&d_tex[nch * b.i_ff + c], d_val * (1 - b.u) * (1 - b.v));
-    agg_add1(&d_tex[nch * b.i_cf + c], d_val * b.u * (1 - b.v));
-    agg_add1(&d_tex[nch * b.i_fc + c], d_val * (1 - b.u) * b.v);
-    agg_add1(&d_tex[nch * b.i_cc + c], d_val * b.u * b.v);
-    d_u += d_val * (-ff * (1 - b.v) + cf * (1 - b.v) - fc * b.v + cc * b.v);
-    d_v += d_val * (-ff * (1 - b.u) - cf * b.u + fc * (1 - b.u) + cc * b.u);
-}
 struct TexAdjoint { // returned by value so that the caller's SurfacePoint adjoint can stay in registers
     V2 d_uv, d_du_dxy, d_dv_dxy;
 };
+// Adjoint of the trilinear lookup (src/texture.h:146-276): scatters into the gradient mip pyramid and returns d(uv),
+// d(du_dxy), d(dv_dxy).  Levels and taps are walked by ROLLED loops and each texel takes one aggregated 3-float
+// reduction (nch <= 3 on this path: reflectances, roughness, normal map), so the whole adjoint is ~0.5k SASS
+// instructions instead of the 36 unrolled aggregated atomics it used to be.
 RB_D TexAdjoint d_tex_eval_mip(const rb_texture& t, const rb_texture& d_t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, Real d0, Real d1, Real d2) {
-    Real d_out[3] = {d0, d1, d2};
     V2 d_uv_ = zero2(), d_du_dxy_ = zero2(), d_dv_dxy_ = zero2();
     Real sx = t.uv_scale[0], sy = t.uv_scale[1];
     V2 uv = mk2(uv_.x * sx, uv_.y * sy);
@@ -96,26 +89,45 @@ RB_D TexAdjoint d_tex_eval_mip(const rb_texture& t, const rb_texture& d_t, int n
     Real max_fp = u_is_max ? fu : fv;
     V2 d_uv = zero2();
     Real d_level = 0;
-    if (level <= 0 || level >= t.num_levels - 1) {
-        int li = level <= 0 ? 0 : t.num_levels - 1;
-        BilerpTap b = bilerp_tap(t, li, uv);
-        Real d_u = 0, d_v = 0;
-        for (int c = 0; c < nch; c++) d_bilerp(t.texels[li], d_t.texels[li], nch, c, b, d_out[c], d_u, d_v);
-        d_uv.x += d_u * t.width[li];
-        d_uv.y += d_v * t.height[li];
+    int l0, nl;
+    Real ld = 0;
+    if (level <= 0) {
+        l0 = 0;
+        nl = 1;
+    } else if (level >= t.num_levels - 1) {
+        l0 = t.num_levels - 1;
+        nl = 1;
     } else {
-        int li = (int)floor(level);
-        Real ld = level - li;
-        BilerpTap b0 = bilerp_tap(t, li, uv), b1 = bilerp_tap(t, li + 1, uv);
-        Real d_u0 = 0, d_v0 = 0, d_u1 = 0, d_v1 = 0;
-        for (int c = 0; c < nch; c++) {
-            Real a0 = bilerp_eval(t.texels[li], nch, c, b0), a1 = bilerp_eval(t.texels[li + 1], nch, c, b1);
-            d_level += d_out[c] * (a1 - a0);
-            d_bilerp(t.texels[li], d_t.texels[li], nch, c, b0, d_out[c] * (1 - ld), d_u0, d_v0);
-            d_bilerp(t.texels[li + 1], d_t.texels[li + 1], nch, c, b1, d_out[c] * ld, d_u1, d_v1);
+        l0 = (int)floor(level);
+        nl = 2;
+        ld = level - l0;
+    }
+    if (nch < 2) d1 = 0;
+    if (nch < 3) d2 = 0;
+#pragma unroll 1
+    for (int j = 0; j < nl; j++) {
+        int li = l0 + j;
+        Real wl = j ? ld : 1 - ld;
+        BilerpTap b = bilerp_tap(t, li, uv);
+        const float* tex = t.texels[li];
+        float* d_tex = d_t.texels[li];
+        Real d_u = 0, d_v = 0, val = 0;
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) { // bit 0: ceil in x, bit 1: ceil in y
+            int idx = nch * (k == 0 ? b.i_ff : k == 1 ? b.i_cf : k == 2 ? b.i_fc : b.i_cc);
+            Real wu = (k & 1) ? b.u : 1 - b.u, wv = (k & 2) ? b.v : 1 - b.v;
+            Real tv = d0 * tex[idx];
+            if (nch > 1) tv += d1 * tex[idx + 1];
+            if (nch > 2) tv += d2 * tex[idx + 2];
+            val += tv * wu * wv;
+            d_u += (k & 1) ? tv * wv : -tv * wv;
+            d_v += (k & 2) ? tv * wu : -tv * wu;
+            Real w = wl * wu * wv;
+            warp_agg_add3(d_tex + idx, (float)(d0 * w), (float)(d1 * w), (float)(d2 * w));
         }
-        d_uv.x += d_u1 * t.width[li + 1] + d_u0 * t.width[li];
-        d_uv.y += d_v1 * t.height[li + 1] + d_v0 * t.height[li];
+        if (nl == 2) d_level += j ? val : -val;
+        d_uv.x += wl * d_u * t.width[li];
+        d_uv.y += wl * d_v * t.height[li];
     }
     V2 d_du = zero2(), d_dv = zero2();
     if (max_fp > Real(1e-8)) {
@@ -186,14 +198,14 @@ RB_HD Frame perturb_shading_frame(const rb_material& m, const SurfacePoint& p) {
     return mk_frame(px, py, pn);
 }
 // normal-only adjoint (the BSDF value only depends on the perturbed normal; src/material.h:331-351)
-RB_D void d_perturb_shading_normal(const rb_material& m, const rb_material& d_m, const SurfacePoint& p, V3 d_n, SurfacePoint& d_p) {
+// Returns the adjoint of the normal-map texel; the caller scatters it into the texture gradient.
+RB_D V3 d_perturb_shading_normal(const rb_material& m, const SurfacePoint& p, V3 d_n, SurfacePoint& d_p) {
     V3 n_local = 2 * mat_normal_tex(m, p) - mk3(1, 1, 1);
     V3 n_world = to_world(p.shading_frame, n_local);
     V3 d_n_world = d_normalize(n_world, d_n);
     V3 d_local = zero3();
     d_to_world(p.shading_frame, n_local, d_n_world, d_p.shading_frame, d_local);
-    Real d_o[3] = {2 * d_local.x, 2 * d_local.y, 2 * d_local.z};
-    d_tex_eval(m.normal_map, d_m.normal_map, 3, p.uv, p.du_dxy, p.dv_dxy, d_o, d_p.uv, d_p.du_dxy, d_p.dv_dxy);
+    return 2 * d_local;
 }
 
 struct BsdfCtx { // quantities shared by eval / pdf / sample
@@ -347,12 +359,10 @@ RB_D void d_bsdf_eval(const rb_material& m, const rb_material& d_m, const Surfac
     V3 kd = max3(m.use_vertex_color ? p.color : mat_diffuse(m, p), 0);
     // diffuse = kd * sh_wo / pi   (gradient passes through the clamp unchanged, src/material.h:505-518)
     V3 d_kd = d_out * (sh_wo / RB_PI);
-    if (m.use_vertex_color) {
-        d_p.color += d_kd;
-    } else {
-        Real d_o[3] = {d_kd.x, d_kd.y, d_kd.z};
-        d_tex_eval(m.diffuse_reflectance, d_m.diffuse_reflectance, 3, p.uv, p.du_dxy, p.dv_dxy, d_o, d_p.uv, d_p.du_dxy, d_p.dv_dxy);
-    }
+    if (m.use_vertex_color) d_p.color += d_kd;
+    // texture adjoints are collected here and scattered by ONE rolled loop at the end (one copy of the mip adjoint)
+    V3 d_slot[4] = {d_kd, zero3(), zero3(), zero3()};
+    unsigned slot_on = m.use_vertex_color ? 0u : 1u;
     Real d_sh_wo = sum(d_out * kd) / RB_PI;
     if (dot(n, wo) < 0) d_sh_wo = -d_sh_wo;
     d_wo += n * d_sh_wo;
@@ -428,17 +438,27 @@ RB_D void d_bsdf_eval(const rb_material& m, const rb_material& d_m, const Surfac
             V3 d_wiwo = d_normalize(wi + wo, d_h);
             d_wi += d_wiwo;
             d_wo += d_wiwo;
-            Real d_o3[3] = {d_ks.x, d_ks.y, d_ks.z};
-            d_tex_eval(m.specular_reflectance, d_m.specular_reflectance, 3, p.uv, p.du_dxy, p.dv_dxy, d_o3, d_p.uv, d_p.du_dxy, d_p.dv_dxy);
+            d_slot[1] = d_ks;
+            slot_on |= 2u;
             if (roughness > min_rough) {
-                Real d_o1[1] = {d_roughness};
-                d_tex_eval(m.roughness, d_m.roughness, 1, p.uv, p.du_dxy, p.dv_dxy, d_o1, d_p.uv, d_p.du_dxy, d_p.dv_dxy);
+                d_slot[2] = mk3(d_roughness, 0, 0);
+                slot_on |= 4u;
             }
         }
     }
     if (mat_has_normal_map(m)) {
-        d_perturb_shading_normal(m, d_m, p, d_n, d_p);
+        d_slot[3] = d_perturb_shading_normal(m, p, d_n, d_p);
+        slot_on |= 8u;
     } else {
         d_p.shading_frame.n += d_n;
+    }
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        if (!((slot_on >> k) & 1u)) continue;
+        const rb_texture* t = k == 0 ? &m.diffuse_reflectance : k == 1 ? &m.specular_reflectance : k == 2 ? &m.roughness : &m.normal_map;
+        const rb_texture* dt = k == 0 ? &d_m.diffuse_reflectance : k == 1 ? &d_m.specular_reflectance : k == 2 ? &d_m.roughness : &d_m.normal_map;
+        V3 d = k == 0 ? d_slot[0] : k == 1 ? d_slot[1] : k == 2 ? d_slot[2] : d_slot[3];
+        Real d_o[3] = {d.x, d.y, d.z};
+        d_tex_eval(*t, *dt, k == 2 ? 1 : 3, p.uv, p.du_dxy, p.dv_dxy, d_o, d_p.uv, d_p.du_dxy, d_p.dv_dxy);
     }
 }

@@ -40,9 +40,28 @@ RB_D bool any_hit(const DevScene& sc, const Ray& ray) {
     return bvh_trace<true>(sc, ray, s, tr, t);
 }
 
-// Pick a light, a triangle on it and a point on the triangle; trace the shadow ray.
-RB_D void sample_light(const DevScene& sc, const SurfacePoint& sp, double light_sel, double tri_sel, V2 uv, LightSampleRec& rec,
-                       SurfacePoint& lp) {
+// Hit point in double precision.  The reference keeps rays and hit points in double and only rounds the rays it hands to
+// Embree (src/scene.cpp:556-567); a shadow ray that starts at an fp32 hit point differs from the reference's in the last
+// bit and resolves differently when it grazes a blocker edge (measured: 4 of 16.8 M samples at 512x512x64 == 1.6e-4
+// relative L2).  Carrying the hit point (only) in double makes the rounded shadow / bounce rays identical again.
+RB_D D3 hit_point_d(const rb_shape& s, int tri, D3 o, D3 d) {
+    int idx[3];
+    shape_tri(s, tri, idx);
+    const float *p0 = s.vertices + 3 * (size_t)idx[0], *p1 = s.vertices + 3 * (size_t)idx[1], *p2 = s.vertices + 3 * (size_t)idx[2];
+    double e1x = (double)p1[0] - p0[0], e1y = (double)p1[1] - p0[1], e1z = (double)p1[2] - p0[2];
+    double e2x = (double)p2[0] - p0[0], e2y = (double)p2[1] - p0[1], e2z = (double)p2[2] - p0[2];
+    double pvx = d.y * e2z - d.z * e2y, pvy = d.z * e2x - d.x * e2z, pvz = d.x * e2y - d.y * e2x;
+    double div = pvx * e1x + pvy * e1y + pvz * e1z;
+    if (fabs(div) < 1e-8) div = div > 0 ? 1e-8 : -1e-8;
+    double sx = o.x - p0[0], sy = o.y - p0[1], sz = o.z - p0[2];
+    double qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;
+    double t = (e2x * qx + e2y * qy + e2z * qz) / div;
+    return d3(o.x + d.x * t, o.y + d.y * t, o.z + d.z * t);
+}
+
+// Pick a light, a triangle on it and a point on the triangle; trace the shadow ray (built in double from the double hit
+// point `p_d`, then rounded once -- src/scene.cpp:692-741).
+RB_D void sample_light(const DevScene& sc, D3 p_d, double light_sel, double tri_sel, double su, double sv, LightSampleRec& rec, SurfacePoint& lp) {
     int light_id = cdf_pick(sc.light_cdf, sc.num_lights, light_sel);
     const DevLight& light = sc.lights[light_id];
     const rb_shape& shape = sc.shapes[light.shape_id];
@@ -50,14 +69,22 @@ RB_D void sample_light(const DevScene& sc, const SurfacePoint& sp, double light_
     int tri = cdf_pick(acdf, shape.num_triangles, tri_sel);
     rec.isect.shape_id = light.shape_id;
     rec.isect.tri_id = tri;
-    rec.uv = uv;
-    lp = sample_light_triangle(shape, tri, uv);
+    rec.uv = mk2((Real)su, (Real)sv);
+    lp = sample_light_triangle(shape, tri, rec.uv);
+    int idx[3];
+    shape_tri(shape, tri, idx);
+    const float *p0 = shape.vertices + 3 * (size_t)idx[0], *p1 = shape.vertices + 3 * (size_t)idx[1], *p2 = shape.vertices + 3 * (size_t)idx[2];
+    double a = sqrt(su), b1 = 1.0 - a, b2 = a * sv;
+    double lx = p0[0] + ((double)p1[0] - p0[0]) * b1 + ((double)p2[0] - p0[0]) * b2;
+    double ly = p0[1] + ((double)p1[1] - p0[1]) * b1 + ((double)p2[1] - p0[1]) * b2;
+    double lz = p0[2] + ((double)p1[2] - p0[2]) * b1 + ((double)p2[2] - p0[2]) * b2;
+    double dx = lx - p_d.x, dy = ly - p_d.y, dz = lz - p_d.z;
+    double len = sqrt(dx * dx + dy * dy + dz * dz);
     Ray sh;
-    V3 d = lp.position - sp.position;
-    sh.org = sp.position;
-    sh.dir = normalize(d);
+    sh.org = mk3((Real)p_d.x, (Real)p_d.y, (Real)p_d.z);
+    sh.dir = len > 0 ? mk3((Real)(dx / len), (Real)(dy / len), (Real)(dz / len)) : zero3();
     sh.tmin = Real(1e-3);
-    sh.tmax = (1 - Real(1e-3)) * length(d);
+    sh.tmax = (Real)((1 - 1e-3f) * len);
     rec.unoccluded = !any_hit(sc, sh);
 }
 
@@ -143,9 +170,12 @@ struct VertexRec {
 // the number of vertices at which an estimate was formed.
 template <bool REC>
 RB_D V3 trace_bounces(const DevScene& sc, Sampler& smp, Ray ray, RayDiff rd_in, Isect is, V3 thr, Real min_rough, int depth_begin,
-                      int max_bounces, VertexRec* rec, int rec_stride, int* num_rec) {
+                      int max_bounces, VertexRec* rec, int rec_stride, int* num_rec, const D3* ray_org_d = nullptr, const D3* ray_dir_d = nullptr) {
     V3 L = zero3();
     int count = 0;
+    // double-precision copy of the current ray (exact for camera rays, promoted fp32 otherwise)
+    D3 od = ray_org_d ? *ray_org_d : d3(ray.org.x, ray.org.y, ray.org.z);
+    D3 dd = ray_dir_d ? *ray_dir_d : d3(ray.dir.x, ray.dir.y, ray.dir.z);
     if (sc.num_lights > 0) {
         for (int depth = depth_begin; depth < max_bounces && is.valid(); depth++) {
             RayDiff rd;
@@ -155,7 +185,8 @@ RB_D V3 trace_bounces(const DevScene& sc, Sampler& smp, Ray ray, RayDiff rd_in, 
             double l_sel = smp.next(), t_sel = smp.next(), lu = smp.next(), lv = smp.next();
             LightSampleRec ls;
             SurfacePoint lp;
-            sample_light(sc, sp, l_sel, t_sel, mk2((Real)lu, (Real)lv), ls, lp);
+            D3 p_d = hit_point_d(sc.shapes[is.shape_id], is.tri_id, od, dd);
+            sample_light(sc, p_d, l_sel, t_sel, lu, lv, ls, lp);
             double bu = smp.next(), bv = smp.next(), bw = smp.next();
             if (REC) {
                 VertexRec& r = rec[(size_t)count * rec_stride];
@@ -170,8 +201,10 @@ RB_D V3 trace_bounces(const DevScene& sc, Sampler& smp, Ray ray, RayDiff rd_in, 
             Real next_rough;
             V3 dir = bsdf_sample_dir(mat, sp, wi, mk2((Real)bu, (Real)bv), bw, min_rough, rd, rd_b, next_rough);
             Ray nray;
-            nray.org = sp.position;
+            nray.org = mk3((Real)p_d.x, (Real)p_d.y, (Real)p_d.z);
             nray.dir = dir;
+            od = p_d;
+            dd = d3(dir.x, dir.y, dir.z);
             nray.tmin = Real(1e-3);
             nray.tmax = INFINITY;
             Isect bis = no_isect();
@@ -246,7 +279,15 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
     V3 p = sp.position;
     V3 thr = cur.thr;
     Real min_rough = cur.min_rough;
-    // ---- next event estimation
+    // The two estimators of this vertex (light sample, BSDF sample) share ONE rolled call of d_bsdf_eval: each prepares
+    // (wo, d_f, d_wo) in a "pre" block and consumes the returned d_wo in a "post" block.  Besides halving the code of
+    // the largest adjoint this reconverges the lanes of a warp that took only one of the two branches.
+    bool on_l = false, on_b = false;
+    V3 wo_l = zero3(), d_f_l = zero3(), d_wo_l = zero3(), dir_l = zero3();
+    V3 wo_b = zero3(), d_f_b = zero3(), d_wo_b = zero3(), dir_b = zero3();
+    Real dist_sq_l = 1, d_dist_sq_l = 0, dist_sq_b = 1, d_cos_l = 0;
+    V3 d_lv[3] = {zero3(), zero3(), zero3()};
+    // ---- next event estimation (pre)
     if (cur.light.unoccluded) {
         const Isect& lis = cur.light.isect;
         const rb_shape& lshape = sc.shapes[lis.shape_id];
@@ -257,7 +298,6 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
         if (lshape.light_id >= 0) {
             const DevLight& light = sc.lights[lshape.light_id];
             if (light.two_sided || dot(-wo, lp.shading_frame.n) > 0) {
-                V3 d_lv[3] = {zero3(), zero3(), zero3()};
                 V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
                 Real cos_l = dot(wo, lp.geom_normal);
                 Real G = fabs(cos_l) / dist_sq;
@@ -273,50 +313,33 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
                 Real d_wgt = G * sum(d_nee * f * Le);
                 Real d_pdf_nee = -d_wgt * wgt / pdf_nee;
                 Real d_G = wgt * sum(d_nee * f * Le);
-                V3 d_f = wgt * G * (d_nee * Le);
                 V3 d_Le = wgt * G * (d_nee * f);
                 Real d_area = -d_pdf_nee * pdf_nee / shape_tri_area(lshape, lis.tri_id);
                 d_shape_tri_area(lshape, lis.tri_id, d_area, d_lv);
                 agg_add3(ds.light_intensity[lshape.light_id], d_Le);
-                Real d_cos_l = cos_l > 0 ? d_G / dist_sq : -d_G / dist_sq;
-                Real d_dist_sq = -d_G * G / dist_sq;
-                V3 d_wo = d_cos_l * lp.geom_normal;
-                SurfacePoint d_lp = zero_point();
-                d_lp.geom_normal = d_cos_l * wo;
-                V3 d_wi = zero3();
-                d_bsdf_eval(mat, d_mat, sp, wi, wo, min_rough, d_f, out.d_point, d_wi, d_wo);
-                V3 d_dir = d_wo / sqrt(dist_sq);
-                Real d_sqrt = -sum(d_wo * dir) / dist_sq;
-                d_dist_sq += Real(0.5) * d_sqrt / sqrt(dist_sq);
-                d_dir += d_length_sq(dir, d_dist_sq);
-                d_lp.position += d_dir;
-                out.d_point.position -= d_dir;
-                out.d_ray.dir -= d_wi;
-                d_sample_light_triangle(lshape, lis.tri_id, cur.light.uv, d_lp, d_lv);
-                int idx[3];
-                shape_tri(lshape, lis.tri_id, idx);
-                float* dv = ds.shapes[lis.shape_id].vertices;
-                if (dv) {
-                    agg_add3(dv + 3 * (size_t)idx[0], d_lv[0]);
-                    agg_add3(dv + 3 * (size_t)idx[1], d_lv[1]);
-                    agg_add3(dv + 3 * (size_t)idx[2], d_lv[2]);
-                }
+                d_cos_l = cos_l > 0 ? d_G / dist_sq : -d_G / dist_sq;
+                on_l = true;
+                wo_l = wo;
+                dir_l = dir;
+                dist_sq_l = dist_sq;
+                d_dist_sq_l = -d_G * G / dist_sq;
+                d_f_l = wgt * G * (d_nee * Le);
+                d_wo_l = d_cos_l * lp.geom_normal;
             }
         }
     }
-    // ---- BSDF-sampled continuation
+    // ---- BSDF-sampled continuation (pre)
+    SurfacePoint bp;
     if (nxt != nullptr && nxt->isect.valid()) {
         const Isect& bis = nxt->isect;
         const rb_shape& bshape = sc.shapes[bis.shape_id];
         RayDiff rd_after;
-        SurfacePoint bp = make_surface_point(bshape, bis.tri_id, nxt->ray, nxt->rd_in, rd_after);
+        bp = make_surface_point(bshape, bis.tri_id, nxt->ray, nxt->rd_in, rd_after);
         V3 dir = bp.position - p;
         Real dist_sq = length_sq(dir);
         V3 wo = dir / sqrt(dist_sq);
         Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
         if (pdf_b > 0) {
-            V3 d_bvp[3] = {zero3(), zero3(), zero3()}, d_bvn[3] = {zero3(), zero3(), zero3()}, d_bvc[3] = {zero3(), zero3(), zero3()};
-            V2 d_bvuv[3] = {zero2(), zero2(), zero2()};
             V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
             V3 factor = f / pdf_b;
             out.d_thr += next.d_thr * factor;
@@ -338,31 +361,72 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
                     agg_add3(ds.light_intensity[bshape.light_id], wgt * (d_scatter * f));
                 }
             }
-            V3 d_wi = zero3();
-            V3 d_wo = next.d_ray.dir;
-            d_bsdf_eval(mat, d_mat, sp, wi, wo, min_rough, d_f, out.d_point, d_wi, d_wo);
-            V3 d_dir = d_wo / sqrt(dist_sq);
-            Real d_sqrt = -sum(d_wo * dir) / dist_sq;
-            Real d_dist_sq = Real(0.5) * d_sqrt / sqrt(dist_sq);
-            d_dir += d_length_sq(dir, d_dist_sq);
-            SurfacePoint d_bp = next.d_point;
-            d_bp.position += d_dir;
-            DRay d_ray = zero_dray();
-            RayDiff d_rd_b = zero_raydiff();
-            Ray bray;
-            bray.org = sp.position;
-            bray.dir = wo;
-            bray.tmin = Real(1e-3);
-            bray.tmax = INFINITY;
-            d_make_surface_point(bshape, bis.tri_id, bray, nxt->rd_in, d_bp, zero_raydiff(), d_ray, d_rd_b, d_bvp, d_bvn, d_bvuv, d_bvc);
-            // position gradient through the sampled direction only below glossy vertices (src/path_contribution.cpp:447-455)
-            if (min_rough > Real(0.01)) {
-                out.d_point.position -= d_dir;
-                out.d_point.position += d_ray.org;
-            }
-            out.d_ray.dir -= d_wi;
-            scatter_vertex_grads(sc, ds, bis, d_bvp, d_bvn, d_bvuv, d_bvc);
+            on_b = true;
+            wo_b = wo;
+            dir_b = dir;
+            dist_sq_b = dist_sq;
+            d_f_b = d_f;
+            d_wo_b = next.d_ray.dir;
         }
+    }
+    // ---- shared BSDF adjoint
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        if (!(k ? on_b : on_l)) continue;
+        V3 d_wi = zero3();
+        V3 d_wo = k ? d_wo_b : d_wo_l;
+        d_bsdf_eval(mat, d_mat, sp, wi, k ? wo_b : wo_l, min_rough, k ? d_f_b : d_f_l, out.d_point, d_wi, d_wo);
+        out.d_ray.dir -= d_wi;
+        if (k) d_wo_b = d_wo; else d_wo_l = d_wo;
+    }
+    // ---- next event estimation (post)
+    if (on_l) {
+        const Isect& lis = cur.light.isect;
+        const rb_shape& lshape = sc.shapes[lis.shape_id];
+        V3 d_dir = d_wo_l / sqrt(dist_sq_l);
+        Real d_sqrt = -sum(d_wo_l * dir_l) / dist_sq_l;
+        Real d_dist_sq = d_dist_sq_l + Real(0.5) * d_sqrt / sqrt(dist_sq_l);
+        d_dir += d_length_sq(dir_l, d_dist_sq);
+        SurfacePoint d_lp = zero_point();
+        d_lp.geom_normal = d_cos_l * wo_l;
+        d_lp.position += d_dir;
+        out.d_point.position -= d_dir;
+        d_sample_light_triangle(lshape, lis.tri_id, cur.light.uv, d_lp, d_lv);
+        int idx[3];
+        shape_tri(lshape, lis.tri_id, idx);
+        float* dv = ds.shapes[lis.shape_id].vertices;
+        if (dv) {
+            agg_add3(dv + 3 * (size_t)idx[0], d_lv[0]);
+            agg_add3(dv + 3 * (size_t)idx[1], d_lv[1]);
+            agg_add3(dv + 3 * (size_t)idx[2], d_lv[2]);
+        }
+    }
+    // ---- BSDF-sampled continuation (post)
+    if (on_b) {
+        const Isect& bis = nxt->isect;
+        const rb_shape& bshape = sc.shapes[bis.shape_id];
+        V3 d_bvp[3] = {zero3(), zero3(), zero3()}, d_bvn[3] = {zero3(), zero3(), zero3()}, d_bvc[3] = {zero3(), zero3(), zero3()};
+        V2 d_bvuv[3] = {zero2(), zero2(), zero2()};
+        V3 d_dir = d_wo_b / sqrt(dist_sq_b);
+        Real d_sqrt = -sum(d_wo_b * dir_b) / dist_sq_b;
+        Real d_dist_sq = Real(0.5) * d_sqrt / sqrt(dist_sq_b);
+        d_dir += d_length_sq(dir_b, d_dist_sq);
+        SurfacePoint d_bp = next.d_point;
+        d_bp.position += d_dir;
+        DRay d_ray = zero_dray();
+        RayDiff d_rd_b = zero_raydiff();
+        Ray bray;
+        bray.org = sp.position;
+        bray.dir = wo_b;
+        bray.tmin = Real(1e-3);
+        bray.tmax = INFINITY;
+        d_make_surface_point(bshape, bis.tri_id, bray, nxt->rd_in, d_bp, zero_raydiff(), d_ray, d_rd_b, d_bvp, d_bvn, d_bvuv, d_bvc);
+        // position gradient through the sampled direction only below glossy vertices (src/path_contribution.cpp:447-455)
+        if (min_rough > Real(0.01)) {
+            out.d_point.position -= d_dir;
+            out.d_point.position += d_ray.org;
+        }
+        scatter_vertex_grads(sc, ds, bis, d_bvp, d_bvn, d_bvuv, d_bvc);
     }
     return out;
 }

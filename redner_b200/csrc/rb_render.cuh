@@ -41,7 +41,8 @@ RB_HD unsigned long long edge_draws_per_sample(const DevScene& sc, const RenderP
 }
 
 // Camera sample -> primary ray (px, py are viewport-relative pixel coordinates), src/camera.cpp:8-43.
-RB_D void primary_ray_for(const DevScene& sc, const RenderParams& rp, int px, int py, Sampler& smp, double& sx, double& sy, Ray& ray, RayDiff& rd) {
+RB_D void primary_ray_for(const DevScene& sc, const RenderParams& rp, int px, int py, Sampler& smp, double& sx, double& sy, Ray& ray, RayDiff& rd,
+                          D3* org_d = nullptr, D3* dir_d = nullptr) {
     double jx = 0.5, jy = 0.5;
     if (!rp.sample_pixel_center) {
         jx = smp.next();
@@ -50,6 +51,7 @@ RB_D void primary_ray_for(const DevScene& sc, const RenderParams& rp, int px, in
     sx = (double(px + sc.cam.vp_beg[0]) + jx) / double(sc.cam.width);
     sy = (double(py + sc.cam.vp_beg[1]) + jy) / double(sc.cam.height);
     cam_primary_ray(sc.cam, sx, sy, ray, rd);
+    if (org_d) cam_sample_primary(sc.cam, sx, sy, *org_d, *dir_d);
 }
 
 // Radiance of one pixel sample, already multiplied by 1/spp.
@@ -60,16 +62,92 @@ RB_D V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, in
     double sx, sy;
     Ray ray;
     RayDiff rd;
-    primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd);
+    D3 od, dd;
+    primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
     Isect is = no_isect();
     V3 acc = zero3();
     if (closest_hit(sc, ray, is)) {
         RayDiff rd_after;
         SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
         acc += weight * hit_emission(sc, is, sp, -ray.dir);
-        acc += weight * trace_bounces<false>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, nullptr, 0, nullptr);
+        acc += weight * trace_bounces<false>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, nullptr, 0, nullptr, &od, &dd);
     }
     return acc;
+}
+
+// G-buffer variant of forward_sample: accumulates every requested channel of the first hit into out[0..nd)
+// (src/primary_contribution.cpp:36-253) plus the path-traced radiance.  Id channels (shape / triangle / material) are
+// assigned, not averaged ("the last sample wins" in the reference); they are returned in ids[] and resolved by the kernel.
+#define RB_MAX_ND 64
+RB_D bool forward_sample_channels(const DevScene& sc, const RenderParams& rp, int pixel, int px, int py, int s, float* out, int* ids) {
+    const Real weight = Real(1) / Real(rp.spp);
+    Sampler smp;
+    smp.init(rp.sampler_type, rp.seed, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
+    double sx, sy;
+    Ray ray;
+    RayDiff rd;
+    D3 od, dd;
+    primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
+    Isect is = no_isect();
+    if (!closest_hit(sc, ray, is)) return false;
+    RayDiff rd_after;
+    const rb_shape& shape = sc.shapes[is.shape_id];
+    const rb_material& mat = sc.materials[shape.material_id];
+    SurfacePoint sp = make_surface_point(shape, is.tri_id, ray, rd, rd_after);
+    int d = 0;
+    for (int c = 0; c < rp.num_channels; c++) {
+        switch (rp.channels[c]) {
+            case RB_CH_RADIANCE: {
+                V3 L = hit_emission(sc, is, sp, -ray.dir);
+                out[d] += (float)(weight * L.x); out[d + 1] += (float)(weight * L.y); out[d + 2] += (float)(weight * L.z);
+                d += 3;
+            } break;
+            case RB_CH_ALPHA: out[d] += (float)weight; d += 1; break;
+            case RB_CH_DEPTH: out[d] += (float)(length(sp.position - ray.org) * weight); d += 1; break;
+            case RB_CH_POSITION: out[d] += (float)(sp.position.x * weight); out[d + 1] += (float)(sp.position.y * weight); out[d + 2] += (float)(sp.position.z * weight); d += 3; break;
+            case RB_CH_GEOMETRY_NORMAL: out[d] += (float)(sp.geom_normal.x * weight); out[d + 1] += (float)(sp.geom_normal.y * weight); out[d + 2] += (float)(sp.geom_normal.z * weight); d += 3; break;
+            case RB_CH_SHADING_NORMAL: {
+                V3 n = sp.shading_frame.n;
+                if (mat_has_normal_map(mat)) n = perturb_shading_frame(mat, sp).n;
+                out[d] += (float)(n.x * weight); out[d + 1] += (float)(n.y * weight); out[d + 2] += (float)(n.z * weight);
+                d += 3;
+            } break;
+            case RB_CH_UV: out[d] += (float)(sp.uv.x * weight); out[d + 1] += (float)(sp.uv.y * weight); d += 2; break;
+            case RB_CH_BARYCENTRIC: out[d] += (float)(sp.bary.x * weight); out[d + 1] += (float)(sp.bary.y * weight); d += 2; break;
+            case RB_CH_DIFFUSE_REFLECTANCE: {
+                V3 r = mat.use_vertex_color ? sp.color : mat_diffuse(mat, sp);
+                out[d] += (float)(r.x * weight); out[d + 1] += (float)(r.y * weight); out[d + 2] += (float)(r.z * weight);
+                d += 3;
+            } break;
+            case RB_CH_SPECULAR_REFLECTANCE: {
+                V3 r = mat_specular(mat, sp);
+                out[d] += (float)(r.x * weight); out[d + 1] += (float)(r.y * weight); out[d + 2] += (float)(r.z * weight);
+                d += 3;
+            } break;
+            case RB_CH_ROUGHNESS: out[d] += (float)(mat_roughness(mat, sp) * weight); d += 1; break;
+            case RB_CH_GENERIC_TEXTURE: {
+                if (mat.generic_texture.num_levels > 0) {
+                    Real buf[RB_MAX_ND];
+                    int n = mat.generic_texture.channels < RB_MAX_ND ? mat.generic_texture.channels : RB_MAX_ND;
+                    tex_eval(mat.generic_texture, n, sp.uv, sp.du_dxy, sp.dv_dxy, buf);
+                    for (int i = 0; i < n; i++) out[d + i] += (float)(buf[i] * weight);
+                }
+                d += rp.max_generic;
+            } break;
+            case RB_CH_VERTEX_COLOR: out[d] += (float)(sp.color.x * weight); out[d + 1] += (float)(sp.color.y * weight); out[d + 2] += (float)(sp.color.z * weight); d += 3; break;
+            case RB_CH_SHAPE_ID: ids[0] = is.shape_id; d += 1; break;
+            case RB_CH_TRIANGLE_ID: ids[1] = is.tri_id; d += 1; break;
+            case RB_CH_MATERIAL_ID: ids[2] = shape.material_id; d += 1; break;
+            default: break;
+        }
+    }
+    if (rp.rad_dim >= 0) {
+        V3 Lb = weight * trace_bounces<false>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, nullptr, 0, nullptr, &od, &dd);
+        // path contributions land at float offset `rad_dim` == the channel INDEX of radiance, like the reference
+        // (src/channels.cpp:27, src/path_contribution.cpp:125-129)
+        out[rp.rad_dim] += (float)Lb.x; out[rp.rad_dim + 1] += (float)Lb.y; out[rp.rad_dim + 2] += (float)Lb.z;
+    }
+    return true;
 }
 
 // Adjoint of one pixel sample.  `recs` is this thread's private record array (max_bounces + 2 entries).
@@ -83,13 +161,14 @@ RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, in
     double sx, sy;
     Ray ray;
     RayDiff rd;
-    primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd);
+    D3 od, dd;
+    primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
     Isect is = no_isect();
     if (!closest_hit(sc, ray, is)) return -1;
     const float* dpx = ka.d_image + (size_t)rp.nd * pixel + rp.rad_dim;
     V3 d_contrib = weight * mk3(dpx[0], dpx[1], dpx[2]);
     int nrec = 0;
-    trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, recs, 1, &nrec);
+    trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, recs, 1, &nrec, &od, &dd);
     // reverse sweep over the interior vertices (src/pathtracer.cpp:431-714)
     VertexAdjoint adj = zero_vertex_adjoint();
     for (int d = nrec - 1; d >= 0; d--) {
@@ -140,9 +219,11 @@ RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, in
     d_ray.dir += (d_prd.dir_dx * (-psx) + d_prd.dir_dy * (-psy)) / delta;
     V2 d_screen = zero2();
     V2* d_screen_ptr = ka.screen_grad ? &d_screen : nullptr;
-    d_cam_sample_primary(sc.cam, (Real)sx, (Real)sy, d_ray, cam_acc, d_screen_ptr);
-    d_cam_sample_primary(sc.cam, (Real)sx + delta, (Real)sy, d_ray_dx, cam_acc, d_screen_ptr);
-    d_cam_sample_primary(sc.cam, (Real)sx, (Real)sy + delta, d_ray_dy, cam_acc, d_screen_ptr);
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) { // centre ray and its two offset rays; rolled to keep one copy of the camera adjoint
+        DRay dr = k == 0 ? d_ray : k == 1 ? d_ray_dx : d_ray_dy;
+        d_cam_sample_primary(sc.cam, (Real)sx + (k == 1 ? delta : Real(0)), (Real)sy + (k == 2 ? delta : Real(0)), dr, cam_acc, d_screen_ptr);
+    }
     if (ka.screen_grad) {
         rb_red_add(&ka.screen_grad[2 * (size_t)pixel + 0], (float)d_screen.x);
         rb_red_add(&ka.screen_grad[2 * (size_t)pixel + 1], (float)d_screen.y);

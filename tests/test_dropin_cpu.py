@@ -1,0 +1,49 @@
+"""CPU suite, part 4: the drop-in claim.  Where the reference checkout is present (build container), the UNMODIFIED
+pyredner package is imported on top of redner_b200/dropin/redner.py and its own RenderFunction marshals a scene all the
+way into our C ABI (which then refuses to render without a GPU -- there is no CPU path)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+SCRIPT = r'''
+import sys, types
+sys.path.insert(0, %(dropin)r)
+sys.path.insert(0, %(ref)r)
+for name in ("skimage", "skimage.io", "skimage.transform", "imageio"):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules["skimage"].io = sys.modules["skimage.io"]
+sys.modules["skimage"].transform = sys.modules["skimage.transform"]
+import torch, pyredner, redner
+assert redner.__file__.startswith(%(dropin)r), redner.__file__
+pyredner.set_use_gpu(torch.cuda.is_available())
+cam = pyredner.Camera(position=torch.tensor([0., 0., -5.]), look_at=torch.tensor([0., 0., 0.]), up=torch.tensor([0., 1., 0.]),
+                      fov=torch.tensor([45.]), clip_near=1e-2, resolution=(16, 16))
+dev = pyredner.get_device()
+mat = pyredner.Material(diffuse_reflectance=torch.tensor([0.5, 0.5, 0.5], device=dev))
+tri = pyredner.Shape(vertices=torch.tensor([[-2.0, 1.5, 0.3], [0.9, 1.2, -0.3], [-0.4, -1.4, 0.2]], device=dev),
+                     indices=torch.tensor([[0, 1, 2]], dtype=torch.int32, device=dev), uvs=None, normals=None, material_id=0)
+lgt = pyredner.Shape(vertices=torch.tensor([[-1., -1., -7.], [1., -1., -7.], [-1., 1., -7.], [1., 1., -7.]], device=dev),
+                     indices=torch.tensor([[0, 1, 2], [1, 3, 2]], dtype=torch.int32, device=dev), uvs=None, normals=None, material_id=0)
+scene = pyredner.Scene(cam, [tri, lgt], [mat], [pyredner.AreaLight(shape_id=1, intensity=torch.tensor([20., 20., 20.]))])
+args = pyredner.RenderFunction.serialize_scene(scene=scene, num_samples=4, max_bounces=1)
+try:
+    img = pyredner.RenderFunction.apply(0, *args)
+    print("RENDERED", float(img.mean()))
+except RuntimeError as e:
+    print("ABI-ERROR", e)
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pyredner")), reason="reference checkout not present")
+def test_unmodified_pyredner_runs_on_the_dropin_module():
+    code = SCRIPT % {"dropin": os.path.join(ROOT, "redner_b200", "dropin"), "ref": REF}
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    last = out.stdout.strip().splitlines()[-1]
+    # on a CPU-only machine the call must arrive at rb_scene_create and be refused loudly; on a GPU box it renders
+    assert last.startswith("RENDERED") or ("ABI-ERROR" in last and "no CPU path" in last), last

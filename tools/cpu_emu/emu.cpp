@@ -222,7 +222,35 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
     ka.d_image = d_image;
     ka.screen_grad = screen_grad;
     const DevScene& sc = scene->dev;
-    if (image) {
+    for (int i = 0; i < opt->num_channels; i++) rp.channels[i] = opt->channels[i];
+    rp.max_generic = scene->max_generic;
+    bool only_radiance = opt->num_channels == 1 && opt->channels[0] == RB_CH_RADIANCE;
+    if (image && !only_radiance) {
+        for (int y = 0; y < rp.vp_h; y++)
+            for (int x = 0; x < rp.vp_w; x++) {
+                int pixel = y * rp.vp_w + x;
+                float acc[RB_MAX_ND] = {0};
+                int ids[3] = {-1, -1, -1}, last = -1;
+                for (int s = 0; s < rp.spp; s++) {
+                    int cur[3] = {-1, -1, -1};
+                    if (forward_sample_channels(sc, rp, pixel, x, y, s, acc, cur)) { last = s; ids[0] = cur[0]; ids[1] = cur[1]; ids[2] = cur[2]; }
+                }
+                float* px = image + (size_t)rp.nd * pixel;
+                int d = 0;
+                for (int c = 0; c < rp.num_channels; c++) {
+                    int ch = rp.channels[c];
+                    int width = (ch == RB_CH_RADIANCE || ch == RB_CH_POSITION || ch == RB_CH_GEOMETRY_NORMAL || ch == RB_CH_SHADING_NORMAL ||
+                                 ch == RB_CH_DIFFUSE_REFLECTANCE || ch == RB_CH_SPECULAR_REFLECTANCE || ch == RB_CH_VERTEX_COLOR) ? 3
+                              : (ch == RB_CH_UV || ch == RB_CH_BARYCENTRIC) ? 2 : (ch == RB_CH_GENERIC_TEXTURE ? rp.max_generic : 1);
+                    if (ch == RB_CH_SHAPE_ID || ch == RB_CH_TRIANGLE_ID || ch == RB_CH_MATERIAL_ID) {
+                        if (last >= 0) px[d] = (float)ids[ch - RB_CH_SHAPE_ID];
+                    } else {
+                        for (int i = 0; i < width; i++) px[d + i] += acc[d + i];
+                    }
+                    d += width;
+                }
+            }
+    } else if (image) {
         for (int y = 0; y < rp.vp_h; y++)
             for (int x = 0; x < rp.vp_w; x++) {
                 int pixel = y * rp.vp_w + x;
