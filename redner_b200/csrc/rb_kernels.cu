@@ -179,6 +179,21 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_BWD) k_backward(const 
     const int nb = (rp.spp + L - 1) / L;
     VertexRec* recs = ka.records + (size_t)gtid * ka.rec_per_thread;
     int n_vertices = 0, n_hits = 0;
+#ifdef RB_LOCKSTEP
+    for (long long g0 = 0; g0 < groups; g0 += nwarps) { // block-uniform trip count: the barriers inside need every warp
+        long long g = g0 + warp;
+        WorkItem w = warp_work(rp, L, ka.owned_rows, g < groups ? g : 0);
+        if (g >= groups) w.valid = false;
+        for (int b = 0; b < nb; b++) {
+            int s = b * L + w.sample_lane;
+            int nv = backward_sample(sc, ka, w.pixel, w.px, w.py, s, recs, cam_acc, w.valid && s < rp.spp);
+            if (nv >= 0) {
+                n_hits++;
+                n_vertices += nv;
+            }
+        }
+    }
+#else
     for (long long g = warp; g < groups; g += nwarps) {
         WorkItem w = warp_work(rp, L, ka.owned_rows, g);
         for (int b = 0; b < nb; b++) {
@@ -192,6 +207,7 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_BWD) k_backward(const 
             }
         }
     }
+#endif
     // statistics for the roofline accounting (mean executed bounces per sample)
     for (int off = 16; off > 0; off >>= 1) {
         n_vertices += __shfl_xor_sync(0xffffffffu, n_vertices, off);

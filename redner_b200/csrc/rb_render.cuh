@@ -152,30 +152,53 @@ RB_D bool forward_sample_channels(const DevScene& sc, const RenderParams& rp, in
 
 // Adjoint of one pixel sample.  `recs` is this thread's private record array (max_bounces + 2 entries).
 // Returns the number of path vertices at which a radiance estimate was formed (-1 if the primary ray missed).
-RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, int px, int py, int s, VertexRec* recs, CamAcc& cam_acc) {
+#ifdef RB_LOCKSTEP // experiment: block-wide phase barriers so that the warps of a block walk the code together
+#define RB_PHASE_SYNC() __syncthreads()
+#else
+#define RB_PHASE_SYNC()
+#endif
+RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, int px, int py, int s, VertexRec* recs, CamAcc& cam_acc, bool act = true) {
     const RenderParams& rp = ka.rp;
     const DevDScene& ds = ka.ds;
     const Real weight = Real(1) / Real(rp.spp);
     Sampler smp;
-    smp.init(rp.sampler_type, rp.seed, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
-    double sx, sy;
+    double sx = 0, sy = 0;
     Ray ray;
     RayDiff rd;
     D3 od, dd;
-    primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
     Isect is = no_isect();
-    if (!closest_hit(sc, ray, is)) return -1;
+    RB_PHASE_SYNC();
+    if (act) {
+        smp.init(rp.sampler_type, rp.seed, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
+        primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
+        act = closest_hit(sc, ray, is);
+    }
+#ifndef RB_LOCKSTEP
+    if (!act) return -1;
+#endif
     const float* dpx = ka.d_image + (size_t)rp.nd * pixel + rp.rad_dim;
-    V3 d_contrib = weight * mk3(dpx[0], dpx[1], dpx[2]);
+    V3 d_contrib = act ? weight * mk3(dpx[0], dpx[1], dpx[2]) : zero3();
     int nrec = 0;
-    trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, recs, 1, &nrec, &od, &dd);
+    RB_PHASE_SYNC();
+    if (act) trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, recs, 1, &nrec, &od, &dd);
     // reverse sweep over the interior vertices (src/pathtracer.cpp:431-714)
     VertexAdjoint adj = zero_vertex_adjoint();
+#ifdef RB_LOCKSTEP
+    for (int d = rp.max_bounces - 1; d >= 0; d--) {
+        bool on = act && d < nrec;
+#else
     for (int d = nrec - 1; d >= 0; d--) {
-        VertexRec cur = recs[d];
-        VertexRec nxt = recs[d + 1];
-        adj = d_vertex(sc, ds, cur, &nxt, d_contrib, adj);
-        if (sc.use_secondary_edge && sc.num_edges > 0) {
+        const bool on = true;
+#endif
+        VertexRec cur, nxt;
+        RB_PHASE_SYNC();
+        if (on) {
+            cur = recs[d];
+            nxt = recs[d + 1];
+            adj = d_vertex(sc, ds, cur, &nxt, d_contrib, adj);
+        }
+        RB_PHASE_SYNC();
+        if (on && sc.use_secondary_edge && sc.num_edges > 0) {
             // boundary term of the visibility at this vertex (src/pathtracer.cpp:500-707)
             Sampler es;
             es.init(rp.sampler_type, rp.seed + 131071ULL, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS,
@@ -190,6 +213,10 @@ RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, in
             secondary_edge_sample(sc, ds, rp, cur, d, es, mk3(dpx[0], dpx[1], dpx[2]), coin, adj.d_point.position);
         }
     }
+    RB_PHASE_SYNC();
+#ifdef RB_LOCKSTEP
+    if (!act) return -1;
+#endif
     // first vertex: emission adjoint (src/primary_contribution.cpp:449-466) ...
     RayDiff rd_after;
     SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);

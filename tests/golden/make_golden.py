@@ -31,7 +31,10 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 def main():
     ref = ref_loader.load()
     dev = torch.device("cpu")
+    only = set(sys.argv[1:])  # optional: regenerate only the named cases
     for name, cfg in CASES.items():
+        if only and name not in only:
+            continue
         img, grads = render_case(ref, dev, cfg, cfg["seed"])
         arrs = {"image": img.numpy()}
         for k, v in grads.items():
@@ -39,6 +42,8 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
         print(name, "image mean %.6f" % img.mean().item(), {k: float(v.norm()) for k, v in grads.items()})
     for name, cfg in STAT_CASES.items():
+        if only and name not in only:
+            continue
         acc = {}
         for seed in cfg["seeds"]:
             _, grads = render_case(ref, dev, cfg, seed)

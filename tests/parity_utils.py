@@ -20,6 +20,8 @@ CASES = {
     # glossy textured room: specular lobe, shading normals, uvs, mip-mapped textures, two lights, 2 bounces
     "glossy_room_sobol_mb2": dict(scene="glossy_room", res=48, spp=8, mb=2, sampler="sobol", edges=0, seed=5),
     "glossy_room_pcg_mb3": dict(scene="glossy_room", res=32, spp=4, mb=3, sampler="independent", edges=0, seed=7),
+    # normal-mapped ball with a mip-mapped specular texture and a differentiable uv_scale
+    "nmap_room_sobol_mb2": dict(scene="nmap_room", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=11),
 }
 STAT_CASES = {
     # secondary-edge (shadow) gradient of the blocker: mean over seeds +- standard error
@@ -43,10 +45,12 @@ def collect_grads(scene):
             if t is not None and t.grad is not None:
                 out["shape%d.%s" % (i, k)] = t.grad.detach().cpu().clone()
     for i, m in enumerate(scene.materials):
-        for k in ("diffuse_reflectance", "specular_reflectance", "roughness"):
+        for k in ("diffuse_reflectance", "specular_reflectance", "roughness", "normal_map"):
             t = getattr(m, k)
             if t is not None and t.texels.grad is not None:
                 out["mat%d.%s" % (i, k)] = t.texels.grad.detach().cpu().clone()
+            if t is not None and t.uv_scale.grad is not None:
+                out["mat%d.%s.uv_scale" % (i, k)] = t.uv_scale.grad.detach().cpu().clone()
     for i, l in enumerate(scene.area_lights):
         if l.intensity.grad is not None:
             out["light%d.intensity" % i] = l.intensity.grad.detach().cpu().clone()

@@ -70,7 +70,7 @@ def uv_sphere(device, radius, center, n_theta=12, n_phi=24, grad=False):
     return (_t(verts, device, grad=grad), _t(idx, device, torch.int32), _t(uvs, device), _t(normals, device))
 
 
-def glossy_room(device, resolution=(128, 128), grad=True, textured=True):
+def glossy_room(device, resolution=(128, 128), grad=True, textured=True, nmap=False):
     """Open box (floor, back wall, side wall) with a glossy textured floor, a Phong-shaded sphere and two area lights."""
     g = torch.Generator().manual_seed(7)
     cam = api.Camera(position=torch.tensor([0.3, 1.4, -4.5]), look_at=torch.tensor([0.0, 0.6, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
@@ -87,8 +87,17 @@ def glossy_room(device, resolution=(128, 128), grad=True, textured=True):
     m_floor = api.Material(diffuse_reflectance=api.Texture(tex, torch.tensor([2.0, 2.0], device=device)),
                            specular_reflectance=_t([0.3, 0.3, 0.3], device, grad=grad), roughness=api.Texture(rough, torch.tensor([2.0, 2.0], device=device)))
     m_wall = api.Material(diffuse_reflectance=_t([0.6, 0.3, 0.25], device, grad=grad), two_sided=True)
-    m_ball = api.Material(diffuse_reflectance=_t([0.2, 0.35, 0.6], device, grad=grad), specular_reflectance=_t([0.5, 0.5, 0.5], device, grad=grad),
-                          roughness=_t([0.2], device, grad=grad))
+    if nmap:
+        # bumpy ball: mip-mapped normal map + mip-mapped specular texture with a differentiable uv_scale
+        nm = torch.tensor([0.5, 0.5, 1.0]) + 0.25 * (torch.rand(8, 8, 3, generator=g) - 0.5)
+        nm = nm.to(device).requires_grad_(grad)
+        spec = (0.2 + 0.5 * torch.rand(8, 8, 3, generator=g)).to(device).requires_grad_(grad)
+        m_ball = api.Material(diffuse_reflectance=_t([0.2, 0.35, 0.6], device, grad=grad),
+                              specular_reflectance=api.Texture(spec, torch.tensor([3.0, 2.0], device=device, requires_grad=grad)),
+                              roughness=_t([0.2], device, grad=grad), normal_map=api.Texture(nm, torch.tensor([2.0, 2.0], device=device)))
+    else:
+        m_ball = api.Material(diffuse_reflectance=_t([0.2, 0.35, 0.6], device, grad=grad), specular_reflectance=_t([0.5, 0.5, 0.5], device, grad=grad),
+                              roughness=_t([0.2], device, grad=grad))
     m_light = api.Material(diffuse_reflectance=_t([0.0, 0.0, 0.0], device))
     floor = api.Shape(_t([[-2.5, 0.0, -2.5], [-2.5, 0.0, 2.5], [2.5, 0.0, -2.5], [2.5, 0.0, 2.5]], device),
                       _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 0, uvs=_t([[0.0, 0.0], [0.0, 1.0], [1.0, 0.0], [1.0, 1.0]], device))
@@ -122,4 +131,10 @@ def random_soup(device, num_tris=2000, resolution=(256, 256), seed=3, grad=False
     return api.Scene(cam, [soup, floor, light], [m, m_l], [api.AreaLight(2, torch.tensor([30.0, 30.0, 30.0]))])
 
 
-SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup}
+def nmap_room(device, **kw):
+    """glossy_room with a normal-mapped, specular-textured ball (normal-map and uv_scale adjoints)."""
+    return glossy_room(device, nmap=True, **kw)
+
+
+SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
+          "nmap_room": nmap_room}

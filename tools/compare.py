@@ -29,26 +29,8 @@ def rel(a, b):
 
 
 def grads_of(scene):
-    out = {}
-    cam = scene.camera
-    for k in ("position", "look_at", "up"):
-        t = getattr(cam, k)
-        if t is not None and t.grad is not None:
-            out["cam." + k] = t.grad.clone()
-    for i, s in enumerate(scene.shapes):
-        for k in ("vertices", "uvs", "normals", "colors"):
-            t = getattr(s, k)
-            if t is not None and t.grad is not None:
-                out["shape%d.%s" % (i, k)] = t.grad.clone()
-    for i, m in enumerate(scene.materials):
-        for k in ("diffuse_reflectance", "specular_reflectance", "roughness"):
-            t = getattr(m, k)
-            if t is not None and t.texels.grad is not None:
-                out["mat%d.%s" % (i, k)] = t.texels.grad.clone()
-    for i, l in enumerate(scene.area_lights):
-        if l.intensity.grad is not None:
-            out["light%d.intensity" % i] = l.intensity.grad.clone()
-    return out
+    import parity_utils
+    return {k: v.clone() for k, v in parity_utils.collect_grads(scene).items()}
 
 
 def run(backend, device, name, res, spp, mb, edges, sampler, seed, do_backward=True, **kw):
