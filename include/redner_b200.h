@@ -189,10 +189,14 @@ int rb_scene_set_partition(rb_scene* scene, int part, int num_parts, int rows_pe
 int rb_scene_last_stats(const rb_scene* scene, int* num_kernel_launches, float* kernel_ms);
 
 /* Per-kernel device times of the last rb_render (CUDA events on the render stream), in launch order
- * { k_forward, k_backward, k_primary_edge, k_finish_camera } (0 for kernels that did not run), the number of path
+ * { k_forward, backward bands (trace + boundary terms + sweep), k_primary_edge, k_finish_camera } (0 for kernels that
+ * did not run), the number of path
  * vertices at which the last backward pass formed a radiance estimate and its number of primary hits (mean executed
  * bounces per sample = path_vertices / (W*H*spp)). */
 int rb_scene_last_stage_stats(const rb_scene* scene, float* stage_ms4, double* path_vertices, double* primary_hits);
+/* Split of the backward bands of the last rb_render, summed over the bands:
+ * { k_bwd_trace, scan + compaction + k_bwd_secondary, k_bwd_sweep } in milliseconds. */
+int rb_scene_last_backward_stats(const rb_scene* scene, float* bwd_ms3);
 /* Host wall-clock milliseconds rb_scene_create spent in { BVH build, light tables, edge list + edge tree }. */
 int rb_scene_build_ms(const rb_scene* scene, float* bvh_lights_edges3);
 

@@ -13,6 +13,9 @@
 // The per-sample logic itself lives in rb_render.cuh.
 #include <cuda_runtime.h>
 
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -24,6 +27,18 @@
 #define RB_BLOCK 128
 #ifndef RB_MIN_BLOCKS_FWD
 #define RB_MIN_BLOCKS_FWD 4
+#endif
+#ifndef RB_MIN_BLOCKS_TRACE
+#define RB_MIN_BLOCKS_TRACE 4
+#endif
+#ifndef RB_MIN_BLOCKS_SEC
+#define RB_MIN_BLOCKS_SEC 4
+#endif
+#ifndef RB_MIN_BLOCKS_SWEEP
+#define RB_MIN_BLOCKS_SWEEP 4
+#endif
+#ifndef RB_BAND_BYTES
+#define RB_BAND_BYTES (1ULL << 30) // scratch budget of one backward band (records + lists)
 #endif
 #ifndef RB_MIN_BLOCKS_BWD
 #define RB_MIN_BLOCKS_BWD 4
@@ -65,6 +80,11 @@ RB_D WorkItem warp_work(const RenderParams& rp, int L, int owned_rows, long long
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+#ifdef RB_LOCKSTEP_FWD
+#define RB_FWD_SYNC() __syncthreads()
+#else
+#define RB_FWD_SYNC()
+#endif
 __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_FWD) k_forward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     const RenderParams& rp = ka.rp;
     const int L = ka.lanes_per_pixel;
@@ -74,11 +94,14 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_FWD) k_forward(const _
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int nb = (rp.spp + L - 1) / L;
-    for (long long g = warp; g < groups; g += nwarps) {
-        WorkItem w = warp_work(rp, L, ka.owned_rows, g);
+    for (long long g0 = 0; g0 < groups; g0 += nwarps) { // block-uniform trip count (phase barrier inside)
+        long long g = g0 + warp;
+        WorkItem w = warp_work(rp, L, ka.owned_rows, g < groups ? g : 0);
+        if (g >= groups) w.valid = false;
         V3 acc = zero3();
         for (int b = 0; b < nb; b++) {
             int s = b * L + w.sample_lane;
+            RB_FWD_SYNC();
             if (w.valid && s < rp.spp) acc += forward_sample(sc, rp, w.pixel, w.px, w.py, s);
         }
         for (int off = L >> 1; off > 0; off >>= 1) {
@@ -162,66 +185,101 @@ RB_D void block_reduce_camera(float* cam_smem, double* cam_accum) {
     }
 }
 
-__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_BWD) k_backward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+// Dense sample index of the band -> (pixel, px, py, s).  Consecutive lanes are consecutive samples of a pixel.
+struct SampleId {
+    int pixel, px, py, s;
+};
+RB_D SampleId band_sample(const RenderParams& rp, long long I) {
+    long long k = I / rp.spp;
+    SampleId id;
+    id.s = (int)(I - k * rp.spp);
+    int j = (int)(k / rp.vp_w);
+    id.px = (int)(k - (long long)j * rp.vp_w);
+    id.py = owned_row_to_row(rp, j);
+    id.pixel = id.py * rp.vp_w + id.px;
+    return id;
+}
+// The work loops below are BLOCK-uniform (every thread of a block runs the same number of iterations, idle ones with
+// act == false) because the per-sample stages contain phase barriers (RB_PHASE_SYNC, rb_render.cuh).
+#define RB_BLOCK_LOOP(t, n) \
+    for (long long t##_base = (long long)blockIdx.x * blockDim.x, t = t##_base + threadIdx.x; t##_base < (n); \
+         t##_base += (long long)gridDim.x * blockDim.x, t = t##_base + threadIdx.x)
+// Stage 1: replay the primal path of every sample of the band, one VertexRec per vertex.
+__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_TRACE) k_bwd_trace(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+    const RenderParams& rp = ka.rp;
+    RB_BLOCK_LOOP(t, ka.band_n) {
+        bool act = t < ka.band_n;
+        SampleId id = band_sample(rp, ka.band_i0 + (act ? t : 0));
+        int n = bwd_trace(sc, rp, id.pixel, id.px, id.py, id.s, ka.records + (size_t)(act ? t : 0) * ka.rec_per_sample, 1, act);
+        if (act) ka.nrec[t] = n;
+    }
+}
+// (hit << 32 | vertices) of one sample: the scan input
+struct CountOp {
+    __host__ __device__ unsigned long long operator()(int nrec) const { return nrec < 0 ? 0ULL : ((1ULL << 32) | (unsigned long long)nrec); }
+};
+// Stage 2: deterministic compaction from the exclusive scan: samples that hit something, and their vertices.
+__global__ void k_bwd_compact(const __grid_constant__ KernelArgs ka) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ka.band_n; t += (long long)gridDim.x * blockDim.x) {
+        int n = ka.nrec[t];
+        unsigned long long o = ka.offs[t];
+        if (n >= 0) {
+            ka.path_list[(unsigned)(o >> 32)] = (int)t;
+            unsigned v = (unsigned)(o & 0xffffffffULL);
+            for (int d = 0; d < n; d++) ka.vert_list[v + d] = (int)t * ka.rec_per_sample + d;
+        }
+        if (t == ka.band_n - 1) {
+            unsigned long long tot = o + CountOp()(n);
+            *ka.totals = tot;
+            // statistics for the roofline accounting (mean executed bounces per sample)
+            atomicAdd(&ka.ds.cam_accum[RB_CAM_ACC], (double)(tot & 0xffffffffULL));
+            atomicAdd(&ka.ds.cam_accum[RB_CAM_ACC + 1], (double)(tot >> 32));
+        }
+    }
+}
+// Stage 3: boundary term of every path vertex (secondary edge sampling); full warps of vertices.
+__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SEC) k_bwd_secondary(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+    const RenderParams& rp = ka.rp;
+    const long long n = (long long)(*ka.totals & 0xffffffffULL);
+    RB_BLOCK_LOOP(t, n) {
+        RB_PHASE_SYNC();
+        if (t < n) {
+            int e = ka.vert_list[t];
+            int ts = e / ka.rec_per_sample, d = e - ts * ka.rec_per_sample;
+            SampleId id = band_sample(rp, ka.band_i0 + ts);
+            // fair strategy coin shared by the 32 vertices of this warp (they sit next to each other in the list)
+            unsigned long long h = rb_hash64shift(((unsigned long long)((ka.band_i0 >> 5) + (t >> 5)) << 20) ^ (rp.seed << 44) ^ 0x9e3779b97f4a7c15ULL);
+            VertexRec cur = ka.records[e];
+            ka.dpos[e] = bwd_secondary(sc, ka, id.pixel, id.s, d, cur, (int)((h >> 17) & 1ULL));
+        }
+    }
+}
+// Stage 4: reverse sweep of every path, first-hit and camera adjoints.
+__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SWEEP) k_bwd_sweep(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     __shared__ float cam_smem[RB_CAM_ACC * RB_BLOCK];
     for (int k = 0; k < RB_CAM_ACC; k++) cam_smem[k * RB_BLOCK + threadIdx.x] = 0.f;
     CamAcc cam_acc;
     cam_acc.base = cam_smem + threadIdx.x;
     cam_acc.stride = RB_BLOCK;
     const RenderParams& rp = ka.rp;
-    const int L = ka.lanes_per_pixel;
-    const int P = 32 / L;
-    long long n_px = (long long)ka.owned_rows * rp.vp_w;
-    long long groups = (n_px + P - 1) / P;
-    long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long warp = gtid >> 5;
-    long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int nb = (rp.spp + L - 1) / L;
-    VertexRec* recs = ka.records + (size_t)gtid * ka.rec_per_thread;
-    int n_vertices = 0, n_hits = 0;
-#ifdef RB_LOCKSTEP
-    for (long long g0 = 0; g0 < groups; g0 += nwarps) { // block-uniform trip count: the barriers inside need every warp
-        long long g = g0 + warp;
-        WorkItem w = warp_work(rp, L, ka.owned_rows, g < groups ? g : 0);
-        if (g >= groups) w.valid = false;
-        for (int b = 0; b < nb; b++) {
-            int s = b * L + w.sample_lane;
-            int nv = backward_sample(sc, ka, w.pixel, w.px, w.py, s, recs, cam_acc, w.valid && s < rp.spp);
-            if (nv >= 0) {
-                n_hits++;
-                n_vertices += nv;
-            }
-        }
-    }
-#else
-    for (long long g = warp; g < groups; g += nwarps) {
-        WorkItem w = warp_work(rp, L, ka.owned_rows, g);
-        for (int b = 0; b < nb; b++) {
-            int s = b * L + w.sample_lane;
-            if (w.valid && s < rp.spp) {
-                int nv = backward_sample(sc, ka, w.pixel, w.px, w.py, s, recs, cam_acc);
-                if (nv >= 0) {
-                    n_hits++;
-                    n_vertices += nv;
-                }
-            }
-        }
-    }
-#endif
-    // statistics for the roofline accounting (mean executed bounces per sample)
-    for (int off = 16; off > 0; off >>= 1) {
-        n_vertices += __shfl_xor_sync(0xffffffffu, n_vertices, off);
-        n_hits += __shfl_xor_sync(0xffffffffu, n_hits, off);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&ka.ds.cam_accum[RB_CAM_ACC], (double)n_vertices);
-        atomicAdd(&ka.ds.cam_accum[RB_CAM_ACC + 1], (double)n_hits);
+    const long long n = (long long)(*ka.totals >> 32);
+    RB_BLOCK_LOOP(t, n) {
+        bool act = t < n;
+        int ts = act ? ka.path_list[t] : 0;
+        SampleId id = band_sample(rp, ka.band_i0 + ts);
+        size_t base = (size_t)ts * ka.rec_per_sample;
+        bwd_sweep(sc, ka, id.pixel, id.px, id.py, id.s, ka.records + base, 1, act ? ka.nrec[ts] : 0, ka.dpos ? ka.dpos + base : nullptr, cam_acc, act);
     }
     block_reduce_camera(cam_smem, ka.ds.cam_accum);
 }
 
 // ------------------------------------------------------------------------------------------------ primary edges
 // One thread per (edge sample i, spp sample s).
+#ifdef RB_LOCKSTEP_PRIM
+#define RB_PRIM_SYNC() __syncthreads()
+#else
+#define RB_PRIM_SYNC()
+#endif
 __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_BWD) k_primary_edge(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka, int dim_base) {
     __shared__ float cam_smem[RB_CAM_ACC * RB_BLOCK];
     for (int k = 0; k < RB_CAM_ACC; k++) cam_smem[k * RB_BLOCK + threadIdx.x] = 0.f;
@@ -233,11 +291,14 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_BWD) k_primary_edge(co
     // samples of this device: i with i % num_parts == part
     const long long n_mine = (n_px - rp.part + rp.num_parts - 1) / rp.num_parts;
     const long long total = n_mine * rp.spp;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        // consecutive threads share the edge-sample index and differ in the spp sample
-        long long i = (t / rp.spp) * rp.num_parts + rp.part;
-        int s = (int)(t % rp.spp);
-        primary_edge_sample(sc, ka, i, s, dim_base, cam_acc);
+    RB_BLOCK_LOOP(t, total) {
+        RB_PRIM_SYNC();
+        if (t < total) {
+            // consecutive threads share the edge-sample index and differ in the spp sample
+            long long i = (t / rp.spp) * rp.num_parts + rp.part;
+            int s = (int)(t % rp.spp);
+            primary_edge_sample(sc, ka, i, s, dim_base, cam_acc);
+        }
     }
     block_reduce_camera(cam_smem, ka.ds.cam_accum);
 }
@@ -342,7 +403,9 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
     int launches = 0;
     double host_stats[2] = {0, 0};
     std::vector<void*> temps;
+    std::vector<cudaEvent_t> band_events; // 4 per backward band: start, after trace, after compaction+secondary, after sweep
     auto cleanup = [&]() {
+        for (cudaEvent_t e : band_events) cudaEventDestroy(e);
         for (void* p : temps) cudaFreeAsync(p, stream);
         for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
         cudaSetDevice(prev);
@@ -395,14 +458,55 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         ka.ds.light_intensity = d_lights;
         ka.ds.cam_accum = cam_accum;
 
-        int grid = pick_grid((const void*)k_backward, scene->device, nullptr);
-        ka.rec_per_thread = rp.max_bounces + 2;
-        VertexRec* recs = nullptr;
-        RB_CUDA_OK(cudaMallocAsync((void**)&recs, (size_t)grid * RB_BLOCK * ka.rec_per_thread * sizeof(VertexRec), stream));
-        temps.push_back(recs);
-        ka.records = recs;
-        k_backward<<<grid, RB_BLOCK, 0, stream>>>(scene->dev, ka);
-        launches++;
+        // ---- interior + first-hit adjoints, band by band: trace -> scan/compact -> boundary terms -> sweep
+        const bool secondary = scene->dev.use_secondary_edge && scene->dev.num_edges > 0 && scene->dev.num_lights > 0;
+        const long long total_samples = (long long)ka.owned_rows * rp.vp_w * rp.spp;
+        ka.rec_per_sample = rp.max_bounces + 1;
+        const size_t per_sample = (size_t)ka.rec_per_sample * (sizeof(VertexRec) + (secondary ? sizeof(V3) : 0) + sizeof(int)) + 2 * sizeof(int) + sizeof(unsigned long long);
+        long long band = (long long)std::max<size_t>(RB_BAND_BYTES / per_sample, 32768);
+        band = std::min<long long>(band, (1LL << 30) / ka.rec_per_sample);
+        band = std::min<long long>(band, std::max<long long>(total_samples, 1));
+        char* scratch = nullptr;
+        size_t scan_bytes = 0;
+        cub::TransformInputIterator<unsigned long long, CountOp, const int*> probe((const int*)nullptr, CountOp());
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, probe, (unsigned long long*)nullptr, (int)band, stream);
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        size_t o_rec = 0, o_dpos = o_rec + al((size_t)band * ka.rec_per_sample * sizeof(VertexRec));
+        size_t o_nrec = o_dpos + al(secondary ? (size_t)band * ka.rec_per_sample * sizeof(V3) : 0);
+        size_t o_offs = o_nrec + al((size_t)band * sizeof(int)), o_paths = o_offs + al((size_t)band * sizeof(unsigned long long));
+        size_t o_verts = o_paths + al((size_t)band * sizeof(int)), o_tot = o_verts + al((size_t)band * ka.rec_per_sample * sizeof(int));
+        size_t o_scan = o_tot + 256, scratch_bytes = o_scan + al(scan_bytes);
+        RB_CUDA_OK(cudaMallocAsync((void**)&scratch, scratch_bytes, stream));
+        temps.push_back(scratch);
+        ka.records = (VertexRec*)(scratch + o_rec);
+        ka.dpos = secondary ? (V3*)(scratch + o_dpos) : nullptr;
+        ka.nrec = (int*)(scratch + o_nrec);
+        ka.offs = (unsigned long long*)(scratch + o_offs);
+        ka.path_list = (int*)(scratch + o_paths);
+        ka.vert_list = (int*)(scratch + o_verts);
+        ka.totals = (unsigned long long*)(scratch + o_tot);
+        int grid_t = pick_grid((const void*)k_bwd_trace, scene->device, nullptr), grid_s = pick_grid((const void*)k_bwd_secondary, scene->device, nullptr);
+        int grid_w = pick_grid((const void*)k_bwd_sweep, scene->device, nullptr);
+        for (long long i0 = 0; i0 < total_samples; i0 += band) {
+            ka.band_i0 = i0;
+            ka.band_n = (int)std::min<long long>(band, total_samples - i0);
+            cudaEvent_t e4[4];
+            for (int i = 0; i < 4; i++) {
+                RB_CUDA_OK(cudaEventCreate(&e4[i]));
+                band_events.push_back(e4[i]);
+            }
+            RB_CUDA_OK(cudaEventRecord(e4[0], stream));
+            k_bwd_trace<<<grid_t, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+            RB_CUDA_OK(cudaEventRecord(e4[1], stream));
+            cub::TransformInputIterator<unsigned long long, CountOp, const int*> counts(ka.nrec, CountOp());
+            cub::DeviceScan::ExclusiveSum(scratch + o_scan, scan_bytes, counts, ka.offs, ka.band_n, stream);
+            k_bwd_compact<<<std::min((ka.band_n + 255) / 256, 148 * 8), 256, 0, stream>>>(ka);
+            if (secondary) k_bwd_secondary<<<grid_s, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+            RB_CUDA_OK(cudaEventRecord(e4[2], stream));
+            k_bwd_sweep<<<grid_w, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+            RB_CUDA_OK(cudaEventRecord(e4[3], stream));
+            launches += secondary ? 6 : 5; // (the scan is two kernels)
+        }
         RB_CUDA_OK(cudaEventRecord(ev[2], stream));
         if (scene->dev.use_primary_edge && scene->dev.num_edges > 0 && scene->dev.prim_edge_cdf != nullptr) {
             int grid_e = pick_grid((const void*)k_primary_edge, scene->device, nullptr);
@@ -426,6 +530,14 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         scene->last_stage_ms[i] = 0.f;
         if (err == cudaSuccess) cudaEventElapsedTime(&scene->last_stage_ms[i], ev[i], ev[i + 1]);
     }
+    for (int i = 0; i < 3; i++) scene->last_bwd_ms[i] = 0.f;
+    if (err == cudaSuccess)
+        for (size_t b = 0; b + 3 < band_events.size(); b += 4)
+            for (int i = 0; i < 3; i++) {
+                float t = 0.f;
+                cudaEventElapsedTime(&t, band_events[b + i], band_events[b + i + 1]);
+                scene->last_bwd_ms[i] += t;
+            }
     scene->last_path_vertices = host_stats[0];
     scene->last_primary_hits = host_stats[1];
     cleanup();

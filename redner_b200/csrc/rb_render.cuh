@@ -9,6 +9,15 @@
 #include "rb_path.cuh"
 #include "rb_secondary.cuh"
 
+#define RB_MAX_SWEEP_DEPTH 64 // emulator-only bound of the fused composition
+// Phase barrier: the warps of a block enter each stage of a sample together, so one instruction-cache miss serves the
+// whole block (measured 2.1x - 7.4x on the backward pass, DESIGN.md "instruction supply").  Every call site is reached
+// by all threads of the block: the kernels iterate block-uniformly and pass an `act` flag instead of branching around.
+#if defined(RB_CPU_EMU) || defined(RB_NO_LOCKSTEP)
+#define RB_PHASE_SYNC()
+#else
+#define RB_PHASE_SYNC() __syncthreads()
+#endif
 struct KernelArgs {
     RenderParams rp;
     int lanes_per_pixel; // L
@@ -17,8 +26,17 @@ struct KernelArgs {
     const float* d_image;
     float* screen_grad;
     DevDScene ds;
-    VertexRec* records; // [threads][max_bounces + 2]
-    int rec_per_thread;
+    // ---- backward band state (rb_kernels.cu): the adjoint pass walks the image in bands of `band_n` pixel samples
+    long long band_i0;           // first dense sample index (owned pixel index * spp + s) of the band
+    int band_n;                  // samples in the band
+    int rec_per_sample;          // max_bounces + 1 records per sample
+    VertexRec* records;          // [band_n][rec_per_sample]
+    V3* dpos;                    // [band_n][rec_per_sample] boundary terms (null without secondary edge sampling)
+    int* nrec;                   // [band_n] vertices with an estimate, -1: primary ray missed
+    unsigned long long* offs;    // [band_n] exclusive scan of (hit << 32 | nrec)
+    int* path_list;              // compacted samples that hit something
+    int* vert_list;              // compacted (sample * rec_per_sample + depth)
+    unsigned long long* totals;  // [1] (paths << 32 | vertices) of the band
 };
 
 RB_HD unsigned long long main_draws_per_sample(const RenderParams& rp) {
@@ -40,9 +58,8 @@ RB_HD unsigned long long edge_draws_per_sample(const DevScene& sc, const RenderP
     return (unsigned long long)(primary_edge_dim_base(sc, rp) + 2 + 7 * rp.max_bounces);
 }
 
-// Camera sample -> primary ray (px, py are viewport-relative pixel coordinates), src/camera.cpp:8-43.
-RB_D void primary_ray_for(const DevScene& sc, const RenderParams& rp, int px, int py, Sampler& smp, double& sx, double& sy, Ray& ray, RayDiff& rd,
-                          D3* org_d = nullptr, D3* dir_d = nullptr) {
+// Screen position of a pixel sample: consumes the first two sampler dimensions unless sample_pixel_center.
+RB_D void primary_sample_pos(const DevScene& sc, const RenderParams& rp, int px, int py, Sampler& smp, double& sx, double& sy) {
     double jx = 0.5, jy = 0.5;
     if (!rp.sample_pixel_center) {
         jx = smp.next();
@@ -50,6 +67,11 @@ RB_D void primary_ray_for(const DevScene& sc, const RenderParams& rp, int px, in
     }
     sx = (double(px + sc.cam.vp_beg[0]) + jx) / double(sc.cam.width);
     sy = (double(py + sc.cam.vp_beg[1]) + jy) / double(sc.cam.height);
+}
+// Camera sample -> primary ray (px, py are viewport-relative pixel coordinates), src/camera.cpp:8-43.
+RB_D void primary_ray_for(const DevScene& sc, const RenderParams& rp, int px, int py, Sampler& smp, double& sx, double& sy, Ray& ray, RayDiff& rd,
+                          D3* org_d = nullptr, D3* dir_d = nullptr) {
+    primary_sample_pos(sc, rp, px, py, smp, sx, sy);
     cam_primary_ray(sc.cam, sx, sy, ray, rd);
     if (org_d) cam_sample_primary(sc.cam, sx, sy, *org_d, *dir_d);
 }
@@ -150,19 +172,18 @@ RB_D bool forward_sample_channels(const DevScene& sc, const RenderParams& rp, in
     return true;
 }
 
-// Adjoint of one pixel sample.  `recs` is this thread's private record array (max_bounces + 2 entries).
-// Returns the number of path vertices at which a radiance estimate was formed (-1 if the primary ray missed).
-#ifdef RB_LOCKSTEP // experiment: block-wide phase barriers so that the warps of a block walk the code together
-#define RB_PHASE_SYNC() __syncthreads()
-#else
-#define RB_PHASE_SYNC()
-#endif
-RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, int px, int py, int s, VertexRec* recs, CamAcc& cam_acc, bool act = true) {
-    const RenderParams& rp = ka.rp;
-    const DevDScene& ds = ka.ds;
-    const Real weight = Real(1) / Real(rp.spp);
+// ---- adjoint of one pixel sample, in three stages (src/pathtracer.cpp:392-762) ----
+// The stages run as three kernels over compacted work lists (rb_kernels.cu); records travel through HBM:
+//   bwd_trace      replays the primal path and writes one VertexRec per vertex             (k_bwd_trace)
+//   bwd_secondary  boundary term of one path vertex -> d(position) of that vertex          (k_bwd_secondary)
+//   bwd_sweep      reverse sweep over the vertices, first-hit and camera adjoints          (k_bwd_sweep)
+// A fused megakernel of the three measured instruction-fetch bound (profiles/r01_*): 0.6 - 1.6 MB of SASS walked once
+// per sample by 16 warps per SM.
+// Returns the number of vertices at which a radiance estimate was formed (-1: the primary ray missed).  Writes
+// recs[0 .. nrec] (the last one is the terminal vertex), `stride` records apart.
+RB_D int bwd_trace(const DevScene& sc, const RenderParams& rp, int pixel, int px, int py, int s, VertexRec* recs, int stride, bool act = true) {
     Sampler smp;
-    double sx = 0, sy = 0;
+    double sx, sy;
     Ray ray;
     RayDiff rd;
     D3 od, dd;
@@ -173,50 +194,48 @@ RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, in
         primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
         act = closest_hit(sc, ray, is);
     }
-#ifndef RB_LOCKSTEP
+    RB_PHASE_SYNC();
     if (!act) return -1;
-#endif
+    int nrec = 0;
+    trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, recs, stride, &nrec, &od, &dd);
+    return nrec;
+}
+// Boundary (visibility) term at vertex `depth` of the path of (pixel, s), src/pathtracer.cpp:500-707.  `coin` picks
+// the edge-sampling strategy and must be uniform over the calling warp.  Returns d(position of the vertex).
+RB_D V3 bwd_secondary(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur, int coin) {
+    const RenderParams& rp = ka.rp;
+    V3 d_position = zero3();
+    Sampler es;
+    es.init(rp.sampler_type, rp.seed + 131071ULL, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * edge_draws_per_sample(sc, rp));
+    es.skip(secondary_edge_dim_base(rp, depth));
+    const float* dpx = ka.d_image + (size_t)rp.nd * pixel + rp.rad_dim;
+    secondary_edge_sample(sc, ka.ds, rp, cur, depth, es, mk3(dpx[0], dpx[1], dpx[2]), coin, d_position);
+    return d_position;
+}
+// Reverse sweep (src/pathtracer.cpp:431-714) + first-hit and camera adjoints.  `dpos` (may be null) holds the
+// boundary terms of the vertices, laid out like `recs`.
+RB_D void bwd_sweep(const DevScene& sc, const KernelArgs& ka, int pixel, int px, int py, int s, const VertexRec* recs, int stride, int nrec,
+                    const V3* dpos, CamAcc& cam_acc, bool act = true) {
+    const RenderParams& rp = ka.rp;
+    const DevDScene& ds = ka.ds;
+    const Real weight = Real(1) / Real(rp.spp);
     const float* dpx = ka.d_image + (size_t)rp.nd * pixel + rp.rad_dim;
     V3 d_contrib = act ? weight * mk3(dpx[0], dpx[1], dpx[2]) : zero3();
-    int nrec = 0;
-    RB_PHASE_SYNC();
-    if (act) trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, recs, 1, &nrec, &od, &dd);
-    // reverse sweep over the interior vertices (src/pathtracer.cpp:431-714)
     VertexAdjoint adj = zero_vertex_adjoint();
-#ifdef RB_LOCKSTEP
-    for (int d = rp.max_bounces - 1; d >= 0; d--) {
-        bool on = act && d < nrec;
-#else
-    for (int d = nrec - 1; d >= 0; d--) {
-        const bool on = true;
-#endif
-        VertexRec cur, nxt;
+    for (int d = rp.max_bounces - 1; d >= 0; d--) { // block-uniform trip count (phase barrier inside)
         RB_PHASE_SYNC();
-        if (on) {
-            cur = recs[d];
-            nxt = recs[d + 1];
+        if (act && d < nrec) {
+            VertexRec cur = recs[(size_t)d * stride];
+            VertexRec nxt = recs[(size_t)(d + 1) * stride];
             adj = d_vertex(sc, ds, cur, &nxt, d_contrib, adj);
-        }
-        RB_PHASE_SYNC();
-        if (on && sc.use_secondary_edge && sc.num_edges > 0) {
-            // boundary term of the visibility at this vertex (src/pathtracer.cpp:500-707)
-            Sampler es;
-            es.init(rp.sampler_type, rp.seed + 131071ULL, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS,
-                    (unsigned long long)s * edge_draws_per_sample(sc, rp));
-            es.skip(secondary_edge_dim_base(rp, d));
-            // warp-uniform fair coin: all 32 lanes of a warp share (pixel group, sample batch); consecutive batches of a
-            // pixel alternate, so a pixel with >= 64 spp uses both strategies equally often
-            int Lp = ka.lanes_per_pixel > 0 ? ka.lanes_per_pixel : 1;
-            unsigned long long h = rb_hash64shift(((unsigned long long)(unsigned)((long long)pixel * Lp / 32) << 24) ^ ((unsigned long long)d << 16) ^
-                                                  (rp.seed << 44));
-            int coin = (int)(((h >> 17) + (unsigned long long)(s / Lp)) & 1ULL);
-            secondary_edge_sample(sc, ds, rp, cur, d, es, mk3(dpx[0], dpx[1], dpx[2]), coin, adj.d_point.position);
+            if (dpos) adj.d_point.position += dpos[(size_t)d * stride];
         }
     }
     RB_PHASE_SYNC();
-#ifdef RB_LOCKSTEP
-    if (!act) return -1;
-#endif
+    if (!act) return;
+    const Ray ray = recs[0].ray;
+    const RayDiff rd = recs[0].rd_in;
+    const Isect is = recs[0].isect;
     // first vertex: emission adjoint (src/primary_contribution.cpp:449-466) ...
     RayDiff rd_after;
     SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
@@ -244,6 +263,10 @@ RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, in
     d_ray_dy.dir = d_prd.dir_dy * (psy / delta);
     d_ray.org += (d_prd.org_dx * (-psx) + d_prd.org_dy * (-psy)) / delta;
     d_ray.dir += (d_prd.dir_dx * (-psx) + d_prd.dir_dy * (-psy)) / delta;
+    Sampler smp;
+    smp.init(rp.sampler_type, rp.seed, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
+    double sx, sy;
+    primary_sample_pos(sc, rp, px, py, smp, sx, sy);
     V2 d_screen = zero2();
     V2* d_screen_ptr = ka.screen_grad ? &d_screen : nullptr;
 #pragma unroll 1
@@ -255,6 +278,21 @@ RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, in
         rb_red_add(&ka.screen_grad[2 * (size_t)pixel + 0], (float)d_screen.x);
         rb_red_add(&ka.screen_grad[2 * (size_t)pixel + 1], (float)d_screen.y);
     }
+}
+// The three stages back to back for ONE sample: used by the host-compiled debug emulator (tools/cpu_emu) only.
+RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, int px, int py, int s, VertexRec* recs, CamAcc& cam_acc) {
+    const RenderParams& rp = ka.rp;
+    int nrec = bwd_trace(sc, rp, pixel, px, py, s, recs, 1);
+    if (nrec < 0) return -1;
+    V3 dpos[RB_MAX_SWEEP_DEPTH];
+    bool sec = sc.use_secondary_edge && sc.num_edges > 0;
+    for (int d = 0; d < nrec && d < RB_MAX_SWEEP_DEPTH; d++) {
+        int Lp = ka.lanes_per_pixel > 0 ? ka.lanes_per_pixel : 1;
+        unsigned long long h = rb_hash64shift(((unsigned long long)(unsigned)((long long)pixel * Lp / 32) << 24) ^ ((unsigned long long)d << 16) ^ (rp.seed << 44));
+        int coin = (int)(((h >> 17) + (unsigned long long)(s / Lp)) & 1ULL);
+        dpos[d] = sec ? bwd_secondary(sc, ka, pixel, s, d, recs[d], coin) : zero3();
+    }
+    bwd_sweep(sc, ka, pixel, px, py, s, recs, 1, nrec, sec ? dpos : nullptr, cam_acc);
     return nrec;
 }
 

@@ -523,6 +523,11 @@ extern "C" int rb_scene_last_stage_stats(const rb_scene* sc, float* stage_ms4, d
     if (primary_hits) *primary_hits = sc->last_primary_hits;
     return 0;
 }
+extern "C" int rb_scene_last_backward_stats(const rb_scene* sc, float* bwd_ms3) {
+    if (!sc || !bwd_ms3) return 1;
+    for (int i = 0; i < 3; i++) bwd_ms3[i] = sc->last_bwd_ms[i];
+    return 0;
+}
 extern "C" int rb_scene_build_ms(const rb_scene* sc, float* bvh_lights_edges3) {
     if (!sc || !bvh_lights_edges3) return 1;
     bvh_lights_edges3[0] = sc->build_ms_bvh;

@@ -24,7 +24,8 @@ struct rb_scene {
     // stats of the last render
     int last_launches = 0;
     float last_kernel_ms = 0.f;
-    float last_stage_ms[4] = {0.f, 0.f, 0.f, 0.f}; // k_forward, k_backward, k_primary_edge, k_finish_camera
+    float last_stage_ms[4] = {0.f, 0.f, 0.f, 0.f}; // k_forward, backward bands, k_primary_edge, k_finish_camera
+    float last_bwd_ms[3] = {0.f, 0.f, 0.f};        // inside the bands: k_bwd_trace, scan + compaction + k_bwd_secondary, k_bwd_sweep
     double last_path_vertices = 0, last_primary_hits = 0;
     // scene-build timings (ms, host clock) for reporting
     float build_ms_bvh = 0.f, build_ms_lights = 0.f, build_ms_edges = 0.f;

@@ -347,7 +347,13 @@ class Scene:  # src/redner.cpp:62-73, src/scene.cpp:63-307
         ms = (C.c_float * 4)()
         v, h = C.c_double(0), C.c_double(0)
         self._lib.rb_scene_last_stage_stats(self._handle, ms, C.byref(v), C.byref(h))
-        return dict(zip(("k_forward", "k_backward", "k_primary_edge", "k_finish_camera"), list(ms))), v.value, h.value
+        out = dict(zip(("k_forward", "k_backward", "k_primary_edge", "k_finish_camera"), list(ms)))
+        if hasattr(self._lib, "rb_scene_last_backward_stats"):
+            # "k_backward" is the sum over the backward bands; its three stages follow
+            b = (C.c_float * 3)()
+            self._lib.rb_scene_last_backward_stats(self._handle, b)
+            out.update(dict(zip(("k_bwd_trace", "k_bwd_secondary", "k_bwd_sweep"), list(b))))
+        return out, v.value, h.value
 
     def build_ms(self):
         ms = (C.c_float * 3)()

@@ -33,5 +33,6 @@ for edges in [int(e) for e in os.environ.get("RB_EDGES", "0,1,2,3").split(",")]:
         ctx.c, ctx.args = c, args
         api.RenderFunction.backward(ctx, (2 * img).contiguous())
         st, v, h = c.scene.last_stage_stats()
-    print("%s %dx%dx%d mb=%d edges=%d: k_forward %.2f ms | k_backward %.2f | k_primary_edge %.2f | vertices/sample %.3f hits/sample %.3f | build %s" %
-          (scene, res, res, spp, mb, edges, f, st["k_backward"], st["k_primary_edge"], v / (res * res * spp), h / (res * res * spp), c.scene.build_ms()))
+    sub = " (trace %.2f sec %.2f sweep %.2f)" % (st["k_bwd_trace"], st["k_bwd_secondary"], st["k_bwd_sweep"]) if "k_bwd_trace" in st else ""
+    print("%s %dx%dx%d mb=%d edges=%d: fwd %.2f ms | bwd %.2f%s | prim %.2f | vert/sample %.3f hits/sample %.3f" %
+          (scene, res, res, spp, mb, edges, f, st["k_backward"], sub, st["k_primary_edge"], v / (res * res * spp), h / (res * res * spp)))
