@@ -197,6 +197,9 @@ int rb_scene_last_stage_stats(const rb_scene* scene, float* stage_ms4, double* p
 /* Split of the backward bands of the last rb_render, summed over the bands:
  * { k_bwd_trace, scan + compaction + k_bwd_secondary, k_bwd_sweep } in milliseconds. */
 int rb_scene_last_backward_stats(const rb_scene* scene, float* bwd_ms3);
+/* rb_render keeps one grow-only scratch allocation per device for the backward pass (gradient descriptors, path
+ * records, work lists; at most ~1 GiB + small).  This frees them all; the next backward pass allocates again. */
+void rb_release_scratch(void);
 /* Host wall-clock milliseconds rb_scene_create spent in { BVH build, light tables, edge list + edge tree }. */
 int rb_scene_build_ms(const rb_scene* scene, float* bvh_lights_edges3);
 

@@ -105,7 +105,7 @@ class rb_dscene_desc(C.Structure):
 
 EXPORTS = [
     "rb_scene_create", "rb_scene_destroy", "rb_scene_max_generic_texture_dimension", "rb_compute_num_channels", "rb_render",
-    "rb_scene_set_partition", "rb_scene_last_stats", "rb_scene_last_stage_stats", "rb_scene_last_backward_stats", "rb_scene_build_ms", "rb_last_error", "rb_version",
+    "rb_scene_set_partition", "rb_scene_last_stats", "rb_scene_last_stage_stats", "rb_scene_last_backward_stats", "rb_release_scratch", "rb_scene_build_ms", "rb_last_error", "rb_version",
 ]
 
 
@@ -132,6 +132,9 @@ def _bind(lib):
     if hasattr(lib, "rb_scene_last_backward_stats"):
         lib.rb_scene_last_backward_stats.argtypes = [C.c_void_p, c_float_p]
         lib.rb_scene_last_backward_stats.restype = C.c_int
+    if hasattr(lib, "rb_release_scratch"):
+        lib.rb_release_scratch.argtypes = []
+        lib.rb_release_scratch.restype = None
     lib.rb_last_error.argtypes = []
     lib.rb_last_error.restype = C.c_char_p
     lib.rb_version.argtypes = []

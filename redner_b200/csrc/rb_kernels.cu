@@ -80,11 +80,7 @@ RB_D WorkItem warp_work(const RenderParams& rp, int L, int owned_rows, long long
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-#ifdef RB_LOCKSTEP_FWD
-#define RB_FWD_SYNC() __syncthreads()
-#else
-#define RB_FWD_SYNC()
-#endif
+#define RB_FWD_SYNC() RB_PHASE_SYNC() // measured: k_forward 5.2 -> 3.7 ms on C2 (one I-cache miss serves the block)
 __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_FWD) k_forward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     const RenderParams& rp = ka.rp;
     const int L = ka.lanes_per_pixel;
@@ -275,11 +271,7 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SWEEP) k_bwd_sweep(con
 
 // ------------------------------------------------------------------------------------------------ primary edges
 // One thread per (edge sample i, spp sample s).
-#ifdef RB_LOCKSTEP_PRIM
-#define RB_PRIM_SYNC() __syncthreads()
-#else
-#define RB_PRIM_SYNC()
-#endif
+#define RB_PRIM_SYNC() RB_PHASE_SYNC() // measured: k_primary_edge 19.2 -> 14.3 ms on C2
 __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_BWD) k_primary_edge(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka, int dim_base) {
     __shared__ float cam_smem[RB_CAM_ACC * RB_BLOCK];
     for (int k = 0; k < RB_CAM_ACC; k++) cam_smem[k * RB_BLOCK + threadIdx.x] = 0.f;
@@ -309,6 +301,46 @@ __global__ void k_finish_camera(DevCamera cam, const double* acc, rb_dcamera out
 }
 
 // ------------------------------------------------------------------------------------------------ driver
+// Backward scratch (gradient descriptors, band records and work lists): ONE grow-only allocation per device, kept for
+// the life of the process so that a training loop pays no cudaMalloc / pool growth per step (measured: ~20 ms per step
+// with per-call cudaMallocAsync of the 1 GiB band).  rb_render holds the lock for the whole backward pass, which also
+// serialises concurrent backward passes on one device; rb_release_scratch() frees everything.
+#include <mutex>
+struct DeviceScratch {
+    char* ptr = nullptr;
+    size_t bytes = 0;
+};
+static std::mutex g_scratch_mutex;
+static DeviceScratch g_scratch[64];
+static char* scratch_ensure(int device, size_t bytes) {
+    DeviceScratch& sc = g_scratch[device & 63];
+    if (sc.bytes >= bytes) return sc.ptr;
+    if (sc.ptr) {
+        cudaDeviceSynchronize();
+        cudaFree(sc.ptr);
+        sc.ptr = nullptr;
+        sc.bytes = 0;
+    }
+    if (cudaMalloc((void**)&sc.ptr, bytes) != cudaSuccess) {
+        sc.ptr = nullptr;
+        return nullptr;
+    }
+    sc.bytes = bytes;
+    return sc.ptr;
+}
+extern "C" void rb_release_scratch(void) {
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int d = 0; d < 64; d++)
+        if (g_scratch[d].ptr) {
+            cudaSetDevice(d);
+            cudaDeviceSynchronize();
+            cudaFree(g_scratch[d].ptr);
+            g_scratch[d] = DeviceScratch();
+        }
+    cudaSetDevice(prev);
+}
 static int pick_grid(const void* kernel, int device, int* blocks_per_sm_out) {
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -402,11 +434,10 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
     for (int i = 0; i < 5; i++) RB_CUDA_OK(cudaEventCreate(&ev[i]));
     int launches = 0;
     double host_stats[2] = {0, 0};
-    std::vector<void*> temps;
+    std::unique_lock<std::mutex> scratch_lock(g_scratch_mutex, std::defer_lock);
     std::vector<cudaEvent_t> band_events; // 4 per backward band: start, after trace, after compaction+secondary, after sweep
     auto cleanup = [&]() {
         for (cudaEvent_t e : band_events) cudaEventDestroy(e);
-        for (void* p : temps) cudaFreeAsync(p, stream);
         for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
         cudaSetDevice(prev);
     };
@@ -433,20 +464,37 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             cleanup();
             return 1;
         }
-        rb_dshape* d_shapes = nullptr;
-        rb_material* d_mats = nullptr;
-        float** d_lights = nullptr;
-        double* cam_accum = nullptr;
+        // ---- scratch layout: gradient descriptors | camera accumulators | band (records, boundary terms, lists, scan)
+        const bool secondary = scene->dev.use_secondary_edge && scene->dev.num_edges > 0 && scene->dev.num_lights > 0;
+        const long long total_samples = (long long)ka.owned_rows * rp.vp_w * rp.spp;
+        ka.rec_per_sample = rp.max_bounces + 1;
+        const size_t per_sample = (size_t)ka.rec_per_sample * (sizeof(VertexRec) + (secondary ? sizeof(V3) : 0) + sizeof(int)) + 2 * sizeof(int) + sizeof(unsigned long long);
+        long long band = (long long)std::max<size_t>(RB_BAND_BYTES / per_sample, 32768);
+        band = std::min<long long>(band, (1LL << 30) / ka.rec_per_sample);
+        band = std::min<long long>(band, std::max<long long>(total_samples, 1));
+        size_t scan_bytes = 0;
+        cub::TransformInputIterator<unsigned long long, CountOp, const int*> probe((const int*)nullptr, CountOp());
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, probe, (unsigned long long*)nullptr, (int)band, stream);
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
         size_t nb_shapes = std::max(1, d_scene->num_shapes) * sizeof(rb_dshape), nb_mats = std::max(1, d_scene->num_materials) * sizeof(rb_material),
                nb_lights = std::max(1, d_scene->num_lights) * sizeof(float*);
-        RB_CUDA_OK(cudaMallocAsync((void**)&d_shapes, nb_shapes, stream));
-        temps.push_back(d_shapes);
-        RB_CUDA_OK(cudaMallocAsync((void**)&d_mats, nb_mats, stream));
-        temps.push_back(d_mats);
-        RB_CUDA_OK(cudaMallocAsync((void**)&d_lights, nb_lights, stream));
-        temps.push_back(d_lights);
-        RB_CUDA_OK(cudaMallocAsync((void**)&cam_accum, (RB_CAM_ACC + 2) * sizeof(double), stream));
-        temps.push_back(cam_accum);
+        size_t o_shapes = 0, o_mats = o_shapes + al(nb_shapes), o_lights = o_mats + al(nb_mats), o_cam = o_lights + al(nb_lights);
+        size_t o_rec = o_cam + al((RB_CAM_ACC + 2) * sizeof(double)), o_dpos = o_rec + al((size_t)band * ka.rec_per_sample * sizeof(VertexRec));
+        size_t o_nrec = o_dpos + al(secondary ? (size_t)band * ka.rec_per_sample * sizeof(V3) : 0);
+        size_t o_offs = o_nrec + al((size_t)band * sizeof(int)), o_paths = o_offs + al((size_t)band * sizeof(unsigned long long));
+        size_t o_verts = o_paths + al((size_t)band * sizeof(int)), o_tot = o_verts + al((size_t)band * ka.rec_per_sample * sizeof(int));
+        size_t o_scan = o_tot + 256, scratch_bytes = o_scan + al(scan_bytes);
+        scratch_lock.lock();
+        char* scratch = scratch_ensure(scene->device, scratch_bytes);
+        if (!scratch) {
+            rb_set_error("rb_render: out of device memory for the backward scratch");
+            cleanup();
+            return 1;
+        }
+        rb_dshape* d_shapes = (rb_dshape*)(scratch + o_shapes);
+        rb_material* d_mats = (rb_material*)(scratch + o_mats);
+        float** d_lights = (float**)(scratch + o_lights);
+        double* cam_accum = (double*)(scratch + o_cam);
         if (d_scene->num_shapes) RB_CUDA_OK(cudaMemcpyAsync(d_shapes, d_scene->shapes, d_scene->num_shapes * sizeof(rb_dshape), cudaMemcpyHostToDevice, stream));
         if (d_scene->num_materials)
             RB_CUDA_OK(cudaMemcpyAsync(d_mats, d_scene->materials, d_scene->num_materials * sizeof(rb_material), cudaMemcpyHostToDevice, stream));
@@ -459,25 +507,6 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         ka.ds.cam_accum = cam_accum;
 
         // ---- interior + first-hit adjoints, band by band: trace -> scan/compact -> boundary terms -> sweep
-        const bool secondary = scene->dev.use_secondary_edge && scene->dev.num_edges > 0 && scene->dev.num_lights > 0;
-        const long long total_samples = (long long)ka.owned_rows * rp.vp_w * rp.spp;
-        ka.rec_per_sample = rp.max_bounces + 1;
-        const size_t per_sample = (size_t)ka.rec_per_sample * (sizeof(VertexRec) + (secondary ? sizeof(V3) : 0) + sizeof(int)) + 2 * sizeof(int) + sizeof(unsigned long long);
-        long long band = (long long)std::max<size_t>(RB_BAND_BYTES / per_sample, 32768);
-        band = std::min<long long>(band, (1LL << 30) / ka.rec_per_sample);
-        band = std::min<long long>(band, std::max<long long>(total_samples, 1));
-        char* scratch = nullptr;
-        size_t scan_bytes = 0;
-        cub::TransformInputIterator<unsigned long long, CountOp, const int*> probe((const int*)nullptr, CountOp());
-        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, probe, (unsigned long long*)nullptr, (int)band, stream);
-        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-        size_t o_rec = 0, o_dpos = o_rec + al((size_t)band * ka.rec_per_sample * sizeof(VertexRec));
-        size_t o_nrec = o_dpos + al(secondary ? (size_t)band * ka.rec_per_sample * sizeof(V3) : 0);
-        size_t o_offs = o_nrec + al((size_t)band * sizeof(int)), o_paths = o_offs + al((size_t)band * sizeof(unsigned long long));
-        size_t o_verts = o_paths + al((size_t)band * sizeof(int)), o_tot = o_verts + al((size_t)band * ka.rec_per_sample * sizeof(int));
-        size_t o_scan = o_tot + 256, scratch_bytes = o_scan + al(scan_bytes);
-        RB_CUDA_OK(cudaMallocAsync((void**)&scratch, scratch_bytes, stream));
-        temps.push_back(scratch);
         ka.records = (VertexRec*)(scratch + o_rec);
         ka.dpos = secondary ? (V3*)(scratch + o_dpos) : nullptr;
         ka.nrec = (int*)(scratch + o_nrec);

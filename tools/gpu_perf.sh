@@ -37,3 +37,4 @@ if [ "$KREGEX" != none ]; then
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 fi
 du -sh gpurun_out
+echo "=== e2e breakdown"; timeout 600 python tools/e2e_breakdown.py 2>&1 | tail -45
