@@ -343,26 +343,52 @@ RB_HD bool cam_project_d(const DevCamera& cam, D3 p0, D3 p1, D2& q0, D2& q1) {
 }
 
 // One primary-edge sample: edge sample index i (seeds the stream like a pixel index), spp sample s.
+// Edge and point on it chosen by primary-edge sample (i, s); false if the sample contributes nothing (edge behind the
+// camera, zero probability, point off screen).  `smp` is left positioned at the first light/bsdf dimension.
+struct PrimEdgePick {
+    int edge_id;
+    double pmf, e_t;
+    D2 q0, q1, ept;
+};
+RB_D bool primary_edge_pick(const DevScene& sc, const RenderParams& rp, long long i, int s, int dim_base, Sampler& smp, PrimEdgePick& pk) {
+    smp.init(rp.sampler_type, rp.seed + 131071ULL, (int)i, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS,
+             (unsigned long long)s * edge_draws_per_sample(sc, rp));
+    smp.skip(dim_base);
+    double e_sel = smp.next();
+    pk.e_t = smp.next();
+    pk.edge_id = cdf_pick(sc.prim_edge_cdf, sc.num_edges, e_sel);
+    pk.pmf = sc.prim_edge_pmf[pk.edge_id];
+    const Edge edge = sc.edges[pk.edge_id];
+    V3 v0 = edge_v0(sc.shapes, edge), v1 = edge_v1(sc.shapes, edge);
+    if (!cam_project_d(sc.cam, d3(v0.x, v0.y, v0.z), d3(v1.x, v1.y, v1.z), pk.q0, pk.q1)) return false;
+    if (pk.pmf <= 0) return false;
+    pk.ept.x = pk.q0.x + pk.e_t * (pk.q1.x - pk.q0.x);
+    pk.ept.y = pk.q0.y + pk.e_t * (pk.q1.y - pk.q0.y);
+    return cam_in_screen(sc.cam, mk2((Real)pk.ept.x, (Real)pk.ept.y));
+}
+// Sort key of a primary-edge sample: (edge, position along the edge).  Samples that are neighbours under this key
+// shoot nearly the same camera rays and scatter into the same two vertices; ~0u = contributes nothing.
+RB_D unsigned primary_edge_key(const DevScene& sc, const RenderParams& rp, long long i, int s, int dim_base) {
+    Sampler smp;
+    PrimEdgePick pk;
+    if (!primary_edge_pick(sc, rp, i, s, dim_base, smp, pk)) return 0xffffffffu;
+    int ebits = 1;
+    while ((1 << ebits) < sc.num_edges && ebits < 31) ebits++;
+    int tbits = 31 - ebits; // (the top bit stays clear so that no key equals ~0u)
+    unsigned tq = tbits > 0 ? (unsigned)rb_clampi((int)(pk.e_t * (double)(1u << tbits)), 0, (1 << tbits) - 1) : 0u;
+    return ((unsigned)pk.edge_id << tbits) | tq;
+}
 RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long long i, int s, int dim_base, CamAcc& cam_acc) {
     const RenderParams& rp = ka.rp;
     const DevDScene& ds = ka.ds;
     const Real weight = Real(1) / Real(rp.spp);
     Sampler smp;
-    smp.init(rp.sampler_type, rp.seed + 131071ULL, (int)i, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS,
-             (unsigned long long)s * edge_draws_per_sample(sc, rp));
-    smp.skip(dim_base);
-    double e_sel = smp.next(), e_t = smp.next();
-    int edge_id = cdf_pick(sc.prim_edge_cdf, sc.num_edges, e_sel);
-    double pmf = sc.prim_edge_pmf[edge_id];
-    const Edge edge = sc.edges[edge_id];
+    PrimEdgePick pk;
+    if (!primary_edge_pick(sc, rp, i, s, dim_base, smp, pk)) return;
+    const double pmf = pk.pmf;
+    const D2 q0 = pk.q0, q1 = pk.q1, ept = pk.ept;
+    const Edge edge = sc.edges[pk.edge_id];
     V3 v0 = edge_v0(sc.shapes, edge), v1 = edge_v1(sc.shapes, edge);
-    D2 q0, q1;
-    if (!cam_project_d(sc.cam, d3(v0.x, v0.y, v0.z), d3(v1.x, v1.y, v1.z), q0, q1)) return;
-    if (pmf <= 0) return;
-    D2 ept;
-    ept.x = q0.x + e_t * (q1.x - q0.x);
-    ept.y = q0.y + e_t * (q1.y - q0.y);
-    if (!cam_in_screen(sc.cam, mk2((Real)ept.x, (Real)ept.y))) return;
     // unit normal of the projected edge: get_normal(normalize(v0_ss - v1_ss)) = (d.y, -d.x)
     double ddx = q0.x - q1.x, ddy = q0.y - q1.y;
     double dl = sqrt(ddx * ddx + ddy * ddy);

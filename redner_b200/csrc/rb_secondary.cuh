@@ -18,6 +18,7 @@
 #define RB_EDGE_H_SAMPLES 16
 #define RB_EDGE_STACK_H 24
 #define RB_EDGE_STACK_L 64
+#define RB_GATHER_BATCH 8
 
 RB_HD M3 m3_rows(V3 a, V3 b, V3 c) {
     M3 r;
@@ -194,22 +195,19 @@ RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sampl
     split_samples(RB_EDGE_H_SAMPLES, prob_cs, u, n_cs, n_ncs);
     if (n_cs > 0) { stack[sp].node = sc.edge_root_cs; stack[sp].num = (short)n_cs; stack[sp].is6d = 0; stack[sp].pmf = prob_cs; sp++; }
     if (n_ncs > 0) { stack[sp].node = sc.edge_root_ncs; stack[sp].num = (short)n_ncs; stack[sp].is6d = 1; stack[sp].pmf = 1 - prob_cs; sp++; }
+    // Interior nodes first, leaves afterwards (in the order the descent reached them, so the reservoir below consumes
+    // `resample_u` exactly as a combined loop would): lanes of a warp would otherwise sit in the leaf branch (silhouette
+    // test + LTC line integral) and the interior branch (two box bounds) of the same loop at the same time.
+    StackH leaves[RB_EDGE_H_SAMPLES];
+    int nl = 0;
     while (sp > 0) {
         StackH it = stack[--sp];
         const EdgeNode& n = sc.edge_nodes[it.node];
         if (n.edge_id >= 0) {
-            Real w = it.num * leaf_importance_h(sc.edges[n.edge_id], c) / it.pmf;
-            if (w > 0) {
-                Real prev = wsum;
-                wsum += w;
-                Real nw = w / wsum;
-                if (resample_u <= nw || prev == 0) {
-                    selected = n.edge_id;
-                    edge_weight = w * it.pmf;
-                    resample_u /= nw;
-                } else {
-                    resample_u = (resample_u - nw) / (1 - nw);
-                }
+            if (nl < RB_EDGE_H_SAMPLES) {
+                leaves[nl] = it;
+                leaves[nl].node = n.edge_id;
+                nl++;
             }
         } else {
             Real i0, i1;
@@ -225,6 +223,22 @@ RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sampl
                 split_samples(it.num, p0, u, n0, n1);
                 if (n0 > 0 && sp < RB_EDGE_STACK_H) { stack[sp].node = n.left; stack[sp].num = (short)n0; stack[sp].is6d = it.is6d; stack[sp].pmf = it.pmf * p0; sp++; }
                 if (n1 > 0 && sp < RB_EDGE_STACK_H) { stack[sp].node = n.right; stack[sp].num = (short)n1; stack[sp].is6d = it.is6d; stack[sp].pmf = it.pmf * (1 - p0); sp++; }
+            }
+        }
+    }
+    for (int k = 0; k < nl; k++) {
+        const StackH it = leaves[k];
+        Real w = it.num * leaf_importance_h(sc.edges[it.node], c) / it.pmf;
+        if (w > 0) {
+            Real prev = wsum;
+            wsum += w;
+            Real nw = w / wsum;
+            if (resample_u <= nw || prev == 0) {
+                selected = it.node;
+                edge_weight = w * it.pmf;
+                resample_u /= nw;
+            } else {
+                resample_u = (resample_u - nw) / (1 - nw);
             }
         }
     }
@@ -246,33 +260,43 @@ RB_D int sample_edge_gather(const EdgeCtx& c, const Ray& nee, const Isect& lis, 
     // encode the tree kind in bit 30
     if (sc.edge_root_cs >= 0) stack[sp++] = sc.edge_root_cs;
     if (sc.edge_root_ncs >= 0) stack[sp++] = sc.edge_root_ncs | (1 << 30);
-    while (sp > 0) {
-        int item = stack[--sp];
-        bool is6d = (item & (1 << 30)) != 0;
-        const EdgeNode& n = sc.edge_nodes[item & ~(1 << 30)];
-        if (n.edge_id >= 0) {
-            Real w = leaf_importance_l(sc.edges[n.edge_id], c, nee, expand);
+    // Same two-phase structure as the hierarchical sampler: box tests run until RB_GATHER_BATCH leaves are pending (or the
+    // stack is empty), then the pending leaves are weighed in arrival order.
+    int pending[RB_GATHER_BATCH];
+    int np = 0;
+    while (sp > 0 || np > 0) {
+        while (sp > 0 && np < RB_GATHER_BATCH) {
+            int item = stack[--sp];
+            bool is6d = (item & (1 << 30)) != 0;
+            const EdgeNode& n = sc.edge_nodes[item & ~(1 << 30)];
+            if (n.edge_id >= 0) {
+                pending[np++] = n.edge_id;
+            } else {
+                for (int k = 0; k < 2; k++) {
+                    int ci = k == 0 ? n.left : n.right;
+                    const EdgeNode& ch = sc.edge_nodes[ci];
+                    bool ok = true;
+                    if (is6d) ok = hough_may_be_silhouette(ch, c.p.position, c.cam_org) && hough_may_be_silhouette(ch, lp.position, c.cam_org);
+                    if (ok && node_hit_by_ray(ch, nee, expand) && sp < RB_EDGE_STACK_L) stack[sp++] = ci | (is6d ? (1 << 30) : 0);
+                }
+            }
+        }
+        for (int k = 0; k < np; k++) {
+            Real w = leaf_importance_l(sc.edges[pending[k]], c, nee, expand);
             if (w > 0) {
                 Real prev = wsum;
                 wsum += w;
                 Real nw = w / wsum;
                 if (resample_u <= nw || prev == 0) {
-                    selected = n.edge_id;
+                    selected = pending[k];
                     edge_weight = w;
                     resample_u /= nw;
                 } else {
                     resample_u = (resample_u - nw) / (1 - nw);
                 }
             }
-        } else {
-            for (int k = 0; k < 2; k++) {
-                int ci = k == 0 ? n.left : n.right;
-                const EdgeNode& ch = sc.edge_nodes[ci];
-                bool ok = true;
-                if (is6d) ok = hough_may_be_silhouette(ch, c.p.position, c.cam_org) && hough_may_be_silhouette(ch, lp.position, c.cam_org);
-                if (ok && node_hit_by_ray(ch, nee, expand) && sp < RB_EDGE_STACK_L) stack[sp++] = ci | (is6d ? (1 << 30) : 0);
-            }
         }
+        np = 0;
     }
     if (selected == -1) return -1;
     Real pmf = edge_weight / wsum;

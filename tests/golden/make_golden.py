@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 import ref_loader  # noqa: E402
-from parity_utils import CASES, STAT_CASES, render_case  # noqa: E402
+from parity_utils import CASES, GBUFFER_CASES, STAT_CASES, render_case, render_gbuffer  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -41,6 +41,12 @@ def main():
             arrs["grad." + k] = v.numpy()
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
         print(name, "image mean %.6f" % img.mean().item(), {k: float(v.norm()) for k, v in grads.items()})
+    for name, cfg in GBUFFER_CASES.items():
+        if only and name not in only:
+            continue
+        img = render_gbuffer(ref, dev, cfg)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), image=img.numpy())
+        print(name, tuple(img.shape), "mean %.6f" % img.mean().item())
     for name, cfg in STAT_CASES.items():
         if only and name not in only:
             continue

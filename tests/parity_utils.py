@@ -23,6 +23,15 @@ CASES = {
     # normal-mapped ball with a mip-mapped specular texture and a differentiable uv_scale
     "nmap_room_sobol_mb2": dict(scene="nmap_room", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=11),
 }
+# forward-only G-buffer renders (src/channels.cpp, src/pathtracer.cpp:44-175); channel names of the `redner.channels` enum.
+# The second case puts radiance LAST to pin the reference's "channel index used as float offset" behaviour.
+GBUFFER_CASES = {
+    "gbuffer_glossy_room": dict(scene="glossy_room", res=40, spp=4, mb=1, sampler="sobol", seed=4,
+                                channels=["radiance", "alpha", "depth", "position", "geometry_normal", "shading_normal", "uv", "barycentric_coordinates",
+                                          "diffuse_reflectance", "specular_reflectance", "roughness", "shape_id", "triangle_id", "material_id"]),
+    "gbuffer_nmap_room_radiance_last": dict(scene="nmap_room", res=32, spp=4, mb=1, sampler="sobol", seed=6,
+                                            channels=["depth", "shading_normal", "radiance"]),
+}
 STAT_CASES = {
     # secondary-edge (shadow) gradient of the blocker: mean over seeds +- standard error
     "c2_shadow_blocker_secondary_stat": dict(scene="shadow_blocker", res=64, spp=64, mb=1, sampler="sobol", edges=3, seeds=list(range(1, 9)),
@@ -69,6 +78,14 @@ def render_case(backend, device, cfg, seed, backward=True):
         img.pow(2).sum().backward()
         grads = collect_grads(sc)
     return img.detach().cpu(), grads
+
+
+def render_gbuffer(backend, device, cfg):
+    sc = scenes.SCENES[cfg["scene"]](device, resolution=(cfg["res"], cfg["res"]), grad=False)
+    st = backend.SamplerType.sobol if cfg["sampler"] == "sobol" else backend.SamplerType.independent
+    chans = [getattr(backend.channels, c) for c in cfg["channels"]]
+    args = api.RenderFunction.serialize_scene(sc, cfg["spp"], cfg["mb"], channels=chans, sampler_type=st, device=device, backend=backend)
+    return api.RenderFunction.apply(cfg["seed"], *args).detach().cpu()
 
 
 def rel_l2(a, b):

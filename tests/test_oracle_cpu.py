@@ -36,6 +36,12 @@ def test_goldens_are_reference_outputs(reference_module, name):
         assert pu.rel_l2(v.numpy(), g["grad." + k]) < 1e-4, k
 
 
+@pytest.mark.parametrize("name", list(pu.GBUFFER_CASES))
+def test_gbuffer_goldens_are_reference_outputs(reference_module, name):
+    img = pu.render_gbuffer(reference_module, torch.device("cpu"), pu.GBUFFER_CASES[name])
+    assert np.array_equal(img.numpy(), pu.load_golden(name)["image"])
+
+
 def _scene_dict(sc):
     cam = sc.camera
     return dict(camera=dict(position=cam.position.detach().double().numpy(), look_at=cam.look_at.double().numpy(), up=cam.up.double().numpy(),
