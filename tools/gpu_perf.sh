@@ -16,19 +16,23 @@ done
 echo "=== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 echo "=== compare full size"; timeout 600 python tools/compare.py shadow_blocker --res 512 --spp 64 --edges 0 2>&1 | tail -5
 echo "=== bench ours"; timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_ours.json
-echo "=== instruction-supply metrics of every kernel of one step"
-timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,sm__icc_request_hit_rate.pct,gcc__average_cache_request_hit_rate.pct,gcc__xbar2gcc_sectors.sum.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active \
-    --clock-control none -k regex:^k_ -c 8 --csv --log-file gpurun_out/icache_metrics.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+echo "=== one profiled step: per-kernel time, DRAM bytes, instruction supply"
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,sm__icc_request_hit_rate.pct,gcc__average_cache_request_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active \
+    --clock-control none --csv --log-file gpurun_out/step_kernels.csv python tools/one_step.py > gpurun_out/one_step.log 2>&1
+python tools/summarize_step.py gpurun_out/step_kernels.csv gpurun_out/dram_traffic.json
 python - <<'PY'
 import csv, collections
-rows = list(csv.reader(open('gpurun_out/icache_metrics.csv')))
+rows = list(csv.reader(open('gpurun_out/step_kernels.csv')))
 hi = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 h = rows[hi]; kn, mn, mv, idc = h.index('Kernel Name'), h.index('Metric Name'), h.index('Metric Value'), h.index('ID')
+seen = set()
 d = collections.OrderedDict()
 for r in rows[hi + 1:]:
-    if len(r) > mv: d.setdefault((r[idc], r[kn].split('(')[0]), {})[r[mn]] = r[mv]
+    if len(r) > mv and r[kn].startswith('k_'): d.setdefault((r[idc], r[kn].split('(')[0]), {})[r[mn]] = r[mv]
 for (i, k), m in d.items():
-    print(k, ' '.join('%s=%s' % (a.split('.')[0].replace('smsp__', '').replace('sm__', ''), b) for a, b in m.items()))
+    if k in seen: continue
+    seen.add(k)
+    print(k, ' '.join('%s=%s' % (a.split('.')[0].replace('smsp__', '').replace('sm__', '').replace('gcc__average_cache_request_', 'gcc_'), b) for a, b in m.items() if 'dram' not in a and 'time' not in a))
 PY
 if [ "$KREGEX" != none ]; then
   echo "=== ncu full $KREGEX"
