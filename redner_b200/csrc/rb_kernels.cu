@@ -234,10 +234,11 @@ __global__ void k_bwd_compact(const __grid_constant__ KernelArgs ka) {
         }
     }
 }
-// Stage 3: boundary term of every path vertex (secondary edge sampling); full warps of vertices.
-__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SEC) k_bwd_secondary(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+// Stage 3a: edge pick of every path vertex (secondary edge sampling); full warps of vertices.  Key = picked edge
+// (num_edges = nothing picked), value = position in the vertex list.
+__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SEC) k_bwd_sec_pick(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     const RenderParams& rp = ka.rp;
-    const long long n = (long long)(*ka.totals & 0xffffffffULL);
+    const long long n = ka.n_verts;
     RB_BLOCK_LOOP(t, n) {
         RB_PHASE_SYNC();
         if (t < n) {
@@ -248,7 +249,29 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SEC) k_bwd_secondary(c
             // strategies are long and different, a block-wide choice keeps its warps in the same code and equally loaded
             unsigned long long h = rb_hash64shift(((unsigned long long)(ka.band_i0 / RB_BLOCK + t_base / RB_BLOCK) << 20) ^ (rp.seed << 44) ^ 0x9e3779b97f4a7c15ULL);
             VertexRec cur = ka.records[e];
-            ka.dpos[e] = bwd_secondary(sc, ka, id.pixel, id.s, d, cur, (int)((h >> 17) & 1ULL));
+            EdgePick pk;
+            bool ok = bwd_secondary_pick(sc, ka, id.pixel, id.s, d, cur, (int)((h >> 17) & 1ULL), pk);
+            if (ok) ka.picks[t] = pk;
+            ka.sec_keys[t] = ok ? (unsigned)pk.edge_id : (unsigned)sc.num_edges;
+            ka.sec_vals[t] = (unsigned)t;
+            ka.dpos[e] = zero3();
+        }
+    }
+}
+// Stage 3b: the two edge rays and their sub-paths, in edge order (neighbouring lanes aim at the same edge).
+__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SEC) k_bwd_sec_shade(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+    const RenderParams& rp = ka.rp;
+    const long long n = ka.n_verts;
+    RB_BLOCK_LOOP(j, n) {
+        RB_PHASE_SYNC();
+        if (j < n && ka.sec_keys_sorted[j] < (unsigned)sc.num_edges) {
+            unsigned t = ka.sec_vals_sorted[j];
+            int e = ka.vert_list[t];
+            int ts = e / ka.rec_per_sample, d = e - ts * ka.rec_per_sample;
+            SampleId id = band_sample(rp, ka.band_i0 + ts);
+            VertexRec cur = ka.records[e];
+            EdgePick pk = ka.picks[t];
+            ka.dpos[e] = bwd_secondary_shade(sc, ka, id.pixel, id.s, d, cur, pk);
         }
     }
 }
@@ -260,7 +283,7 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SWEEP) k_bwd_sweep(con
     cam_acc.base = cam_smem + threadIdx.x;
     cam_acc.stride = RB_BLOCK;
     const RenderParams& rp = ka.rp;
-    const long long n = (long long)(*ka.totals >> 32);
+    const long long n = ka.n_paths;
     RB_BLOCK_LOOP(t, n) {
         bool act = t < n;
         int ts = act ? ka.path_list[t] : 0;
@@ -485,7 +508,8 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         const bool secondary = scene->dev.use_secondary_edge && scene->dev.num_edges > 0 && scene->dev.num_lights > 0;
         const long long total_samples = (long long)ka.owned_rows * rp.vp_w * rp.spp;
         ka.rec_per_sample = rp.max_bounces + 1;
-        const size_t per_sample = (size_t)ka.rec_per_sample * (sizeof(VertexRec) + (secondary ? sizeof(V3) : 0) + sizeof(int)) + 2 * sizeof(int) + sizeof(unsigned long long);
+        const size_t per_sample = (size_t)ka.rec_per_sample * (sizeof(VertexRec) + (secondary ? sizeof(V3) + sizeof(EdgePick) + 16 + 8 : 0) + sizeof(int)) + 2 * sizeof(int) +
+                                  sizeof(unsigned long long);
         long long band = (long long)std::max<size_t>(RB_BAND_BYTES / per_sample, 32768);
         band = std::min<long long>(band, (1LL << 30) / ka.rec_per_sample);
         band = std::min<long long>(band, std::max<long long>(total_samples, 1));
@@ -501,7 +525,16 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         size_t o_offs = o_nrec + al((size_t)band * sizeof(int)), o_paths = o_offs + al((size_t)band * sizeof(unsigned long long));
         size_t o_verts = o_paths + al((size_t)band * sizeof(int)), o_tot = o_verts + al((size_t)band * ka.rec_per_sample * sizeof(int));
         size_t o_scan = o_tot + 256;
-        size_t scratch_bytes = o_scan + al(scan_bytes);
+        // boundary terms: edge picks, (edge, vertex) sort buffers, radix-sort temporaries
+        const size_t max_verts = (size_t)band * ka.rec_per_sample;
+        size_t sec_sort_bytes = 0;
+        if (secondary)
+            cub::DeviceRadixSort::SortPairs(nullptr, sec_sort_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const unsigned*)nullptr, (unsigned*)nullptr, (int)max_verts, 0, 32,
+                                            stream);
+        size_t o_picks = o_scan + al(scan_bytes), o_sk0 = o_picks + al(secondary ? max_verts * sizeof(EdgePick) : 0);
+        size_t o_sv0 = o_sk0 + al(secondary ? max_verts * 4 : 0), o_sk1 = o_sv0 + al(secondary ? max_verts * 4 : 0), o_sv1 = o_sk1 + al(secondary ? max_verts * 4 : 0);
+        size_t o_ssort = o_sv1 + al(secondary ? max_verts * 4 : 0);
+        size_t scratch_bytes = o_ssort + al(sec_sort_bytes);
         // primary-edge pass (reuses the band area): keys/values double buffers + radix-sort temporaries
         const bool primary = scene->dev.use_primary_edge && scene->dev.num_edges > 0 && scene->dev.prim_edge_cdf != nullptr;
         const long long n_px_all = (long long)rp.vp_w * rp.vp_h;
@@ -542,8 +575,15 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         ka.path_list = (int*)(scratch + o_paths);
         ka.vert_list = (int*)(scratch + o_verts);
         ka.totals = (unsigned long long*)(scratch + o_tot);
-        int grid_t = pick_grid((const void*)k_bwd_trace, scene->device, nullptr), grid_s = pick_grid((const void*)k_bwd_secondary, scene->device, nullptr);
-        int grid_w = pick_grid((const void*)k_bwd_sweep, scene->device, nullptr);
+        ka.picks = (EdgePick*)(scratch + o_picks);
+        ka.sec_keys = (unsigned*)(scratch + o_sk0);
+        ka.sec_vals = (unsigned*)(scratch + o_sv0);
+        ka.sec_keys_sorted = (unsigned*)(scratch + o_sk1);
+        ka.sec_vals_sorted = (unsigned*)(scratch + o_sv1);
+        int grid_t = pick_grid((const void*)k_bwd_trace, scene->device, nullptr), grid_p = pick_grid((const void*)k_bwd_sec_pick, scene->device, nullptr);
+        int grid_s = pick_grid((const void*)k_bwd_sec_shade, scene->device, nullptr), grid_w = pick_grid((const void*)k_bwd_sweep, scene->device, nullptr);
+        int edge_bits = 1; // key range of the boundary-term sort: [0, num_edges]
+        while ((1LL << edge_bits) <= (long long)scene->dev.num_edges && edge_bits < 32) edge_bits++;
         for (long long i0 = 0; i0 < total_samples; i0 += band) {
             ka.band_i0 = i0;
             ka.band_n = (int)std::min<long long>(band, total_samples - i0);
@@ -558,11 +598,26 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             cub::TransformInputIterator<unsigned long long, CountOp, const int*> counts(ka.nrec, CountOp());
             cub::DeviceScan::ExclusiveSum(scratch + o_scan, scan_bytes, counts, ka.offs, ka.band_n, stream);
             k_bwd_compact<<<std::min((ka.band_n + 255) / 256, 148 * 8), 256, 0, stream>>>(ka);
-            if (secondary) k_bwd_secondary<<<grid_s, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+            // the list sizes come back to the host once per band (the only sync inside the pass): exact grids and sort sizes
+            unsigned long long totals_h = 0;
+            RB_CUDA_OK(cudaMemcpyAsync(&totals_h, ka.totals, sizeof(totals_h), cudaMemcpyDeviceToHost, stream));
+            RB_CUDA_OK(cudaStreamSynchronize(stream));
+            ka.n_paths = (int)(totals_h >> 32);
+            ka.n_verts = (int)(totals_h & 0xffffffffULL);
+            launches += 4;
+            if (secondary && ka.n_verts > 0) {
+                k_bwd_sec_pick<<<grid_p, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+                cub::DeviceRadixSort::SortPairs(scratch + o_ssort, sec_sort_bytes, ka.sec_keys, ka.sec_keys_sorted, ka.sec_vals, ka.sec_vals_sorted, ka.n_verts, 0, edge_bits,
+                                                stream);
+                k_bwd_sec_shade<<<grid_s, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+                launches += 2 + 4;
+            }
             RB_CUDA_OK(cudaEventRecord(e4[2], stream));
-            k_bwd_sweep<<<grid_w, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+            if (ka.n_paths > 0) {
+                k_bwd_sweep<<<grid_w, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+                launches++;
+            }
             RB_CUDA_OK(cudaEventRecord(e4[3], stream));
-            launches += secondary ? 6 : 5; // (the scan is two kernels)
         }
         RB_CUDA_OK(cudaEventRecord(ev[2], stream));
         if (scene->dev.use_primary_edge && scene->dev.num_edges > 0 && scene->dev.prim_edge_cdf != nullptr) {

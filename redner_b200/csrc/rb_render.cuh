@@ -37,6 +37,10 @@ struct KernelArgs {
     int* path_list;              // compacted samples that hit something
     int* vert_list;              // compacted (sample * rec_per_sample + depth)
     unsigned long long* totals;  // [1] (paths << 32 | vertices) of the band
+    EdgePick* picks;             // [vertices] edge chosen for each entry of vert_list
+    unsigned *sec_keys, *sec_vals; // [vertices] (edge id | invalid, index into vert_list), before and after the sort
+    unsigned *sec_keys_sorted, *sec_vals_sorted;
+    int n_paths, n_verts;        // host copies of `totals` (read back once per band)
 };
 
 RB_HD unsigned long long main_draws_per_sample(const RenderParams& rp) {
@@ -200,17 +204,30 @@ RB_D int bwd_trace(const DevScene& sc, const RenderParams& rp, int pixel, int px
     trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, recs, stride, &nrec, &od, &dd);
     return nrec;
 }
-// Boundary (visibility) term at vertex `depth` of the path of (pixel, s), src/pathtracer.cpp:500-707.  `coin` picks
-// the edge-sampling strategy and must be uniform over the calling warp.  Returns d(position of the vertex).
-RB_D V3 bwd_secondary(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur, int coin) {
-    const RenderParams& rp = ka.rp;
-    V3 d_position = zero3();
+// Boundary (visibility) term at vertex `depth` of the path of (pixel, s), src/pathtracer.cpp:500-707, in two steps (see
+// rb_secondary.cuh).  `coin` picks the edge-sampling strategy and should be uniform over the calling block.
+RB_D Sampler bwd_edge_sampler(const DevScene& sc, const RenderParams& rp, int pixel, int s, int depth, int consumed) {
     Sampler es;
     es.init(rp.sampler_type, rp.seed + 131071ULL, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * edge_draws_per_sample(sc, rp));
-    es.skip(secondary_edge_dim_base(rp, depth));
+    es.skip(secondary_edge_dim_base(rp, depth) + consumed);
+    return es;
+}
+RB_D bool bwd_secondary_pick(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur, int coin, EdgePick& pk) {
+    Sampler es = bwd_edge_sampler(sc, ka.rp, pixel, s, depth, 0);
+    return secondary_edge_pick(sc, cur, es, coin, pk);
+}
+// Returns d(position of the vertex).
+RB_D V3 bwd_secondary_shade(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur, const EdgePick& pk) {
+    const RenderParams& rp = ka.rp;
+    V3 d_position = zero3();
     const float* dpx = ka.d_image + (size_t)rp.nd * pixel + rp.rad_dim;
-    secondary_edge_sample(sc, ka.ds, rp, cur, depth, es, mk3(dpx[0], dpx[1], dpx[2]), coin, d_position);
+    secondary_edge_shade(sc, ka.ds, rp, cur, depth, bwd_edge_sampler(sc, rp, pixel, s, depth, 4), mk3(dpx[0], dpx[1], dpx[2]), pk, d_position);
     return d_position;
+}
+RB_D V3 bwd_secondary(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur, int coin) {
+    EdgePick pk;
+    if (!bwd_secondary_pick(sc, ka, pixel, s, depth, cur, coin, pk)) return zero3();
+    return bwd_secondary_shade(sc, ka, pixel, s, depth, cur, pk);
 }
 // Reverse sweep (src/pathtracer.cpp:431-714) + first-hit and camera adjoints.  `dpos` (may be null) holds the
 // boundary terms of the vertices, laid out like `recs`.

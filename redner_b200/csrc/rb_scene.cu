@@ -18,9 +18,25 @@ void rb_set_error(const std::string& msg) { g_last_error = msg; }
 extern "C" const char* rb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char* rb_version(void) { return "redner_b200 0.1 (sm_100a)"; }
 
+// Scene buffers come from the device's default stream-ordered pool.  Its default release threshold (0) hands the memory
+// back to the driver at every synchronisation, so a scene rebuilt each optimiser step would pay a real allocation each
+// time: keep up to 256 MiB cached in the pool.
+static void keep_pool_warm(int device) {
+    static std::mutex m;
+    static bool done[64] = {};
+    std::lock_guard<std::mutex> lock(m);
+    if (done[device & 63]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = 256ULL << 20;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[device & 63] = true;
+}
 template <typename T>
 static int dev_alloc(rb_scene* sc, T** out, size_t count, cudaStream_t stream) {
     void* p = nullptr;
+    keep_pool_warm(sc->device);
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
     RB_CUDA_OK(cudaMallocAsync(&p, bytes, stream));
     sc->allocs.push_back(p);

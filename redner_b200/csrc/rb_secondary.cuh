@@ -329,16 +329,24 @@ RB_HD V3 intersect_jacobian(V3 org, V3 dir, V3 p, V3 n, V3 l) {
     return t * (l - dir * (dot(l, n) / dn));
 }
 
-// Samples one silhouette edge as seen from path vertex `cur` (depth `depth`), traces the two sub-paths on either side
-// of it and accumulates the boundary-term gradient into the shading point position (d_position) and the two edge
-// vertices.  `smp` is the edge sampler positioned at this depth's first dimension; `d_color` is the raw d_image pixel.
-RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const VertexRec& cur, int depth, Sampler smp,
-                                V3 d_color, int strategy_bit, V3& d_position) {
-    const Real weight = Real(1) / Real(rp.spp);
+// Boundary term of one path vertex in two steps (src/edge.cpp:826-2053):
+//   secondary_edge_pick   chooses a silhouette edge and a point on it as seen from the vertex (hierarchy or gather)
+//   secondary_edge_shade  traces the two rays on either side of it with their sub-paths and accumulates the gradient
+//                         of the shading-point position (returned) and of the two edge vertices (scattered)
+// k_bwd_secondary_pick / _shade run them as two kernels with a sort by edge in between: after the pick only about half
+// of the lanes are still alive and each continues towards a different edge.
+struct alignas(16) EdgePick {
+    int edge_id;
+    int flags; // bit 0: diffuse lobe, bit 1: gather strategy, bit 2: diffuse or glossy
+    float w;   // edge_weight / strategy pmf
+    V3 sample_p, mwt;
+};
+// `smp` is the edge sampler positioned at this depth's first dimension (4 dimensions are consumed here).
+RB_D bool secondary_edge_pick(const DevScene& sc, const VertexRec& cur, Sampler& smp, int strategy_bit, EdgePick& pk) {
     double s_edge_sel = smp.next(), s_resample = smp.next(), s_component = smp.next(), s_t = smp.next();
     Real min_rough = cur.min_rough;
     // secondary edges are only sampled until the first rough bounce (src/edge.cpp:1396-1401)
-    if (min_rough > Real(1e-2)) return;
+    if (min_rough > Real(1e-2)) return false;
     const rb_shape& shape = sc.shapes[cur.isect.shape_id];
     const rb_material& mat = sc.materials[shape.material_id];
     RayDiff rd;
@@ -355,7 +363,7 @@ RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const R
 
     V3 kd = mat_diffuse(mat, sp), ks = mat_specular(mat, sp);
     Real wd = luminance(kd), ws = luminance(ks), wsum = wd + ws;
-    if (wsum <= 0) return;
+    if (wsum <= 0) return false;
     Real pd = wd / wsum, ps = ws / wsum;
     V3 n = sp.shading_frame.n;
     if (mat.two_sided && dot(wi, n) < 0) n = -n;
@@ -408,11 +416,11 @@ RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const R
     if (!use_nee) {
         // (edge_sel is no longer consumed by the strategy coin, so it is uniform on [0, 1) as it stands)
         edge_id = sample_edge_hier(c, edge_sel, (Real)s_resample, edge_weight);
-        if (edge_id == -1 || edge_weight <= 0) return;
+        if (edge_id == -1 || edge_weight <= 0) return false;
         const Edge& e = sc.edges[edge_id];
-        if (!edge_is_silhouette(sc.shapes, sp.position, e)) return;
+        if (!edge_is_silhouette(sc.shapes, sp.position, e)) return false;
         V3 a = mul(c.m_inv, edge_v0(sc.shapes, e) - sp.position), b = mul(c.m_inv, edge_v1(sc.shapes, e) - sp.position);
-        if (a.z <= 0 && b.z <= 0) return;
+        if (a.z <= 0 && b.z <= 0) return false;
         if (a.z < 0) a = (a * b.z - b * a.z) / (b.z - a.z);
         if (b.z < 0) b = (a * b.z - b * a.z) / (b.z - a.z);
         V3 wt = normalize(b - a);
@@ -442,14 +450,35 @@ RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const R
             l -= value / line_pdf(l);
         }
         Real lpdf = line_pdf(l);
-        if (!(lpdf > 0)) return;
+        if (!(lpdf > 0)) return false;
         sample_p = mul(c.m, vo + l * wt);
         edge_weight /= (m_pmf * lpdf);
         mwt = mul(c.m, wt);
     } else {
         edge_id = sample_edge_gather(c, nee, cur.light.isect, lp, (Real)s_resample, edge_weight, sample_p, mwt);
-        if (edge_id == -1 || edge_weight <= 0) return;
+        if (edge_id == -1 || edge_weight <= 0) return false;
     }
+    pk.edge_id = edge_id;
+    pk.flags = (diffuse_lobe ? 1 : 0) | (use_nee ? 2 : 0) | (diffuse_or_glossy ? 4 : 0);
+    pk.w = (float)(edge_weight / nee_pmf);
+    pk.sample_p = sample_p;
+    pk.mwt = mwt;
+    return true;
+}
+// `smp` must be positioned 4 dimensions after the start of this depth (both edge rays share the following light / bsdf
+// samples); `d_color` is the raw d_image pixel.
+RB_D void secondary_edge_shade(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const VertexRec& cur, int depth, Sampler smp, V3 d_color,
+                               const EdgePick& pk, V3& d_position) {
+    const Real weight = Real(1) / Real(rp.spp);
+    const Real min_rough = cur.min_rough;
+    const rb_shape& shape = sc.shapes[cur.isect.shape_id];
+    const rb_material& mat = sc.materials[shape.material_id];
+    RayDiff rd;
+    SurfacePoint sp = make_surface_point(shape, cur.isect.tri_id, cur.ray, cur.rd_in, rd);
+    V3 wi = -cur.ray.dir;
+    const int edge_id = pk.edge_id;
+    const bool diffuse_lobe = (pk.flags & 1) != 0, use_nee = (pk.flags & 2) != 0, diffuse_or_glossy = (pk.flags & 4) != 0;
+    const V3 sample_p = pk.sample_p, mwt = pk.mwt;
     const Edge edge = sc.edges[edge_id];
     V3 v0 = edge_v0(sc.shapes, edge), v1 = edge_v1(sc.shapes, edge);
     V3 hpn = normalize(cross(v0 - sp.position, v1 - sp.position));
@@ -473,7 +502,7 @@ RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const R
         rd_e.dir_dx = rd.dir_dx - 2 * (-dot(wi, h) * sp.dn_dx + ddn_dx * h);
         rd_e.dir_dy = rd.dir_dy - 2 * (-dot(wi, h) * sp.dn_dy + ddn_dy * h);
     }
-    V3 nt = cur.thr * f * d_color * (edge_weight / nee_pmf);
+    V3 nt = cur.thr * f * d_color * (Real)pk.w;
     // advance the sampler past this depth's 4 dimensions: both edge rays share the following light/bsdf samples
     Isect eis[2];
     SurfacePoint esp[2];
@@ -535,4 +564,12 @@ RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const R
         agg_add3(dv + 3 * (size_t)edge.v0, dv0);
         agg_add3(dv + 3 * (size_t)edge.v1, dv1);
     }
+}
+
+// pick + shade for one vertex (host-compiled emulator; the kernels run the two steps separately)
+RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const VertexRec& cur, int depth, Sampler smp,
+                                V3 d_color, int strategy_bit, V3& d_position) {
+    EdgePick pk;
+    if (!secondary_edge_pick(sc, cur, smp, strategy_bit, pk)) return;
+    secondary_edge_shade(sc, ds, rp, cur, depth, smp, d_color, pk, d_position);
 }
