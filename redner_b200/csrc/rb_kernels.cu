@@ -18,6 +18,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -510,7 +511,12 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         ka.rec_per_sample = rp.max_bounces + 1;
         const size_t per_sample = (size_t)ka.rec_per_sample * (sizeof(VertexRec) + (secondary ? sizeof(V3) + sizeof(EdgePick) + 16 + 8 : 0) + sizeof(int)) + 2 * sizeof(int) +
                                   sizeof(unsigned long long);
-        long long band = (long long)std::max<size_t>(RB_BAND_BYTES / per_sample, 32768);
+        size_t band_bytes = RB_BAND_BYTES;
+        if (const char* env = getenv("RB_BAND_BYTES")) { // test hook: force many small bands
+            long long v = atoll(env);
+            if (v > 0) band_bytes = (size_t)v;
+        }
+        long long band = (long long)std::max<size_t>(band_bytes / per_sample, 1024);
         band = std::min<long long>(band, (1LL << 30) / ka.rec_per_sample);
         band = std::min<long long>(band, std::max<long long>(total_samples, 1));
         size_t scan_bytes = 0;

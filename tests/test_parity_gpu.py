@@ -72,6 +72,18 @@ def test_gbuffer_golden(rb, dev, name):
             d += n
 
 
+def test_band_size_does_not_change_gradients(rb, dev, monkeypatch):
+    """The adjoint pass walks the image in bands (records through HBM, per-band compaction and sorts): one band or
+    hundreds of tiny ones must give the same sample-exact gradients (secondary edges off: their strategy coin is per block)."""
+    cfg = dict(pu.CASES["glossy_room_sobol_mb2"], edges=1)
+    _, g_one = pu.render_case(rb, dev, cfg, 9)
+    monkeypatch.setenv("RB_BAND_BYTES", str(1 << 20))
+    _, g_many = pu.render_case(rb, dev, cfg, 9)
+    assert set(g_one) == set(g_many)
+    for k in g_one:
+        assert pu.rel_l2(g_many[k].numpy(), g_one[k].numpy()) < 1e-5, k
+
+
 def test_backward_rejects_gbuffer_channels(rb, dev):
     """The adjoint pass is implemented for channels == [radiance]; anything else must fail loudly, not silently differ."""
     sc = scenes.SCENES["single_triangle"](dev, resolution=(16, 16))
