@@ -422,14 +422,26 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
     RayDiff rd;
     cam_primary_ray(sc.cam, ept.x, ept.y, cray, rd);
     Real contrib = 0;
+    Ray rays[2];
+    Isect hits[2];
+    bool connected = false;
     for (int side = 0; side < 2; side++) {
         double sgn = side == 0 ? 1.0 : -1.0;
         D3 o, d;
         cam_sample_primary(sc.cam, ept.x + sgn * nx * offset, ept.y + sgn * ny * offset, o, d);
-        Ray ray = make_ray(o, d);
+        rays[side] = make_ray(o, d);
+        hits[side] = no_isect();
+        closest_hit(sc, rays[side], hits[side]);
+        // at least one side must see a face of the edge, otherwise the edge is hidden here and the sample is dropped
+        // (primary_edge_weights_updater, src/edge.cpp:653-676)
+        connected = connected || (hits[side].shape_id == edge.shape_id && (hits[side].tri_id == edge.f0 || hits[side].tri_id == edge.f1));
+    }
+    if (!connected) return;
+    for (int side = 0; side < 2; side++) {
+        const Ray ray = rays[side];
+        const Isect is = hits[side];
+        if (!is.valid()) continue;
         V3 thr = side == 0 ? wgt : -wgt;
-        Isect is = no_isect();
-        if (!closest_hit(sc, ray, is)) continue;
         RayDiff rd_after;
         SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
         contrib += sum(weight * thr * hit_emission(sc, is, sp, -ray.dir));

@@ -77,6 +77,44 @@ inline bool host_pos_less(const float* a, const float* b) { // strict lexicograp
 }
 inline bool host_pos_eq(const float* a, const float* b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
 
+// Host sort of the reference's Thrust (sequential backend, thrust/system/detail/sequential/stable_merge_sort.inl,
+// insertion_sort.h, merge.inl): insertion sort for <= 32 elements, otherwise sort both halves recursively and merge,
+// taking from the right run whenever comp(right, left).  Identical to std::stable_sort for a strict weak ordering;
+// restated because one of the reference's comparators is not strict.
+template <typename T, typename Comp>
+inline void host_merge_sort_range(std::vector<T>& v, size_t first, size_t last, Comp comp) {
+    if (last - first <= 32) {
+        for (size_t i = first + 1; i < last; i++) {
+            T tmp = v[i];
+            if (comp(tmp, v[first])) {
+                for (size_t j = i; j > first; j--) v[j] = v[j - 1];
+                v[first] = tmp;
+            } else {
+                size_t j = i, k = i - 1;
+                while (comp(tmp, v[k])) {
+                    v[j] = v[k];
+                    j = k;
+                    --k;
+                }
+                v[j] = tmp;
+            }
+        }
+        return;
+    }
+    size_t middle = first + (last - first) / 2;
+    host_merge_sort_range(v, first, middle, comp);
+    host_merge_sort_range(v, middle, last, comp);
+    std::vector<T> a(v.begin() + first, v.begin() + middle), b(v.begin() + middle, v.begin() + last);
+    size_t i = 0, j = 0, o = first;
+    while (i < a.size() && j < b.size()) v[o++] = comp(b[j], a[i]) ? b[j++] : a[i++];
+    while (i < a.size()) v[o++] = a[i++];
+    while (j < b.size()) v[o++] = b[j++];
+}
+template <typename T, typename Comp>
+inline void host_merge_sort_like_reference(std::vector<T>& v, Comp comp) {
+    host_merge_sort_range(v, 0, v.size(), comp);
+}
+
 // `shapes` carries device (or emulator-host) pointers; only material / light ids and the null-ness of `normals` are
 // read from it here, geometry comes from `meshes`.
 inline void host_build_edges(const std::vector<rb_shape>& shapes, const std::vector<HostMesh>& meshes, const DevCamera& cam, bool want_primary,
@@ -123,13 +161,16 @@ inline void host_build_edges(const std::vector<rb_shape>& shapes, const std::vec
             hi = V + 3 * (size_t)e.v1;
             if (host_pos_less(hi, lo)) std::swap(lo, hi);
         };
-        std::stable_sort(merged.begin(), merged.end(), [&](const Edge& x, const Edge& y) {
+        // The reference's comparator answers TRUE for equal keys (src/edge.cpp:93-131), so the order of seam twins -- and
+        // with it which copy of a duplicated vertex a sample's gradient lands on -- is whatever its sort algorithm makes
+        // of that: restated step by step above (host_merge_sort_like_reference).
+        host_merge_sort_like_reference(merged, [&](const Edge& x, const Edge& y) {
             const float *xl, *xh, *yl, *yh;
             key(x, xl, xh);
             key(y, yl, yh);
             if (!host_pos_eq(xl, yl)) return host_pos_less(xl, yl);
             if (!host_pos_eq(xh, yh)) return host_pos_less(xh, yh);
-            return false;
+            return true;
         });
         std::vector<int> new_f1(merged.size());
         for (size_t i = 0; i < merged.size(); i++) {

@@ -20,6 +20,11 @@ CASES = {
     # glossy textured room: specular lobe, shading normals, uvs, mip-mapped textures, two lights, 2 bounces
     "glossy_room_sobol_mb2": dict(scene="glossy_room", res=48, spp=8, mb=2, sampler="sobol", edges=0, seed=5),
     "glossy_room_pcg_mb3": dict(scene="glossy_room", res=32, spp=4, mb=3, sampler="independent", edges=0, seed=7),
+    # primary edges on a smooth, uv-seamed mesh behind / in front of other geometry: hidden-edge rejection (an edge sample
+    # counts only if one of its two rays sees a face of the edge) and the order of duplicated seam edges.  Rays graze the
+    # silhouette by construction, so a few hit decisions differ between any two BVHs -- the reference itself changes by
+    # ~1e-4 between two runs (Embree's parallel build) -- hence the looser tolerance on the vertex gradient.
+    "glossy_room_primary_edges": dict(scene="glossy_room", res=40, spp=8, mb=1, sampler="sobol", edges=1, seed=13, vertex_tol=5e-3),
     # normal-mapped ball with a mip-mapped specular texture and a differentiable uv_scale
     "nmap_room_sobol_mb2": dict(scene="nmap_room", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=11),
 }
