@@ -442,10 +442,7 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             rp.rad_dim = i;
         }
     }
-    if (d_image != nullptr && !only_radiance) {
-        rb_set_error("rb_render: the backward pass is implemented for channels == [radiance] only (G-buffer adjoints: SURVEY.md 8f rank 3)");
-        return 1;
-    }
+    rp.only_radiance = only_radiance ? 1 : 0;
     rp.nd = rb_compute_num_channels(opt->channels, opt->num_channels, rp.max_generic);
     if (rp.nd > RB_MAX_ND) {
         rb_set_error("rb_render: more than 64 image dimensions requested");
@@ -506,7 +503,7 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             return 1;
         }
         // ---- scratch layout: gradient descriptors | camera accumulators | band (records, boundary terms, lists, scan)
-        const bool secondary = scene->dev.use_secondary_edge && scene->dev.num_edges > 0 && scene->dev.num_lights > 0;
+        const bool secondary = scene->dev.use_secondary_edge && scene->dev.num_edges > 0 && scene->dev.num_lights > 0 && rp.rad_dim >= 0;
         const long long total_samples = (long long)ka.owned_rows * rp.vp_w * rp.spp;
         ka.rec_per_sample = rp.max_bounces + 1;
         const size_t per_sample = (size_t)ka.rec_per_sample * (sizeof(VertexRec) + (secondary ? sizeof(V3) + sizeof(EdgePick) + 16 + 8 : 0) + sizeof(int)) + 2 * sizeof(int) +

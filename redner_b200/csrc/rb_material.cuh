@@ -78,7 +78,9 @@ struct TexAdjoint { // returned by value so that the caller's SurfacePoint adjoi
 // d(du_dxy), d(dv_dxy).  Levels and taps are walked by ROLLED loops and each texel takes one aggregated 3-float
 // reduction (nch <= 3 on this path: reflectances, roughness, normal map), so the whole adjoint is ~0.5k SASS
 // instructions instead of the 36 unrolled aggregated atomics it used to be.
-RB_D TexAdjoint d_tex_eval_mip(const rb_texture& t, const rb_texture& d_t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, Real d0, Real d1, Real d2) {
+// `nch` is the texel stride; the call covers channels [c0, c0 + ncomp), ncomp <= 3 (wider textures: one call per triple).
+RB_D TexAdjoint d_tex_eval_mip(const rb_texture& t, const rb_texture& d_t, int nch, V2 uv_, V2 du_dxy_, V2 dv_dxy_, Real d0, Real d1, Real d2, int c0 = 0,
+                               int ncomp = 3) {
     V2 d_uv_ = zero2(), d_du_dxy_ = zero2(), d_dv_dxy_ = zero2();
     Real sx = t.uv_scale[0], sy = t.uv_scale[1];
     V2 uv = mk2(uv_.x * sx, uv_.y * sy);
@@ -102,8 +104,9 @@ RB_D TexAdjoint d_tex_eval_mip(const rb_texture& t, const rb_texture& d_t, int n
         nl = 2;
         ld = level - l0;
     }
-    if (nch < 2) d1 = 0;
-    if (nch < 3) d2 = 0;
+    if (ncomp > nch - c0) ncomp = nch - c0;
+    if (ncomp < 2) d1 = 0;
+    if (ncomp < 3) d2 = 0;
 #pragma unroll 1
     for (int j = 0; j < nl; j++) {
         int li = l0 + j;
@@ -114,11 +117,11 @@ RB_D TexAdjoint d_tex_eval_mip(const rb_texture& t, const rb_texture& d_t, int n
         Real d_u = 0, d_v = 0, val = 0;
 #pragma unroll 1
         for (int k = 0; k < 4; k++) { // bit 0: ceil in x, bit 1: ceil in y
-            int idx = nch * (k == 0 ? b.i_ff : k == 1 ? b.i_cf : k == 2 ? b.i_fc : b.i_cc);
+            int idx = nch * (k == 0 ? b.i_ff : k == 1 ? b.i_cf : k == 2 ? b.i_fc : b.i_cc) + c0;
             Real wu = (k & 1) ? b.u : 1 - b.u, wv = (k & 2) ? b.v : 1 - b.v;
             Real tv = d0 * tex[idx];
-            if (nch > 1) tv += d1 * tex[idx + 1];
-            if (nch > 2) tv += d2 * tex[idx + 2];
+            if (ncomp > 1) tv += d1 * tex[idx + 1];
+            if (ncomp > 2) tv += d2 * tex[idx + 2];
             val += tv * wu * wv;
             d_u += (k & 1) ? tv * wv : -tv * wv;
             d_v += (k & 2) ? tv * wu : -tv * wu;
@@ -159,10 +162,14 @@ RB_D void d_tex_eval(const rb_texture& t, const rb_texture& d_t, int nch, V2 uv_
         }
         return;
     }
-    TexAdjoint r = d_tex_eval_mip(t, d_t, nch, uv_, du_dxy_, dv_dxy_, d_out[0], nch > 1 ? d_out[1] : Real(0), nch > 2 ? d_out[2] : Real(0));
-    d_uv_ += r.d_uv;
-    d_du_dxy_ += r.d_du_dxy;
-    d_dv_dxy_ += r.d_dv_dxy;
+#pragma unroll 1
+    for (int c0 = 0; c0 < nch; c0 += 3) { // one pass for every texture of the BSDF (nch <= 3); generic textures take more
+        TexAdjoint r = d_tex_eval_mip(t, d_t, nch, uv_, du_dxy_, dv_dxy_, d_out[c0], c0 + 1 < nch ? d_out[c0 + 1] : Real(0),
+                                      c0 + 2 < nch ? d_out[c0 + 2] : Real(0), c0, 3);
+        d_uv_ += r.d_uv;
+        d_du_dxy_ += r.d_du_dxy;
+        d_dv_dxy_ += r.d_dv_dxy;
+    }
 }
 
 // ---------------------------------------------------------------- material helpers

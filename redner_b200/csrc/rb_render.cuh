@@ -43,6 +43,15 @@ struct KernelArgs {
     int n_paths, n_verts;        // host copies of `totals` (read back once per band)
 };
 
+RB_HD int rb_channel_width(int ch, int max_generic) { // floats of one channel, src/channels.cpp:42-113
+    switch (ch) {
+        case RB_CH_RADIANCE: case RB_CH_POSITION: case RB_CH_GEOMETRY_NORMAL: case RB_CH_SHADING_NORMAL: case RB_CH_DIFFUSE_REFLECTANCE:
+        case RB_CH_SPECULAR_REFLECTANCE: case RB_CH_VERTEX_COLOR: return 3;
+        case RB_CH_UV: case RB_CH_BARYCENTRIC: return 2;
+        case RB_CH_GENERIC_TEXTURE: return max_generic;
+        default: return 1;
+    }
+}
 RB_HD unsigned long long main_draws_per_sample(const RenderParams& rp) {
     return (unsigned long long)((rp.sample_pixel_center ? 0 : 2) + 7 * rp.max_bounces);
 }
@@ -101,10 +110,106 @@ RB_D V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, in
     return acc;
 }
 
-// G-buffer variant of forward_sample: accumulates every requested channel of the first hit into out[0..nd)
-// (src/primary_contribution.cpp:36-253) plus the path-traced radiance.  Id channels (shape / triangle / material) are
-// assigned, not averaged ("the last sample wins" in the reference); they are returned in ids[] and resolved by the kernel.
+// Values of every non-radiance, non-id channel at a first hit, at their float offsets in vals[0..nd) (unweighted;
+// src/primary_contribution.cpp:36-253).  Radiance and id slots are left untouched.
 #define RB_MAX_ND 64
+RB_D void channel_values_at_hit(const DevScene& sc, const RenderParams& rp, const Isect& is, const SurfacePoint& sp, const Ray& ray, Real* vals) {
+    const rb_shape& shape = sc.shapes[is.shape_id];
+    const rb_material& mat = sc.materials[shape.material_id];
+    int d = 0;
+    for (int c = 0; c < rp.num_channels; c++) {
+        switch (rp.channels[c]) {
+            case RB_CH_RADIANCE: d += 3; break;
+            case RB_CH_ALPHA: vals[d] = 1; d += 1; break;
+            case RB_CH_DEPTH: vals[d] = length(sp.position - ray.org); d += 1; break;
+            case RB_CH_POSITION: vals[d] = sp.position.x; vals[d + 1] = sp.position.y; vals[d + 2] = sp.position.z; d += 3; break;
+            case RB_CH_GEOMETRY_NORMAL: vals[d] = sp.geom_normal.x; vals[d + 1] = sp.geom_normal.y; vals[d + 2] = sp.geom_normal.z; d += 3; break;
+            case RB_CH_SHADING_NORMAL: {
+                V3 n = sp.shading_frame.n;
+                if (mat_has_normal_map(mat)) n = perturb_shading_frame(mat, sp).n;
+                vals[d] = n.x; vals[d + 1] = n.y; vals[d + 2] = n.z;
+                d += 3;
+            } break;
+            case RB_CH_UV: vals[d] = sp.uv.x; vals[d + 1] = sp.uv.y; d += 2; break;
+            case RB_CH_BARYCENTRIC: vals[d] = sp.bary.x; vals[d + 1] = sp.bary.y; d += 2; break;
+            case RB_CH_DIFFUSE_REFLECTANCE: {
+                V3 r = mat.use_vertex_color ? sp.color : mat_diffuse(mat, sp);
+                vals[d] = r.x; vals[d + 1] = r.y; vals[d + 2] = r.z;
+                d += 3;
+            } break;
+            case RB_CH_SPECULAR_REFLECTANCE: {
+                V3 r = mat_specular(mat, sp);
+                vals[d] = r.x; vals[d + 1] = r.y; vals[d + 2] = r.z;
+                d += 3;
+            } break;
+            case RB_CH_ROUGHNESS: vals[d] = mat_roughness(mat, sp); d += 1; break;
+            case RB_CH_GENERIC_TEXTURE: {
+                if (mat.generic_texture.num_levels > 0) {
+                    int n = mat.generic_texture.channels < RB_MAX_ND ? mat.generic_texture.channels : RB_MAX_ND;
+                    tex_eval(mat.generic_texture, n, sp.uv, sp.du_dxy, sp.dv_dxy, vals + d);
+                }
+                d += rp.max_generic;
+            } break;
+            case RB_CH_VERTEX_COLOR: vals[d] = sp.color.x; vals[d + 1] = sp.color.y; vals[d + 2] = sp.color.z; d += 3; break;
+            default: d += 1; break; // ids
+        }
+    }
+}
+// Adjoint of channel_values_at_hit (src/primary_contribution.cpp:486-692): d_vals[0..nd) are the (already weighted)
+// adjoints of the channel values; results go to the surface-point adjoint, the ray origin (depth) and the textures.
+RB_D void d_channel_values_at_hit(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const Isect& is, const SurfacePoint& sp, const Ray& ray,
+                                  const Real* d_vals, SurfacePoint& d_sp, V3& d_ray_org) {
+    const rb_shape& shape = sc.shapes[is.shape_id];
+    const rb_material& mat = sc.materials[shape.material_id];
+    const rb_material& d_mat = ds.materials[shape.material_id];
+    int d = 0;
+    for (int c = 0; c < rp.num_channels; c++) {
+        switch (rp.channels[c]) {
+            case RB_CH_RADIANCE: d += 3; break;
+            case RB_CH_DEPTH: {
+                V3 diff = sp.position - ray.org;
+                Real l = length(diff);
+                if (l > 0) {
+                    V3 g = diff * (d_vals[d] / l);
+                    d_sp.position += g;
+                    d_ray_org -= g;
+                }
+                d += 1;
+            } break;
+            case RB_CH_POSITION: d_sp.position += mk3(d_vals[d], d_vals[d + 1], d_vals[d + 2]); d += 3; break;
+            case RB_CH_GEOMETRY_NORMAL: d_sp.geom_normal += mk3(d_vals[d], d_vals[d + 1], d_vals[d + 2]); d += 3; break;
+            // (the reference sends this adjoint to the unperturbed shading normal even under a normal map, :551-566)
+            case RB_CH_SHADING_NORMAL: d_sp.shading_frame.n += mk3(d_vals[d], d_vals[d + 1], d_vals[d + 2]); d += 3; break;
+            case RB_CH_UV: d_sp.uv += mk2(d_vals[d], d_vals[d + 1]); d += 2; break;
+            case RB_CH_BARYCENTRIC: d_sp.bary += mk2(d_vals[d], d_vals[d + 1]); d += 2; break;
+            case RB_CH_DIFFUSE_REFLECTANCE:
+                if (mat.use_vertex_color) d_sp.color += mk3(d_vals[d], d_vals[d + 1], d_vals[d + 2]);
+                else d_tex_eval(mat.diffuse_reflectance, d_mat.diffuse_reflectance, 3, sp.uv, sp.du_dxy, sp.dv_dxy, d_vals + d, d_sp.uv, d_sp.du_dxy, d_sp.dv_dxy);
+                d += 3;
+                break;
+            case RB_CH_SPECULAR_REFLECTANCE:
+                d_tex_eval(mat.specular_reflectance, d_mat.specular_reflectance, 3, sp.uv, sp.du_dxy, sp.dv_dxy, d_vals + d, d_sp.uv, d_sp.du_dxy, d_sp.dv_dxy);
+                d += 3;
+                break;
+            case RB_CH_ROUGHNESS:
+                d_tex_eval(mat.roughness, d_mat.roughness, 1, sp.uv, sp.du_dxy, sp.dv_dxy, d_vals + d, d_sp.uv, d_sp.du_dxy, d_sp.dv_dxy);
+                d += 1;
+                break;
+            case RB_CH_GENERIC_TEXTURE:
+                if (mat.generic_texture.num_levels > 0 && d_mat.generic_texture.num_levels > 0) {
+                    int n = mat.generic_texture.channels < RB_MAX_ND ? mat.generic_texture.channels : RB_MAX_ND;
+                    d_tex_eval(mat.generic_texture, d_mat.generic_texture, n, sp.uv, sp.du_dxy, sp.dv_dxy, d_vals + d, d_sp.uv, d_sp.du_dxy, d_sp.dv_dxy);
+                }
+                d += rp.max_generic;
+                break;
+            case RB_CH_VERTEX_COLOR: d_sp.color += mk3(d_vals[d], d_vals[d + 1], d_vals[d + 2]); d += 3; break;
+            default: d += 1; break; // alpha and ids: nothing to propagate
+        }
+    }
+}
+// G-buffer variant of forward_sample: accumulates every requested channel of the first hit into out[0..nd)
+// plus the path-traced radiance.  Id channels (shape / triangle / material) are assigned, not averaged ("the last
+// sample wins" in the reference); they are returned in ids[] and resolved by the kernel.
 RB_D bool forward_sample_channels(const DevScene& sc, const RenderParams& rp, int pixel, int px, int py, int s, float* out, int* ids) {
     const Real weight = Real(1) / Real(rp.spp);
     Sampler smp;
@@ -118,54 +223,26 @@ RB_D bool forward_sample_channels(const DevScene& sc, const RenderParams& rp, in
     if (!closest_hit(sc, ray, is)) return false;
     RayDiff rd_after;
     const rb_shape& shape = sc.shapes[is.shape_id];
-    const rb_material& mat = sc.materials[shape.material_id];
     SurfacePoint sp = make_surface_point(shape, is.tri_id, ray, rd, rd_after);
+    Real vals[RB_MAX_ND];
+    for (int i = 0; i < rp.nd; i++) vals[i] = 0;
+    channel_values_at_hit(sc, rp, is, sp, ray, vals);
     int d = 0;
     for (int c = 0; c < rp.num_channels; c++) {
-        switch (rp.channels[c]) {
-            case RB_CH_RADIANCE: {
-                V3 L = hit_emission(sc, is, sp, -ray.dir);
-                out[d] += (float)(weight * L.x); out[d + 1] += (float)(weight * L.y); out[d + 2] += (float)(weight * L.z);
-                d += 3;
-            } break;
-            case RB_CH_ALPHA: out[d] += (float)weight; d += 1; break;
-            case RB_CH_DEPTH: out[d] += (float)(length(sp.position - ray.org) * weight); d += 1; break;
-            case RB_CH_POSITION: out[d] += (float)(sp.position.x * weight); out[d + 1] += (float)(sp.position.y * weight); out[d + 2] += (float)(sp.position.z * weight); d += 3; break;
-            case RB_CH_GEOMETRY_NORMAL: out[d] += (float)(sp.geom_normal.x * weight); out[d + 1] += (float)(sp.geom_normal.y * weight); out[d + 2] += (float)(sp.geom_normal.z * weight); d += 3; break;
-            case RB_CH_SHADING_NORMAL: {
-                V3 n = sp.shading_frame.n;
-                if (mat_has_normal_map(mat)) n = perturb_shading_frame(mat, sp).n;
-                out[d] += (float)(n.x * weight); out[d + 1] += (float)(n.y * weight); out[d + 2] += (float)(n.z * weight);
-                d += 3;
-            } break;
-            case RB_CH_UV: out[d] += (float)(sp.uv.x * weight); out[d + 1] += (float)(sp.uv.y * weight); d += 2; break;
-            case RB_CH_BARYCENTRIC: out[d] += (float)(sp.bary.x * weight); out[d + 1] += (float)(sp.bary.y * weight); d += 2; break;
-            case RB_CH_DIFFUSE_REFLECTANCE: {
-                V3 r = mat.use_vertex_color ? sp.color : mat_diffuse(mat, sp);
-                out[d] += (float)(r.x * weight); out[d + 1] += (float)(r.y * weight); out[d + 2] += (float)(r.z * weight);
-                d += 3;
-            } break;
-            case RB_CH_SPECULAR_REFLECTANCE: {
-                V3 r = mat_specular(mat, sp);
-                out[d] += (float)(r.x * weight); out[d + 1] += (float)(r.y * weight); out[d + 2] += (float)(r.z * weight);
-                d += 3;
-            } break;
-            case RB_CH_ROUGHNESS: out[d] += (float)(mat_roughness(mat, sp) * weight); d += 1; break;
-            case RB_CH_GENERIC_TEXTURE: {
-                if (mat.generic_texture.num_levels > 0) {
-                    Real buf[RB_MAX_ND];
-                    int n = mat.generic_texture.channels < RB_MAX_ND ? mat.generic_texture.channels : RB_MAX_ND;
-                    tex_eval(mat.generic_texture, n, sp.uv, sp.du_dxy, sp.dv_dxy, buf);
-                    for (int i = 0; i < n; i++) out[d + i] += (float)(buf[i] * weight);
-                }
-                d += rp.max_generic;
-            } break;
-            case RB_CH_VERTEX_COLOR: out[d] += (float)(sp.color.x * weight); out[d + 1] += (float)(sp.color.y * weight); out[d + 2] += (float)(sp.color.z * weight); d += 3; break;
-            case RB_CH_SHAPE_ID: ids[0] = is.shape_id; d += 1; break;
-            case RB_CH_TRIANGLE_ID: ids[1] = is.tri_id; d += 1; break;
-            case RB_CH_MATERIAL_ID: ids[2] = shape.material_id; d += 1; break;
-            default: break;
+        int w = rb_channel_width(rp.channels[c], rp.max_generic);
+        if (rp.channels[c] == RB_CH_RADIANCE) {
+            V3 L = hit_emission(sc, is, sp, -ray.dir);
+            out[d] += (float)(weight * L.x); out[d + 1] += (float)(weight * L.y); out[d + 2] += (float)(weight * L.z);
+        } else if (rp.channels[c] == RB_CH_SHAPE_ID) {
+            ids[0] = is.shape_id;
+        } else if (rp.channels[c] == RB_CH_TRIANGLE_ID) {
+            ids[1] = is.tri_id;
+        } else if (rp.channels[c] == RB_CH_MATERIAL_ID) {
+            ids[2] = shape.material_id;
+        } else {
+            for (int i = 0; i < w; i++) out[d + i] += (float)(vals[d + i] * weight);
         }
+        d += w;
     }
     if (rp.rad_dim >= 0) {
         V3 Lb = weight * trace_bounces<false>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, nullptr, 0, nullptr, &od, &dd);
@@ -201,7 +278,8 @@ RB_D int bwd_trace(const DevScene& sc, const RenderParams& rp, int pixel, int px
     RB_PHASE_SYNC();
     if (!act) return -1;
     int nrec = 0;
-    trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, recs, stride, &nrec, &od, &dd);
+    // (without a radiance channel only the first hit matters: the terminal record alone)
+    trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.rad_dim >= 0 ? rp.max_bounces : 0, recs, stride, &nrec, &od, &dd);
     return nrec;
 }
 // Boundary (visibility) term at vertex `depth` of the path of (pixel, s), src/pathtracer.cpp:500-707, in two steps (see
@@ -220,7 +298,7 @@ RB_D bool bwd_secondary_pick(const DevScene& sc, const KernelArgs& ka, int pixel
 RB_D V3 bwd_secondary_shade(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur, const EdgePick& pk) {
     const RenderParams& rp = ka.rp;
     V3 d_position = zero3();
-    const float* dpx = ka.d_image + (size_t)rp.nd * pixel + rp.rad_dim;
+    const float* dpx = ka.d_image + (size_t)rp.nd * pixel + (rp.rad_dim >= 0 ? rp.rad_dim : 0);
     secondary_edge_shade(sc, ka.ds, rp, cur, depth, bwd_edge_sampler(sc, rp, pixel, s, depth, 4), mk3(dpx[0], dpx[1], dpx[2]), pk, d_position);
     return d_position;
 }
@@ -236,8 +314,9 @@ RB_D void bwd_sweep(const DevScene& sc, const KernelArgs& ka, int pixel, int px,
     const RenderParams& rp = ka.rp;
     const DevDScene& ds = ka.ds;
     const Real weight = Real(1) / Real(rp.spp);
-    const float* dpx = ka.d_image + (size_t)rp.nd * pixel + rp.rad_dim;
-    V3 d_contrib = act ? weight * mk3(dpx[0], dpx[1], dpx[2]) : zero3();
+    const float* dpx_all = ka.d_image + (size_t)rp.nd * pixel;
+    const float* dpx = dpx_all + (rp.rad_dim >= 0 ? rp.rad_dim : 0);
+    V3 d_contrib = (act && rp.rad_dim >= 0) ? weight * mk3(dpx[0], dpx[1], dpx[2]) : zero3();
     VertexAdjoint adj = zero_vertex_adjoint();
     for (int d = rp.max_bounces - 1; d >= 0; d--) { // block-uniform trip count (phase barrier inside)
         RB_PHASE_SYNC();
@@ -264,10 +343,16 @@ RB_D void bwd_sweep(const DevScene& sc, const KernelArgs& ka, int pixel, int px,
             if (light.directly_visible) agg_add3(ds.light_intensity[shape.light_id], d_contrib);
         }
     }
+    DRay d_ray = adj.d_ray;
+    // G-buffer channels of the first hit (src/primary_contribution.cpp:486-692)
+    if (!rp.only_radiance) {
+        Real d_vals[RB_MAX_ND];
+        for (int i = 0; i < rp.nd; i++) d_vals[i] = weight * dpx_all[i];
+        d_channel_values_at_hit(sc, ds, rp, is, sp, ray, d_vals, adj.d_point, d_ray.org);
+    }
     // ... and the hit itself back to the mesh and the camera (src/primary_intersection.cpp:5-130)
     V3 d_vp[3] = {zero3(), zero3(), zero3()}, d_vn[3] = {zero3(), zero3(), zero3()}, d_vc[3] = {zero3(), zero3(), zero3()};
     V2 d_vuv[3] = {zero2(), zero2(), zero2()};
-    DRay d_ray = adj.d_ray;
     RayDiff d_prd = zero_raydiff();
     d_make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, adj.d_point, zero_raydiff(), d_ray, d_prd, d_vp, d_vn, d_vuv, d_vc);
     scatter_vertex_grads(sc, ds, is, d_vp, d_vn, d_vuv, d_vc);
@@ -302,7 +387,7 @@ RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, in
     int nrec = bwd_trace(sc, rp, pixel, px, py, s, recs, 1);
     if (nrec < 0) return -1;
     V3 dpos[RB_MAX_SWEEP_DEPTH];
-    bool sec = sc.use_secondary_edge && sc.num_edges > 0;
+    bool sec = sc.use_secondary_edge && sc.num_edges > 0 && rp.rad_dim >= 0;
     for (int d = 0; d < nrec && d < RB_MAX_SWEEP_DEPTH; d++) {
         int Lp = ka.lanes_per_pixel > 0 ? ka.lanes_per_pixel : 1;
         unsigned long long h = rb_hash64shift(((unsigned long long)(unsigned)((long long)pixel * Lp / 32) << 24) ^ ((unsigned long long)d << 16) ^ (rp.seed << 44));
@@ -414,8 +499,9 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
     int vp_w = rp.vp_w;
     int xi = rb_clampi(int(ept.x * sc.cam.width - sc.cam.vp_beg[0]), 0, sc.cam.vp_end[0] - sc.cam.vp_beg[0]);
     int yi = rb_clampi(int(ept.y * sc.cam.height - sc.cam.vp_beg[1]), 0, sc.cam.vp_end[1] - sc.cam.vp_beg[1]);
-    const float* dpx = ka.d_image + (size_t)rp.nd * ((size_t)yi * vp_w + xi) + rp.rad_dim;
-    V3 d_color = mk3(dpx[0], dpx[1], dpx[2]);
+    const float* dpx_all = ka.d_image + (size_t)rp.nd * ((size_t)yi * vp_w + xi);
+    const float* dpx = dpx_all + (rp.rad_dim >= 0 ? rp.rad_dim : 0);
+    V3 d_color = rp.rad_dim >= 0 ? mk3(dpx[0], dpx[1], dpx[2]) : zero3();
     V3 wgt = d_color / (Real)pmf;
     // ray differential of the un-offset ray, shared by both sides (src/edge.cpp:594-608)
     Ray cray;
@@ -444,10 +530,29 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
         V3 thr = side == 0 ? wgt : -wgt;
         RayDiff rd_after;
         SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
-        contrib += sum(weight * thr * hit_emission(sc, is, sp, -ray.dir));
-        Sampler sub = smp; // both sides consume the same light / bsdf samples (src/pathtracer.cpp:871-886)
-        V3 Lb = trace_bounces<false>(sc, sub, ray, rd, is, thr, Real(0), 0, rp.max_bounces, nullptr, 0, nullptr);
-        contrib += sum(weight * Lb);
+        if (rp.rad_dim >= 0) {
+            contrib += sum(weight * thr * hit_emission(sc, is, sp, -ray.dir));
+            Sampler sub = smp; // both sides consume the same light / bsdf samples (src/pathtracer.cpp:871-886)
+            V3 Lb = trace_bounces<false>(sc, sub, ray, rd, is, thr, Real(0), 0, rp.max_bounces, nullptr, 0, nullptr);
+            contrib += sum(weight * Lb);
+        }
+        if (!rp.only_radiance) {
+            // every other channel enters the edge integrand with its own d_image component as the multiplier
+            // (channel_multipliers, src/edge.cpp:476-481; src/primary_contribution.cpp:256-435)
+            Real vals[RB_MAX_ND];
+            for (int k = 0; k < rp.nd; k++) vals[k] = 0;
+            channel_values_at_hit(sc, rp, is, sp, ray, vals);
+            Real acc = 0;
+            int d = 0;
+            for (int c = 0; c < rp.num_channels; c++) {
+                int w = rb_channel_width(rp.channels[c], rp.max_generic);
+                int ch = rp.channels[c];
+                if (ch != RB_CH_RADIANCE && ch != RB_CH_SHAPE_ID && ch != RB_CH_TRIANGLE_ID && ch != RB_CH_MATERIAL_ID)
+                    for (int k = 0; k < w; k++) acc += vals[d + k] * (Real)dpx_all[d + k];
+                d += w;
+            }
+            contrib += (side == 0 ? weight : -weight) * acc / (Real)pmf;
+        }
     }
     if (contrib == 0) return;
     // Eq. 8: gradients of the edge equation w.r.t. the projected end points

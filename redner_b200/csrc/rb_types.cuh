@@ -162,6 +162,7 @@ struct RenderParams {
     int num_channels;
     int channels[RB_CH_COUNT];
     int max_generic;
+    int only_radiance; // channels == [radiance]: the common case, skips every G-buffer branch
     // multi-GPU partition over viewport rows
     int part, num_parts, rows_per_stripe;
     int vp_w, vp_h;

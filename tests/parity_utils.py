@@ -25,6 +25,14 @@ CASES = {
     # silhouette by construction, so a few hit decisions differ between any two BVHs -- the reference itself changes by
     # ~1e-4 between two runs (Embree's parallel build) -- hence the looser tolerance on the vertex gradient.
     "glossy_room_primary_edges": dict(scene="glossy_room", res=40, spp=8, mb=1, sampler="sobol", edges=1, seed=13, vertex_tol=5e-3),
+    # adjoints of the G-buffer channels (deferred rendering), interior + primary edges: src/primary_contribution.cpp:438-713,
+    # channel multipliers of the edge integrand src/edge.cpp:476-481
+    "gbuffer_bwd_glossy_room": dict(scene="glossy_room", res=32, spp=4, mb=1, sampler="sobol", edges=1, seed=4, vertex_tol=5e-3,
+                                    channels=["radiance", "alpha", "depth", "position", "geometry_normal", "shading_normal", "uv", "barycentric_coordinates",
+                                              "diffuse_reflectance", "specular_reflectance", "roughness", "shape_id"]),
+    # no radiance channel at all, max_bounces 0 (the deferred-shading set-up of the tutorials); camera gradients included
+    "gbuffer_bwd_single_triangle_no_radiance": dict(scene="single_triangle", res=32, spp=4, mb=0, sampler="sobol", edges=1, seed=7,
+                                                    channels=["depth", "alpha", "position", "uv"]),
     # normal-mapped ball with a mip-mapped specular texture and a differentiable uv_scale
     "nmap_room_sobol_mb2": dict(scene="nmap_room", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=11),
 }
@@ -74,13 +82,16 @@ def collect_grads(scene):
 def render_case(backend, device, cfg, seed, backward=True):
     sc = scenes.SCENES[cfg["scene"]](device, resolution=(cfg["res"], cfg["res"]))
     st = backend.SamplerType.sobol if cfg["sampler"] == "sobol" else backend.SamplerType.independent
-    args = api.RenderFunction.serialize_scene(sc, cfg["spp"], cfg["mb"], sampler_type=st, device=device, backend=backend,
+    chans = [getattr(backend.channels, c) for c in cfg["channels"]] if "channels" in cfg else None
+    args = api.RenderFunction.serialize_scene(sc, cfg["spp"], cfg["mb"], channels=chans, sampler_type=st, device=device, backend=backend,
                                               use_primary_edge_sampling=bool(cfg["edges"] & 1),
                                               use_secondary_edge_sampling=bool(cfg["edges"] & 2))
     img = api.RenderFunction.apply(seed, *args)
     grads = {}
     if backward and img.requires_grad:
-        img.pow(2).sum().backward()
+        # G-buffer cases weight the image dimensions differently so that no channel's adjoint can hide behind another's
+        w = torch.linspace(0.5, 1.5, img.shape[-1], device=img.device) if chans is not None else 1.0
+        (img * w).pow(2).sum().backward()
         grads = collect_grads(sc)
     return img.detach().cpu(), grads
 

@@ -86,13 +86,17 @@ def test_band_size_does_not_change_gradients(rb, dev, monkeypatch):
         assert pu.rel_l2(g_many[k].numpy(), g_one[k].numpy()) < 1e-5, k
 
 
-def test_backward_rejects_gbuffer_channels(rb, dev):
-    """The adjoint pass is implemented for channels == [radiance]; anything else must fail loudly, not silently differ."""
-    sc = scenes.SCENES["single_triangle"](dev, resolution=(16, 16))
-    args = api.RenderFunction.serialize_scene(sc, 2, 1, channels=[rb.channels.radiance, rb.channels.depth], device=dev, backend=rb)
+def test_gbuffer_backward_without_radiance_skips_path_tracing(rb, dev):
+    """Deferred set-up (no radiance channel): gradients flow through the first hit and the primary edges only; the
+    boundary (secondary-edge) stage and the bounce replay must not run, whatever max_bounces says."""
+    sc = scenes.SCENES["single_triangle"](dev, resolution=(24, 24))
+    args = api.RenderFunction.serialize_scene(sc, 4, 2, channels=[rb.channels.depth, rb.channels.position], device=dev, backend=rb,
+                                              use_secondary_edge_sampling=True)
     img = api.RenderFunction.apply(3, *args)
-    with pytest.raises(RuntimeError):
-        img.sum().backward()
+    img.sum().backward()
+    g = pu.collect_grads(sc)
+    assert float(g["shape0.vertices"].abs().sum()) > 0 and all(torch.isfinite(v).all() for v in g.values())
+    assert float(g["light0.intensity"].abs().sum()) == 0.0
 
 
 @pytest.mark.parametrize("name", list(pu.STAT_CASES))

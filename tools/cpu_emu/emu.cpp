@@ -225,6 +225,7 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
     for (int i = 0; i < opt->num_channels; i++) rp.channels[i] = opt->channels[i];
     rp.max_generic = scene->max_generic;
     bool only_radiance = opt->num_channels == 1 && opt->channels[0] == RB_CH_RADIANCE;
+    rp.only_radiance = only_radiance ? 1 : 0;
     if (image && !only_radiance) {
         for (int y = 0; y < rp.vp_h; y++)
             for (int x = 0; x < rp.vp_w; x++) {
