@@ -97,7 +97,8 @@ typedef struct rb_area_light {
     int two_sided, directly_visible;
 } rb_area_light;
 
-/* EnvironmentMap -- src/envmap.h (second wave; rb_scene_create rejects scenes with an envmap for now). */
+/* EnvironmentMap -- src/envmap.h:19-51, constructor src/redner.cpp:169-178.  `values` is the [h, w, 3] mip pyramid, the two
+ * tables are the caller's importance-sampling CDFs (pyredner/envmap.py:36-61); all device memory, matrices row-major. */
 typedef struct rb_envmap {
     rb_texture values;
     float env_to_world[16], world_to_env[16];
@@ -147,6 +148,12 @@ typedef struct rb_dcamera {
     float* distortion;                /* 8 floats or NULL */
 } rb_dcamera;
 
+/* DEnvironmentMap -- src/envmap.h:53-61: gradient mip pyramid and the 16 floats of d(world_to_env) (device memory) */
+typedef struct rb_denvmap {
+    rb_texture values;
+    float* world_to_env;
+} rb_denvmap;
+
 /* DScene -- src/scene.h DScene / src/redner.cpp:75-82 */
 typedef struct rb_dscene_desc {
     rb_dcamera camera;
@@ -156,6 +163,7 @@ typedef struct rb_dscene_desc {
     const rb_material* materials; /* host array; texel pointers are gradient buffers */
     int num_lights;
     float* const* light_intensity; /* host array of device pointers (3 floats each) -- src/area_light.h:38-43 */
+    const rb_denvmap* envmap;      /* host pointer or NULL */
 } rb_dscene_desc;
 
 typedef struct rb_scene rb_scene;

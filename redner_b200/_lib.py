@@ -94,12 +94,17 @@ class rb_dcamera(C.Structure):
     ]
 
 
+class rb_denvmap(C.Structure):
+    _fields_ = [("values", rb_texture), ("world_to_env", C.c_void_p)]
+
+
 class rb_dscene_desc(C.Structure):
     _fields_ = [
         ("camera", rb_dcamera),
         ("num_shapes", C.c_int), ("shapes", C.POINTER(rb_dshape)),
         ("num_materials", C.c_int), ("materials", C.POINTER(rb_material)),
         ("num_lights", C.c_int), ("light_intensity", C.POINTER(C.c_void_p)),
+        ("envmap", C.POINTER(rb_denvmap)),
     ]
 
 

@@ -160,6 +160,27 @@ class AreaLight:
         self.shape_id, self.intensity, self.two_sided, self.directly_visible = shape_id, intensity, two_sided, directly_visible
 
 
+class EnvironmentMap:
+    """pyredner.EnvironmentMap (pyredner/envmap.py:6-86): latitude-longitude radiance image infinitely far away, with the
+    luminance x sin(theta) sampling tables the renderer importance-samples (generate_envmap_pdf, :36-61)."""
+
+    def __init__(self, values, env_to_world: Optional[torch.Tensor] = None, directly_visible: bool = True):
+        self.values = values if isinstance(values, Texture) else Texture(values)
+        self.env_to_world = env_to_world if env_to_world is not None else torch.eye(4, 4)
+        assert self.env_to_world.dtype == torch.float32
+        self.world_to_env = torch.inverse(self.env_to_world).contiguous()
+        self.directly_visible = directly_visible
+        t = self.values.texels.detach()
+        assert t.dim() == 3 and t.shape[2] == 3, "the environment map must be an image [height, width, 3]"
+        lum = 0.212671 * t[:, :, 0] + 0.715160 * t[:, :, 1] + 0.072169 * t[:, :, 2]
+        cdf_xs_ = torch.cumsum(lum, dim=1)
+        y_weight = torch.sin(math.pi * (torch.arange(lum.shape[0], dtype=torch.float32, device=lum.device) + 0.5) / float(lum.shape[0]))
+        cdf_ys_ = torch.cumsum(cdf_xs_[:, -1] * y_weight, dim=0)
+        self.pdf_norm = (lum.shape[0] * lum.shape[1]) / (cdf_ys_[-1].item() * (2 * math.pi * math.pi))
+        self.sample_cdf_xs = ((cdf_xs_ - cdf_xs_[:, 0:1]) / torch.clamp(cdf_xs_[:, -1:], min=1e-8)).contiguous()
+        self.sample_cdf_ys = ((cdf_ys_ - cdf_ys_[0]) / torch.clamp(cdf_ys_[-1], min=1e-8)).contiguous()
+
+
 class Scene:
     def __init__(self, camera: Camera, shapes: List[Shape], materials: List[Material], area_lights: List[AreaLight], envmap=None):
         self.camera, self.shapes, self.materials, self.area_lights, self.envmap = camera, shapes, materials, area_lights, envmap
@@ -243,9 +264,15 @@ class RenderFunction(torch.autograd.Function):
             args += [m.compute_specular_lighting, m.two_sided, m.use_vertex_color]
         for light in scene.area_lights:
             args += [light.shape_id, light.intensity.cpu(), light.two_sided, light.directly_visible]
-        if scene.envmap is not None:
-            raise NotImplementedError("environment maps: second wave (SURVEY.md section 2 row 13)")
-        args.append(None)
+        if scene.envmap is not None:  # pyredner/render_pytorch.py:240-253
+            e = scene.envmap
+            for t in (e.env_to_world, e.world_to_env, e.sample_cdf_ys, e.sample_cdf_xs):
+                assert torch.isfinite(t).all()
+            _serialize_texture(e.values, args, device)
+            args += [e.env_to_world.cpu().contiguous(), e.world_to_env.cpu().contiguous(), e.sample_cdf_ys.to(device), e.sample_cdf_xs.to(device),
+                     e.pdf_norm, e.directly_visible]
+        else:
+            args.append(None)
         args += [num_samples, max_bounces, channels, sampler_type]
         args += [use_primary_edge_sampling and vis, use_secondary_edge_sampling and vis]
         args += [sample_pixel_center, device, backend]
@@ -274,8 +301,11 @@ class RenderFunction(torch.autograd.Function):
             mat_args.append((texs, nxt(), nxt(), nxt()))
         for _ in range(num_lights):
             light_args.append([nxt() for _ in range(4)])
-        envmap = nxt()
-        assert envmap is None
+        env_args = None
+        n_env = nxt()
+        if n_env is not None:
+            env_mips = [nxt() for _ in range(n_env)]
+            env_args = (env_mips, nxt(), nxt(), nxt(), nxt(), nxt(), nxt(), nxt())  # uv_scale, e2w, w2e, cdf_ys, cdf_xs, pdf_norm, visible
         num_samples, max_bounces, channels, sampler_type = nxt(), nxt(), nxt(), nxt()
         use_prim, use_sec, pixel_center, device, backend = nxt(), nxt(), nxt(), nxt(), nxt()
         rb = backend
@@ -305,7 +335,13 @@ class RenderFunction(torch.autograd.Function):
         lights = [rb.AreaLight(sid, fp(inten), ts, dv) for sid, inten, ts, dv in light_args]
         use_gpu = device.type == "cuda"
         gpu_index = device.index if device.index is not None else -1
-        c.scene = rb.Scene(camera, shapes, materials, lights, None, use_gpu, gpu_index, use_prim, use_sec)
+        envmap = None
+        if env_args is not None:
+            mips, uv_scale, e2w, w2e, cdf_ys, cdf_xs, pdf_norm, visible = env_args
+            env_tex = rb.Texture3([fp(m) for m in mips], [int(m.shape[1]) for m in mips], [int(m.shape[0]) for m in mips], 3, fp(uv_scale))
+            envmap = rb.EnvironmentMap(env_tex, fp(e2w), fp(w2e), fp(cdf_ys), fp(cdf_xs), pdf_norm, visible)
+        c.env_args, c.envmap = env_args, envmap
+        c.scene = rb.Scene(camera, shapes, materials, lights, envmap, use_gpu, gpu_index, use_prim, use_sec)
         ns = num_samples if isinstance(num_samples, (tuple, list)) else (num_samples, num_samples)
         channels = [rb.channels(int(ch)) for ch in channels]
         c.options = rb.RenderOptions(seed[0], ns[0], max_bounces, channels, rb.SamplerType(int(sampler_type)), pixel_center)
@@ -371,7 +407,13 @@ class RenderFunction(torch.autograd.Function):
             d_materials.append(rb.DMaterial(*[m[1] for m in made]))
         d_intensities = [z(3) for _ in c.light_args]
         d_lights = [rb.DAreaLight(fp(t)) for t in d_intensities]
-        d_scene = rb.DScene(d_camera, d_shapes, d_materials, d_lights, None, dev.type == "cuda", dev.index if dev.index is not None else -1)
+        d_envmap, d_env_bufs = None, None
+        if c.env_args is not None:  # pyredner/render_pytorch.py:948-968
+            mips = c.env_args[0]
+            d_env_bufs = ([torch.zeros_like(m) for m in mips], torch.zeros(2, device=dev), torch.zeros(4, 4, device=dev))
+            d_env_tex = rb.Texture3([fp(m) for m in d_env_bufs[0]], [int(m.shape[1]) for m in mips], [int(m.shape[0]) for m in mips], 3, fp(d_env_bufs[1]))
+            d_envmap = rb.DEnvironmentMap(d_env_tex, fp(d_env_bufs[2]))
+        d_scene = rb.DScene(d_camera, d_shapes, d_materials, d_lights, d_envmap, dev.type == "cuda", dev.index if dev.index is not None else -1)
         c.options.seed = c.seed[1]
         c.options.num_samples = c.num_samples[1]
         rb.render(c.scene, c.options, rb.float_ptr(0), fp(grad_img), d_scene, rb.float_ptr(0), rb.float_ptr(0))
@@ -392,7 +434,12 @@ class RenderFunction(torch.autograd.Function):
             out += [None, None, None]
         for d_i in d_intensities:
             out += [None, d_i.cpu(), None, None]
-        out.append(None)  # envmap
+        if d_env_bufs is not None:  # pyredner/render_pytorch.py:1154-1164
+            out.append(None)  # number of levels
+            out += list(d_env_bufs[0])
+            out += [d_env_bufs[1], None, d_env_bufs[2].cpu(), None, None, None, None]  # uv_scale, env_to_world, world_to_env, cdfs, pdf_norm, visible
+        else:
+            out.append(None)  # envmap
         out += [None] * 9  # num_samples .. backend
         return tuple(out)
 

@@ -444,6 +444,11 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
     }
     rp.only_radiance = only_radiance ? 1 : 0;
     rp.nd = rb_compute_num_channels(opt->channels, opt->num_channels, rp.max_generic);
+    rp.rad_off = -1;
+    for (int i = 0, off = 0; i < opt->num_channels; i++) {
+        if (opt->channels[i] == RB_CH_RADIANCE) rp.rad_off = off;
+        off += rb_channel_width(opt->channels[i], rp.max_generic);
+    }
     if (rp.nd > RB_MAX_ND) {
         rb_set_error("rb_render: more than 64 image dimensions requested");
         return 1;
@@ -569,6 +574,16 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         ka.ds.materials = d_mats;
         ka.ds.light_intensity = d_lights;
         ka.ds.cam_accum = cam_accum;
+        memset(&ka.ds.env_values, 0, sizeof(rb_texture));
+        ka.ds.env_w2e = nullptr;
+        if (d_scene->envmap != nullptr) {
+            ka.ds.env_values = d_scene->envmap->values;
+            ka.ds.env_w2e = d_scene->envmap->world_to_env;
+        } else if (scene->dev.has_envmap) {
+            rb_set_error("rb_render: the scene has an environment map but d_scene has no envmap gradient buffers");
+            cleanup();
+            return 1;
+        }
 
         // ---- interior + first-hit adjoints, band by band: trace -> scan/compact -> boundary terms -> sweep
         ka.records = (VertexRec*)(scratch + o_rec);

@@ -10,6 +10,7 @@
 #pragma once
 #include "rb_bvh.cuh"
 #include "rb_camera.cuh"
+#include "rb_envmap.cuh"
 #include "rb_material.cuh"
 #include "rb_sampler.cuh"
 #include "rb_shape.cuh"
@@ -25,10 +26,23 @@ RB_D int cdf_pick(const double* cdf, int n, double x) {
 }
 
 struct LightSampleRec {
-    Isect isect;      // (light shape, triangle)
-    V2 uv;            // the 2-D sample used on the triangle
+    Isect isect;      // (light shape, triangle); environment map: shape_id = -1 and tri_id = bits of dir.z
+    V2 uv;            // the 2-D sample used on the triangle; environment map: (dir.x, dir.y) of the sampled direction
     bool unoccluded;  // shadow ray reached the light (nee_ray.tmax >= 0)
 };
+// The environment-map sample keeps its world direction in the record (the adjoint pass needs exactly the direction the
+// primal pass used; re-sampling from rounded random numbers would not give it).
+RB_HD void light_rec_set_env_dir(LightSampleRec& r, V3 dir) {
+    r.isect.shape_id = -1;
+    float z = (float)dir.z;
+    memcpy(&r.isect.tri_id, &z, sizeof(int));
+    r.uv = mk2(dir.x, dir.y);
+}
+RB_HD V3 light_rec_env_dir(const LightSampleRec& r) {
+    float z;
+    memcpy(&z, &r.isect.tri_id, sizeof(float));
+    return mk3(r.uv.x, r.uv.y, (Real)z);
+}
 
 RB_D bool closest_hit(const DevScene& sc, const Ray& ray, Isect& is) {
     float t;
@@ -63,6 +77,19 @@ RB_D D3 hit_point_d(const rb_shape& s, int tri, D3 o, D3 d) {
 // point `p_d`, then rounded once -- src/scene.cpp:692-741).
 RB_D void sample_light(const DevScene& sc, D3 p_d, double light_sel, double tri_sel, double su, double sv, LightSampleRec& rec, SurfacePoint& lp) {
     int light_id = cdf_pick(sc.light_cdf, sc.num_lights, light_sel);
+    if (sc.has_envmap && light_id == sc.num_lights - 1) {
+        // environment map: direction by importance sampling, shadow ray to infinity (src/scene.cpp:703-711)
+        V3 dir = envmap_sample(sc.env, su, sv);
+        light_rec_set_env_dir(rec, dir);
+        lp = zero_point();
+        Ray sh;
+        sh.org = mk3((Real)p_d.x, (Real)p_d.y, (Real)p_d.z);
+        sh.dir = dir;
+        sh.tmin = Real(1e-3);
+        sh.tmax = INFINITY;
+        rec.unoccluded = !any_hit(sc, sh);
+        return;
+    }
     const DevLight& light = sc.lights[light_id];
     const rb_shape& shape = sc.shapes[light.shape_id];
     const double* acdf = sc.area_cdf_pool + sc.area_cdf_offset[light_id];
@@ -100,6 +127,12 @@ RB_D V3 hit_emission(const DevScene& sc, const Isect& is, const SurfacePoint& sp
     return zero3();
 }
 
+// Radiance of the environment map seen along a ray that left the scene (src/primary_contribution.cpp:25-29).
+RB_D V3 miss_emission(const DevScene& sc, V3 dir, const RayDiff& rd) {
+    if (!sc.has_envmap || !sc.env.directly_visible) return zero3();
+    return envmap_eval(sc.env, dir, rd);
+}
+
 RB_D Real mis_power2(Real p_other, Real p_this) {
     double r = (double)p_other / (double)p_this;
     return (Real)(1.0 / (1.0 + r * r));
@@ -108,9 +141,21 @@ RB_D Real mis_power2(Real p_other, Real p_this) {
 // Radiance estimate at one vertex: returns nee + scatter (not yet multiplied by the throughput) and the
 // throughput factor for the next vertex.
 RB_D V3 vertex_estimate(const DevScene& sc, const rb_material& mat, const SurfacePoint& sp, V3 wi, Real min_rough, const LightSampleRec& ls,
-                        const SurfacePoint& lp, const Isect& bis, const SurfacePoint& bp, V3& scatter_factor, bool& scatter_ok) {
+                        const SurfacePoint& lp, const Isect& bis, const SurfacePoint& bp, V3 bdir, V3& scatter_factor, bool& scatter_ok) {
     V3 nee = zero3();
-    if (ls.unoccluded) {
+    if (ls.unoccluded && !ls.isect.valid()) {
+        // environment light (src/path_contribution.cpp:51-67); the lookup is unfiltered (zero ray differential)
+        if (sc.has_envmap) {
+            V3 wo = light_rec_env_dir(ls);
+            Real pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
+            if (pdf_nee > 0) {
+                V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+                V3 Le = envmap_eval(sc.env, wo, zero_raydiff());
+                Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
+                nee = (mis_power2(pdf_b, pdf_nee) / pdf_nee) * f * Le;
+            }
+        }
+    } else if (ls.unoccluded) {
         const rb_shape& lshape = sc.shapes[ls.isect.shape_id];
         V3 dir = lp.position - sp.position;
         Real dist_sq = length_sq(dir);
@@ -149,6 +194,15 @@ RB_D V3 vertex_estimate(const DevScene& sc, const rb_material& mat, const Surfac
             }
             scatter_factor = f / pdf_b;
             scatter_ok = true;
+        }
+    } else if (sc.has_envmap) {
+        // the BSDF ray left the scene (src/path_contribution.cpp:99-118); bdir is zero when the BSDF sample failed
+        Real pdf_b = bsdf_pdf(mat, sp, wi, bdir, min_rough);
+        if (length_sq(bdir) > 0 && pdf_b > Real(1e-20)) {
+            V3 f = bsdf_eval(mat, sp, wi, bdir, min_rough);
+            V3 Le = envmap_eval(sc.env, bdir, zero_raydiff());
+            Real pdf_nee = envmap_pdf(sc.env, bdir) * (Real)sc.light_pmf[sc.num_lights - 1];
+            scatter = (mis_power2(pdf_nee, pdf_b) / pdf_b) * f * Le;
         }
     }
     return nee + scatter;
@@ -214,7 +268,7 @@ RB_D V3 trace_bounces(const DevScene& sc, Sampler& smp, Ray ray, RayDiff rd_in, 
             if (closest_hit(sc, nray, bis)) bp = make_surface_point(sc.shapes[bis.shape_id], bis.tri_id, nray, rd_b, rd_after);
             V3 factor;
             bool ok;
-            V3 est = vertex_estimate(sc, mat, sp, wi, min_rough, ls, lp, bis, bp, factor, ok);
+            V3 est = vertex_estimate(sc, mat, sp, wi, min_rough, ls, lp, bis, bp, dir, factor, ok);
             L += thr * est;
             count++;
             thr = ok ? thr * factor : zero3();
@@ -283,13 +337,32 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
     // The two estimators of this vertex (light sample, BSDF sample) share ONE rolled call of d_bsdf_eval: each prepares
     // (wo, d_f, d_wo) in a "pre" block and consumes the returned d_wo in a "post" block.  Besides halving the code of
     // the largest adjoint this reconverges the lanes of a warp that took only one of the two branches.
-    bool on_l = false, on_b = false;
+    bool on_l = false, on_b = false, env_l = false, env_b = false;
     V3 wo_l = zero3(), d_f_l = zero3(), d_wo_l = zero3(), dir_l = zero3();
     V3 wo_b = zero3(), d_f_b = zero3(), d_wo_b = zero3(), dir_b = zero3();
     Real dist_sq_l = 1, d_dist_sq_l = 0, dist_sq_b = 1, d_cos_l = 0;
     V3 d_lv[3] = {zero3(), zero3(), zero3()};
     // ---- next event estimation (pre)
-    if (cur.light.unoccluded) {
+    if (cur.light.unoccluded && !cur.light.isect.valid()) {
+        // environment light (src/path_contribution.cpp:295-337): no dependence of the direction on the vertex position
+        if (sc.has_envmap) {
+            V3 wo = light_rec_env_dir(cur.light);
+            Real pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
+            if (pdf_nee > 0) {
+                V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+                V3 Le = envmap_eval(sc.env, wo, zero_raydiff());
+                Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
+                Real wgt = mis_power2(pdf_b, pdf_nee) / pdf_nee;
+                V3 d_nee = d_contrib * thr;
+                out.d_thr += d_contrib * (wgt * f * Le);
+                RayDiff d_rd0 = zero_raydiff();
+                d_envmap_eval(sc.env, wo, zero_raydiff(), wgt * (d_nee * f), ds.env_values, ds.env_w2e, d_wo_l, d_rd0);
+                on_l = env_l = true;
+                wo_l = wo;
+                d_f_l = wgt * (d_nee * Le);
+            }
+        }
+    } else if (cur.light.unoccluded) {
         const Isect& lis = cur.light.isect;
         const rb_shape& lshape = sc.shapes[lis.shape_id];
         SurfacePoint lp = sample_light_triangle(lshape, lis.tri_id, cur.light.uv);
@@ -369,6 +442,23 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
             d_f_b = d_f;
             d_wo_b = next.d_ray.dir;
         }
+    } else if (nxt != nullptr && sc.has_envmap) {
+        // the BSDF ray left the scene (src/path_contribution.cpp:520-590); nothing flows back into the sampling procedure
+        V3 wo = nxt->ray.dir;
+        Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
+        if (length_sq(wo) > 0 && pdf_b > 0) {
+            V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+            V3 Le = envmap_eval(sc.env, wo, zero_raydiff());
+            Real pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
+            Real wgt = mis_power2(pdf_nee, pdf_b) / pdf_b;
+            V3 d_scatter = d_contrib * thr;
+            out.d_thr += d_contrib * (wgt * f * Le);
+            RayDiff d_rd0 = zero_raydiff();
+            d_envmap_eval(sc.env, wo, zero_raydiff(), wgt * (d_scatter * f), ds.env_values, ds.env_w2e, d_wo_b, d_rd0);
+            on_b = env_b = true;
+            wo_b = wo;
+            d_f_b = wgt * (d_scatter * Le);
+        }
     }
     // ---- shared BSDF adjoint
 #pragma unroll 1
@@ -381,7 +471,7 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
         if (k) d_wo_b = d_wo; else d_wo_l = d_wo;
     }
     // ---- next event estimation (post)
-    if (on_l) {
+    if (on_l && !env_l) {
         const Isect& lis = cur.light.isect;
         const rb_shape& lshape = sc.shapes[lis.shape_id];
         V3 d_dir = d_wo_l / sqrt(dist_sq_l);
@@ -403,7 +493,7 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
         }
     }
     // ---- BSDF-sampled continuation (post)
-    if (on_b) {
+    if (on_b && !env_b) {
         const Isect& bis = nxt->isect;
         const rb_shape& bshape = sc.shapes[bis.shape_id];
         V3 d_bvp[3] = {zero3(), zero3(), zero3()}, d_bvn[3] = {zero3(), zero3(), zero3()}, d_bvc[3] = {zero3(), zero3(), zero3()};

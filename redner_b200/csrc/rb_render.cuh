@@ -106,6 +106,8 @@ RB_D V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, in
         SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
         acc += weight * hit_emission(sc, is, sp, -ray.dir);
         acc += weight * trace_bounces<false>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.max_bounces, nullptr, 0, nullptr, &od, &dd);
+    } else {
+        acc += weight * miss_emission(sc, ray.dir, rd);
     }
     return acc;
 }
@@ -220,7 +222,13 @@ RB_D bool forward_sample_channels(const DevScene& sc, const RenderParams& rp, in
     D3 od, dd;
     primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
     Isect is = no_isect();
-    if (!closest_hit(sc, ray, is)) return false;
+    if (!closest_hit(sc, ray, is)) {
+        if (rp.rad_off >= 0) {
+            V3 L = weight * miss_emission(sc, ray.dir, rd);
+            out[rp.rad_off] += (float)L.x; out[rp.rad_off + 1] += (float)L.y; out[rp.rad_off + 2] += (float)L.z;
+        }
+        return false;
+    }
     RayDiff rd_after;
     const rb_shape& shape = sc.shapes[is.shape_id];
     SurfacePoint sp = make_surface_point(shape, is.tri_id, ray, rd, rd_after);
@@ -274,9 +282,22 @@ RB_D int bwd_trace(const DevScene& sc, const RenderParams& rp, int pixel, int px
         smp.init(rp.sampler_type, rp.seed, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
         primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
         act = closest_hit(sc, ray, is);
+        if (!act) is.shape_id = -2; // "traced and missed" (as opposed to an idle lane)
     }
     RB_PHASE_SYNC();
-    if (!act) return -1;
+    if (!act) {
+        // a primary ray that leaves the scene still has an adjoint when it sees the environment map
+        if (is.shape_id == -2 && sc.has_envmap && sc.env.directly_visible && rp.rad_off >= 0) {
+            VertexRec& r = recs[0];
+            r.ray = ray;
+            r.rd_in = rd;
+            r.isect = no_isect();
+            r.thr = mk3(1, 1, 1);
+            r.min_rough = 0;
+            return 0;
+        }
+        return -1;
+    }
     int nrec = 0;
     // (without a radiance channel only the first hit matters: the terminal record alone)
     trace_bounces<true>(sc, smp, ray, rd, is, mk3(1, 1, 1), Real(0), 0, rp.rad_dim >= 0 ? rp.max_bounces : 0, recs, stride, &nrec, &od, &dd);
@@ -317,6 +338,9 @@ RB_D void bwd_sweep(const DevScene& sc, const KernelArgs& ka, int pixel, int px,
     const float* dpx_all = ka.d_image + (size_t)rp.nd * pixel;
     const float* dpx = dpx_all + (rp.rad_dim >= 0 ? rp.rad_dim : 0);
     V3 d_contrib = (act && rp.rad_dim >= 0) ? weight * mk3(dpx[0], dpx[1], dpx[2]) : zero3();
+    // first-hit emission sits at the channel's true offset (differs from rad_dim only when radiance is not the first channel)
+    const float* dpe = dpx_all + (rp.rad_off >= 0 ? rp.rad_off : 0);
+    V3 d_emission = (act && rp.rad_off >= 0) ? weight * mk3(dpe[0], dpe[1], dpe[2]) : zero3();
     VertexAdjoint adj = zero_vertex_adjoint();
     for (int d = rp.max_bounces - 1; d >= 0; d--) { // block-uniform trip count (phase barrier inside)
         RB_PHASE_SYNC();
@@ -332,30 +356,35 @@ RB_D void bwd_sweep(const DevScene& sc, const KernelArgs& ka, int pixel, int px,
     const Ray ray = recs[0].ray;
     const RayDiff rd = recs[0].rd_in;
     const Isect is = recs[0].isect;
-    // first vertex: emission adjoint (src/primary_contribution.cpp:449-466) ...
-    RayDiff rd_after;
-    SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
-    {
-        const rb_shape& shape = sc.shapes[is.shape_id];
-        V3 wi = -ray.dir;
-        if (shape.light_id >= 0 && dot(wi, sp.shading_frame.n) > 0) {
-            const DevLight& light = sc.lights[shape.light_id];
-            if (light.directly_visible) agg_add3(ds.light_intensity[shape.light_id], d_contrib);
-        }
-    }
     DRay d_ray = adj.d_ray;
-    // G-buffer channels of the first hit (src/primary_contribution.cpp:486-692)
-    if (!rp.only_radiance) {
-        Real d_vals[RB_MAX_ND];
-        for (int i = 0; i < rp.nd; i++) d_vals[i] = weight * dpx_all[i];
-        d_channel_values_at_hit(sc, ds, rp, is, sp, ray, d_vals, adj.d_point, d_ray.org);
-    }
-    // ... and the hit itself back to the mesh and the camera (src/primary_intersection.cpp:5-130)
-    V3 d_vp[3] = {zero3(), zero3(), zero3()}, d_vn[3] = {zero3(), zero3(), zero3()}, d_vc[3] = {zero3(), zero3(), zero3()};
-    V2 d_vuv[3] = {zero2(), zero2(), zero2()};
     RayDiff d_prd = zero_raydiff();
-    d_make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, adj.d_point, zero_raydiff(), d_ray, d_prd, d_vp, d_vn, d_vuv, d_vc);
-    scatter_vertex_grads(sc, ds, is, d_vp, d_vn, d_vuv, d_vc);
+    if (is.valid()) {
+        // first vertex: emission adjoint (src/primary_contribution.cpp:449-466) ...
+        RayDiff rd_after;
+        SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
+        {
+            const rb_shape& shape = sc.shapes[is.shape_id];
+            V3 wi = -ray.dir;
+            if (shape.light_id >= 0 && dot(wi, sp.shading_frame.n) > 0) {
+                const DevLight& light = sc.lights[shape.light_id];
+                if (light.directly_visible) agg_add3(ds.light_intensity[shape.light_id], d_emission);
+            }
+        }
+        // G-buffer channels of the first hit (src/primary_contribution.cpp:486-692)
+        if (!rp.only_radiance) {
+            Real d_vals[RB_MAX_ND];
+            for (int i = 0; i < rp.nd; i++) d_vals[i] = weight * dpx_all[i];
+            d_channel_values_at_hit(sc, ds, rp, is, sp, ray, d_vals, adj.d_point, d_ray.org);
+        }
+        // ... and the hit itself back to the mesh and the camera (src/primary_intersection.cpp:5-130)
+        V3 d_vp[3] = {zero3(), zero3(), zero3()}, d_vn[3] = {zero3(), zero3(), zero3()}, d_vc[3] = {zero3(), zero3(), zero3()};
+        V2 d_vuv[3] = {zero2(), zero2(), zero2()};
+        d_make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, adj.d_point, zero_raydiff(), d_ray, d_prd, d_vp, d_vn, d_vuv, d_vc);
+        scatter_vertex_grads(sc, ds, is, d_vp, d_vn, d_vuv, d_vc);
+    } else {
+        // the primary ray left the scene: environment map seen directly (src/primary_contribution.cpp:469-483)
+        d_envmap_eval(sc.env, ray.dir, rd, d_emission, ds.env_values, ds.env_w2e, d_ray.dir, d_prd);
+    }
     const Real delta = Real(1e-3);
     Real psx = Real(0.5) / sc.cam.width, psy = Real(0.5) / sc.cam.height;
     DRay d_ray_dx, d_ray_dy;

@@ -289,20 +289,21 @@ static std::vector<HostMesh>& host_meshes(rb_scene* sc) {
 
 int rb_build_lights(rb_scene* sc, cudaStream_t stream) {
     int L = (int)sc->lights.size();
-    sc->dev.num_lights = L;
+    const bool env = sc->dev.has_envmap != 0;
+    sc->dev.num_lights = L + (env ? 1 : 0);
     sc->dev.lights = nullptr;
-    if (L == 0) return 0;
+    if (sc->dev.num_lights == 0) return 0;
     HostLightTables t;
     std::string err;
-    if (!host_build_lights(sc->lights, host_meshes(sc), t, err)) {
+    if (!host_build_lights(sc->lights, host_meshes(sc), t, err, env, env ? sc->dev.env.pdf_norm : 0.0, env ? host_bsphere_radius(host_meshes(sc)) : 0.0)) {
         rb_set_error(err);
         return 1;
     }
     DevLight* d_lights;
     double *d_pmf, *d_cdf, *d_areas, *d_pool;
     int* d_off;
-    if (dev_upload(sc, &d_lights, sc->lights.data(), L, stream) || dev_upload(sc, &d_pmf, t.pmf.data(), L, stream) ||
-        dev_upload(sc, &d_cdf, t.cdf.data(), L, stream) || dev_upload(sc, &d_areas, t.areas.data(), L, stream) ||
+    if (dev_upload(sc, &d_lights, sc->lights.data(), L, stream) || dev_upload(sc, &d_pmf, t.pmf.data(), t.pmf.size(), stream) ||
+        dev_upload(sc, &d_cdf, t.cdf.data(), t.cdf.size(), stream) || dev_upload(sc, &d_areas, t.areas.data(), L, stream) ||
         dev_upload(sc, &d_pool, t.pool.data(), t.pool.size(), stream) || dev_upload(sc, &d_off, t.offsets.data(), L, stream))
         return 1;
     RB_CUDA_OK(cudaStreamSynchronize(stream)); // host vectors go out of scope
@@ -384,8 +385,14 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
         rb_set_error("rb_scene_create: use_gpu == 0 requested, but redner_b200 has no CPU path (CUDA sm_100a only)");
         return 1;
     }
-    if (desc->envmap != nullptr) {
-        rb_set_error("rb_scene_create: environment maps are not implemented yet (SURVEY.md section 2 row 13, second wave)");
+    if (desc->envmap != nullptr && (desc->use_primary_edge_sampling || desc->use_secondary_edge_sampling)) {
+        rb_set_error("rb_scene_create: environment maps are implemented for the interior (non-edge) terms only; edge sampling with an "
+                     "environment map is not implemented yet");
+        return 1;
+    }
+    if (desc->envmap != nullptr && (desc->envmap->values.num_levels <= 0 || desc->envmap->values.width[0] <= 0 || desc->envmap->sample_cdf_ys == nullptr ||
+                                    desc->envmap->sample_cdf_xs == nullptr)) {
+        rb_set_error("rb_scene_create: the environment map needs an image texture ([h, w, 3] mip pyramid) and its two sampling tables");
         return 1;
     }
     const rb_camera& c = desc->camera;
@@ -476,13 +483,24 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
     bool need_edges = sc->dev.use_primary_edge || sc->dev.use_secondary_edge;
     auto& meshes = host_meshes(sc);
     meshes.assign(sc->shapes.size(), HostMesh());
-    std::vector<char> need(sc->shapes.size(), need_edges ? 1 : 0);
+    std::vector<char> need(sc->shapes.size(), (need_edges || desc->envmap != nullptr) ? 1 : 0); // (envmap: bounding sphere of everything)
     for (const DevLight& l : sc->lights) need[l.shape_id] = 1;
     for (size_t s = 0; s < sc->shapes.size(); s++)
         if (need[s] && fetch_mesh(sc->shapes[s], meshes[s], stream)) return fail();
     if (cudaStreamSynchronize(stream) != cudaSuccess) {
         rb_set_error("rb_scene_create: device-to-host geometry copy failed (are the shape buffers device pointers?)");
         return fail();
+    }
+    sc->dev.has_envmap = desc->envmap != nullptr;
+    if (sc->dev.has_envmap) {
+        const rb_envmap& e = *desc->envmap;
+        sc->dev.env.values = e.values;
+        memcpy(sc->dev.env.w2e, e.world_to_env, sizeof(sc->dev.env.w2e));
+        memcpy(sc->dev.env.e2w, e.env_to_world, sizeof(sc->dev.env.e2w));
+        sc->dev.env.cdf_ys = e.sample_cdf_ys;
+        sc->dev.env.cdf_xs = e.sample_cdf_xs;
+        sc->dev.env.pdf_norm = e.pdf_norm;
+        sc->dev.env.directly_visible = e.directly_visible;
     }
     if (rb_build_lights(sc, stream)) return fail();
     auto t2 = std::chrono::high_resolution_clock::now();

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -24,7 +25,32 @@ struct HostEdgeTables {
     std::vector<double> prim_pmf, prim_cdf;
 };
 
-inline bool host_build_lights(const std::vector<DevLight>& lights, const std::vector<HostMesh>& meshes, HostLightTables& out, std::string& err) {
+// Radius of the scene's bounding sphere as the reference computes it (src/scene.cpp:156-195) -- including its slip of
+// folding each shape's Y extent into the Z bounds; the radius only scales the environment map's selection weight.
+inline double host_bsphere_radius(const std::vector<HostMesh>& meshes) {
+    if (meshes.empty()) return 0;
+    float inf = std::numeric_limits<float>::infinity();
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (const HostMesh& m : meshes) {
+        float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+        for (size_t v = 0; v + 2 < m.vertices.size(); v += 3)
+            for (int a = 0; a < 3; a++) {
+                mn[a] = std::min(mn[a], m.vertices[v + a]);
+                mx[a] = std::max(mx[a], m.vertices[v + a]);
+            }
+        lo[0] = std::min(mn[0], lo[0]);
+        lo[1] = std::min(mn[1], lo[1]);
+        lo[2] = std::min(mn[1], lo[2]);
+        hi[0] = std::max(mx[0], hi[0]);
+        hi[1] = std::max(mx[1], hi[1]);
+        hi[2] = std::max(mx[1], hi[2]);
+    }
+    float d[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+    return 0.5f * std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+}
+// `env_pdf_norm` > 0 appends the environment map as the last light (src/scene.cpp:197-253).
+inline bool host_build_lights(const std::vector<DevLight>& lights, const std::vector<HostMesh>& meshes, HostLightTables& out, std::string& err,
+                              bool has_env = false, double env_pdf_norm = 0, double bsphere_radius = 0) {
     int L = (int)lights.size();
     out.pmf.assign(L, 0);
     out.cdf.assign(L, 0);
@@ -59,6 +85,13 @@ inline bool host_build_lights(const std::vector<DevLight>& lights, const std::ve
         double lum = 0.212671f * (double)light.intensity[0] + 0.715160f * (double)light.intensity[1] + 0.072169f * (double)light.intensity[2];
         out.pmf[l] = sum_area * lum * double(M_PI);
         total += out.pmf[l];
+    }
+    if (has_env) {
+        double area = 4 * double(M_PI) * bsphere_radius * bsphere_radius;
+        out.pmf.push_back(area > 0 ? area / env_pdf_norm : 1.0);
+        out.cdf.push_back(0);
+        total += out.pmf.back();
+        L++;
     }
     if (!(total > 0)) {
         err = "rb_scene_create: total light importance is not positive (src/scene.cpp:243)";

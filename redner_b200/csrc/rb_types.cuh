@@ -107,6 +107,16 @@ struct __align__(16) EdgeNode {
     int edge_id;
 };
 
+// EnvironmentMap, src/envmap.h:19-51 (the texture and the two sampling tables are caller-owned device memory)
+struct DevEnvmap {
+    rb_texture values;
+    float w2e[16], e2w[16];
+    const float* cdf_ys; // [height]
+    const float* cdf_xs; // [height][width]
+    float pdf_norm;
+    int directly_visible;
+};
+
 struct DevScene {
     DevCamera cam;
     const rb_shape* shapes;
@@ -114,7 +124,9 @@ struct DevScene {
     const rb_material* materials;
     int num_materials;
     const DevLight* lights;
-    int num_lights;
+    int num_lights; // area lights + 1 if there is an environment map (it is the LAST entry of light_pmf / light_cdf)
+    int has_envmap;
+    DevEnvmap env;
     const double* light_pmf;
     const double* light_cdf;
     const double* light_areas;
@@ -146,6 +158,8 @@ struct DevDScene {
     const rb_dshape* shapes;
     const rb_material* materials; // texel pointers are gradient buffers
     float* const* light_intensity;
+    rb_texture env_values; // gradient mip pyramid of the environment map (num_levels == 0: none)
+    float* env_w2e;        // 16 floats, gradient of world_to_env
     // internal double accumulators for the camera (reduced per block, finished by one tiny kernel):
     // [0..15] d_cam_to_world, [16..31] d_world_to_cam, [32..40] d_intrinsic_mat_inv, [41..49] d_intrinsic_mat
     double* cam_accum;
@@ -159,6 +173,7 @@ struct RenderParams {
     int sample_pixel_center;
     int nd;        // total image dimensions per pixel
     int rad_dim;   // float offset of the radiance channel (reference stores the channel index here)
+    int rad_off;   // TRUE float offset of the radiance channel: where first-hit emission goes (src/primary_contribution.cpp:36-45)
     int num_channels;
     int channels[RB_CH_COUNT];
     int max_generic;

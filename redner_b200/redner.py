@@ -260,7 +260,7 @@ class DAreaLight:  # src/redner.cpp:166-167
         self.addr = _addr(intensity)
 
 
-class EnvironmentMap:  # src/redner.cpp:169-178 (second wave: accepted here, rejected by rb_scene_create)
+class EnvironmentMap:  # src/redner.cpp:169-178
     def __init__(self, values, env_to_world, world_to_env, sample_cdf_ys, sample_cdf_xs, pdf_norm, directly_visible):
         e = L.rb_envmap()
         e.values = values._c
@@ -280,8 +280,10 @@ class EnvironmentMap:  # src/redner.cpp:169-178 (second wave: accepted here, rej
 
 class DEnvironmentMap:  # src/redner.cpp:179-181
     def __init__(self, values, world_to_env):
-        self.values = values
-        self.world_to_env = world_to_env
+        e = L.rb_denvmap()
+        e.values = values._c
+        e.world_to_env = _addr(world_to_env) or None
+        self._c = e
 
 
 class RenderOptions:  # src/redner.cpp:207-216, src/pathtracer.h:16-23
@@ -379,8 +381,9 @@ class DScene:  # src/redner.cpp:75-82
         d.num_shapes, d.shapes = len(shapes), self._shapes
         d.num_materials, d.materials = len(materials), self._materials
         d.num_lights, d.light_intensity = len(area_lights), self._lights
-        self._c = d
         self.envmap = envmap
+        d.envmap = C.pointer(envmap._c) if envmap is not None else None
+        self._c = d
 
 
 def render(scene, options, rendered_image, d_rendered_image, d_scene, screen_gradient_image, debug_image, stream=None):

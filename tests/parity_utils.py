@@ -33,6 +33,9 @@ CASES = {
     # no radiance channel at all, max_bounces 0 (the deferred-shading set-up of the tutorials); camera gradients included
     "gbuffer_bwd_single_triangle_no_radiance": dict(scene="single_triangle", res=32, spp=4, mb=0, sampler="sobol", edges=1, seed=7,
                                                     channels=["depth", "alpha", "position", "uv"]),
+    # environment map: importance-sampled light + BSDF-miss lookups with MIS, sky seen directly by the camera, gradients of
+    # the map's texels and of its rotation (src/envmap.h, src/path_contribution.cpp:51-118,295-337,520-590)
+    "env_ball_sobol_mb2": dict(scene="env_ball", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=21),
     # normal-mapped ball with a mip-mapped specular texture and a differentiable uv_scale
     "nmap_room_sobol_mb2": dict(scene="nmap_room", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=11),
 }
@@ -73,6 +76,12 @@ def collect_grads(scene):
                 out["mat%d.%s" % (i, k)] = t.texels.grad.detach().cpu().clone()
             if t is not None and t.uv_scale.grad is not None:
                 out["mat%d.%s.uv_scale" % (i, k)] = t.uv_scale.grad.detach().cpu().clone()
+    env = getattr(scene, "envmap", None)
+    if env is not None:
+        if env.values.texels.grad is not None:
+            out["envmap.values"] = env.values.texels.grad.detach().cpu().clone()
+        if env.env_to_world.grad is not None:
+            out["envmap.env_to_world"] = env.env_to_world.grad.detach().cpu().clone()
     for i, l in enumerate(scene.area_lights):
         if l.intensity.grad is not None:
             out["light%d.intensity" % i] = l.intensity.grad.detach().cpu().clone()

@@ -131,10 +131,35 @@ def random_soup(device, num_tris=2000, resolution=(256, 256), seed=3, grad=False
     return api.Scene(cam, [soup, floor, light], [m, m_l], [api.AreaLight(2, torch.tensor([30.0, 30.0, 30.0]))])
 
 
+def env_ball(device, resolution=(64, 64), grad=True):
+    """A glossy ball and a textured floor under an environment map (plus one small area light, so that light selection
+    mixes both kinds); the camera sees the sky directly."""
+    g = torch.Generator().manual_seed(11)
+    cam = api.Camera(position=torch.tensor([0.2, 1.1, -4.0]), look_at=torch.tensor([0.0, 0.6, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
+                     fov=torch.tensor([45.0]), clip_near=1e-2, resolution=resolution)
+    sky = (0.2 + 1.5 * torch.rand(16, 32, 3, generator=g)).to(device).requires_grad_(grad)
+    a = 0.4
+    e2w = torch.tensor([[math.cos(a), 0.0, math.sin(a), 0.0], [0.0, 1.0, 0.0, 0.0], [-math.sin(a), 0.0, math.cos(a), 0.0], [0.0, 0.0, 0.0, 1.0]],
+                       requires_grad=grad)
+    env = api.EnvironmentMap(sky, e2w)
+    tex = (0.2 + 0.6 * torch.rand(8, 8, 3, generator=g)).to(device).requires_grad_(grad)
+    m_floor = api.Material(diffuse_reflectance=api.Texture(tex, torch.tensor([2.0, 2.0], device=device)))
+    m_ball = api.Material(diffuse_reflectance=_t([0.3, 0.25, 0.5], device, grad=grad), specular_reflectance=_t([0.4, 0.4, 0.4], device, grad=grad),
+                          roughness=_t([0.25], device, grad=grad))
+    m_light = api.Material(diffuse_reflectance=_t([0.0, 0.0, 0.0], device))
+    floor = api.Shape(_t([[-2.0, 0.0, -2.0], [-2.0, 0.0, 2.0], [2.0, 0.0, -2.0], [2.0, 0.0, 2.0]], device),
+                      _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 0, uvs=_t([[0.0, 0.0], [0.0, 1.0], [1.0, 0.0], [1.0, 1.0]], device))
+    v, i, uv, n = uv_sphere(device, 0.6, (0.1, 0.6, 0.2), grad=grad)
+    ball = api.Shape(v, i, 1, uvs=uv, normals=n)
+    lamp = api.Shape(_t([[-0.4, 2.4, -0.4], [-0.4, 2.4, 0.4], [0.4, 2.4, -0.4], [0.4, 2.4, 0.4]], device), _t([[0, 2, 1], [1, 2, 3]], device, torch.int32), 2)
+    lights = [api.AreaLight(2, torch.tensor([6.0, 6.0, 5.0], requires_grad=grad))]
+    return api.Scene(cam, [floor, ball, lamp], [m_floor, m_ball, m_light], lights, envmap=env)
+
+
 def nmap_room(device, **kw):
     """glossy_room with a normal-mapped, specular-textured ball (normal-map and uv_scale adjoints)."""
     return glossy_room(device, nmap=True, **kw)
 
 
 SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
-          "nmap_room": nmap_room}
+          "nmap_room": nmap_room, "env_ball": env_ball}

@@ -145,8 +145,20 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
         meshes[s].indices.assign(sc->shapes[s].indices, sc->shapes[s].indices + 3 * (size_t)sc->shapes[s].num_triangles);
     }
     d.num_lights = (int)sc->lights.size();
+    d.has_envmap = desc->envmap != nullptr;
+    if (d.has_envmap) {
+        const rb_envmap& e = *desc->envmap;
+        d.env.values = e.values;
+        memcpy(d.env.w2e, e.world_to_env, sizeof(d.env.w2e));
+        memcpy(d.env.e2w, e.env_to_world, sizeof(d.env.e2w));
+        d.env.cdf_ys = e.sample_cdf_ys;
+        d.env.cdf_xs = e.sample_cdf_xs;
+        d.env.pdf_norm = e.pdf_norm;
+        d.env.directly_visible = e.directly_visible;
+        d.num_lights++;
+    }
     if (d.num_lights > 0) {
-        if (!host_build_lights(sc->lights, meshes, sc->lt, g_err)) return 1;
+        if (!host_build_lights(sc->lights, meshes, sc->lt, g_err, d.has_envmap != 0, d.has_envmap ? desc->envmap->pdf_norm : 0.0, host_bsphere_radius(meshes))) return 1;
         d.lights = sc->lights.data();
         d.light_pmf = sc->lt.pmf.data();
         d.light_cdf = sc->lt.cdf.data();
@@ -213,6 +225,11 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
     for (int i = 0; i < opt->num_channels; i++)
         if (opt->channels[i] == RB_CH_RADIANCE) rp.rad_dim = i;
     rp.nd = host_compute_num_channels(opt->channels, opt->num_channels, scene->max_generic);
+    rp.rad_off = -1;
+    for (int i = 0, off = 0; i < opt->num_channels; i++) {
+        if (opt->channels[i] == RB_CH_RADIANCE) rp.rad_off = off;
+        off += rb_channel_width(opt->channels[i], scene->max_generic);
+    }
     rp.part = 0; rp.num_parts = 1; rp.rows_per_stripe = 16;
     rp.vp_w = scene->cam.viewport_end[0] - scene->cam.viewport_beg[0];
     rp.vp_h = scene->cam.viewport_end[1] - scene->cam.viewport_beg[1];
@@ -268,6 +285,12 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
         ka.ds.materials = d_scene->materials;
         ka.ds.light_intensity = d_scene->light_intensity;
         ka.ds.cam_accum = cam_accum.data();
+        memset(&ka.ds.env_values, 0, sizeof(rb_texture));
+        ka.ds.env_w2e = nullptr;
+        if (d_scene->envmap != nullptr) {
+            ka.ds.env_values = d_scene->envmap->values;
+            ka.ds.env_w2e = d_scene->envmap->world_to_env;
+        }
         CamAcc acc;
         acc.base = cam_f.data();
         acc.stride = 1;
