@@ -555,8 +555,11 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
     for (int side = 0; side < 2; side++) {
         const Ray ray = rays[side];
         const Isect is = hits[side];
-        if (!is.valid()) continue;
         V3 thr = side == 0 ? wgt : -wgt;
+        if (!is.valid()) { // this side looks past the edge into the environment (src/primary_contribution.cpp:25-29)
+            if (rp.rad_dim >= 0) contrib += sum(weight * thr * miss_emission(sc, ray.dir, rd));
+            continue;
+        }
         RayDiff rd_after;
         SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
         if (rp.rad_dim >= 0) {

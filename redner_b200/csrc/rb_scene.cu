@@ -385,9 +385,9 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
         rb_set_error("rb_scene_create: use_gpu == 0 requested, but redner_b200 has no CPU path (CUDA sm_100a only)");
         return 1;
     }
-    if (desc->envmap != nullptr && (desc->use_primary_edge_sampling || desc->use_secondary_edge_sampling)) {
-        rb_set_error("rb_scene_create: environment maps are implemented for the interior (non-edge) terms only; edge sampling with an "
-                     "environment map is not implemented yet");
+    if (desc->envmap != nullptr && desc->use_secondary_edge_sampling) {
+        rb_set_error("rb_scene_create: secondary edge sampling with an environment map is not implemented yet (interior terms and primary "
+                     "edges are)");
         return 1;
     }
     if (desc->envmap != nullptr && (desc->envmap->values.num_levels <= 0 || desc->envmap->values.width[0] <= 0 || desc->envmap->sample_cdf_ys == nullptr ||

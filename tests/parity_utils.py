@@ -36,6 +36,10 @@ CASES = {
     # environment map: importance-sampled light + BSDF-miss lookups with MIS, sky seen directly by the camera, gradients of
     # the map's texels and of its rotation (src/envmap.h, src/path_contribution.cpp:51-118,295-337,520-590)
     "env_ball_sobol_mb2": dict(scene="env_ball", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=21),
+    # primary edges against the sky.  Sample-exact only for a sky without mip dependence: the reference looks edge rays'
+    # differentials up at the wrong index (written at [idx], read at [2 idx + side]: src/edge.cpp:443-444 vs :608), so the
+    # filter footprint of anything an edge ray sees is stale data there; we use the differential of the edge point.
+    "env_ball_flat_sky_primary_edges": dict(scene="env_ball_flat_sky", res=40, spp=8, mb=1, sampler="sobol", edges=1, seed=22, vertex_tol=5e-3),
     # normal-mapped ball with a mip-mapped specular texture and a differentiable uv_scale
     "nmap_room_sobol_mb2": dict(scene="nmap_room", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=11),
 }

@@ -131,13 +131,16 @@ def random_soup(device, num_tris=2000, resolution=(256, 256), seed=3, grad=False
     return api.Scene(cam, [soup, floor, light], [m, m_l], [api.AreaLight(2, torch.tensor([30.0, 30.0, 30.0]))])
 
 
-def env_ball(device, resolution=(64, 64), grad=True):
+def env_ball(device, resolution=(64, 64), grad=True, constant_sky=False):
     """A glossy ball and a textured floor under an environment map (plus one small area light, so that light selection
     mixes both kinds); the camera sees the sky directly."""
     g = torch.Generator().manual_seed(11)
     cam = api.Camera(position=torch.tensor([0.2, 1.1, -4.0]), look_at=torch.tensor([0.0, 0.6, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
                      fov=torch.tensor([45.0]), clip_near=1e-2, resolution=resolution)
-    sky = (0.2 + 1.5 * torch.rand(16, 32, 3, generator=g)).to(device).requires_grad_(grad)
+    sky = (0.2 + 1.5 * torch.rand(16, 32, 3, generator=g))
+    if constant_sky:  # same image size, one colour: no dependence on the mip level
+        sky = torch.ones(16, 32, 3) * torch.tensor([0.6, 0.7, 0.9])
+    sky = sky.to(device).requires_grad_(grad)
     a = 0.4
     e2w = torch.tensor([[math.cos(a), 0.0, math.sin(a), 0.0], [0.0, 1.0, 0.0, 0.0], [-math.sin(a), 0.0, math.cos(a), 0.0], [0.0, 0.0, 0.0, 1.0]],
                        requires_grad=grad)
@@ -156,10 +159,14 @@ def env_ball(device, resolution=(64, 64), grad=True):
     return api.Scene(cam, [floor, ball, lamp], [m_floor, m_ball, m_light], lights, envmap=env)
 
 
+def env_ball_flat_sky(device, **kw):
+    return env_ball(device, constant_sky=True, **kw)
+
+
 def nmap_room(device, **kw):
     """glossy_room with a normal-mapped, specular-textured ball (normal-map and uv_scale adjoints)."""
     return glossy_room(device, nmap=True, **kw)
 
 
 SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
-          "nmap_room": nmap_room, "env_ball": env_ball}
+          "nmap_room": nmap_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}

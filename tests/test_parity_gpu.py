@@ -43,7 +43,9 @@ def test_golden_case(rb, dev, name):
     exact_vertices = not (cfg["sampler"] == "independent" and cfg["edges"])  # PCG edge streams depend on global compaction
     for k, v in grads.items():
         ref = g["grad." + k]
-        if k.endswith("vertices") and not exact_vertices:
+        if np.linalg.norm(ref) < 1e-9:  # a gradient that is exactly zero up to rounding (e.g. rotating a one-colour sky)
+            assert np.linalg.norm(v.numpy()) < 1e-4, k
+        elif k.endswith("vertices") and not exact_vertices:
             assert pu.rel_l2(v.numpy(), ref) < 0.5, k
         elif k.endswith("vertices") and "vertex_tol" in cfg:
             assert pu.rel_l2(v.numpy(), ref) < cfg["vertex_tol"], (k, pu.rel_l2(v.numpy(), ref))
