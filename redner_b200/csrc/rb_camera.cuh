@@ -6,8 +6,9 @@
 // The forward ray is evaluated in double from the float camera parameters exactly like the reference
 // (Real == double there) and rounded to fp32 once, so the rays entering the fp32 BVH traversal are the
 // same fp32 rays the reference hands to Embree (src/scene.cpp:556-567).
-// Supported: perspective and orthographic cameras without distortion (fisheye / panorama / Brown-Conrady
-// are rejected by rb_scene_create; SURVEY.md section 7 step 9 "second wave").
+// Supported: perspective, orthographic, fisheye (equi-angular) and panorama cameras without distortion parameters
+// (Brown-Conrady distortion is rejected by rb_scene_create).  A fisheye sample outside the unit disc gives a NULL ray
+// (zero origin and direction, src/camera.h:160-162): it is traced by nobody and contributes nothing.
 #pragma once
 #include "rb_types.cuh"
 
@@ -34,6 +35,29 @@ RB_HD void cam_sample_primary(const DevCamera& cam, double sx, double sy, D3& or
         D3 n = d3_normalize(d);
         D3 w = d3(C[0] * n.x + C[1] * n.y + C[2] * n.z, C[4] * n.x + C[5] * n.y + C[6] * n.z, C[8] * n.x + C[9] * n.y + C[10] * n.z);
         dir = d3_normalize(w);
+    } else if (cam.type == RB_CAMERA_FISHEYE || cam.type == RB_CAMERA_PANORAMA) {
+        const double pi = 3.14159265358979323846;
+        double lx, ly, lz;
+        if (cam.type == RB_CAMERA_FISHEYE) { // equi-angular: radius on the unit disc -> polar angle
+            double x = 2.0 * (sx - 0.5), y = 2.0 * (sy - 0.5);
+            if (x * x + y * y > 1.0) {
+                org = d3(0, 0, 0);
+                dir = d3(0, 0, 0);
+                return;
+            }
+            double r = sqrt(x * x + y * y), phi = atan2(y, x), theta = r * (pi / 2);
+            lx = -cos(phi) * sin(theta);
+            ly = -sin(phi) * sin(theta);
+            lz = cos(theta);
+        } else { // latitude-longitude
+            double theta = pi * sy, phi = 2 * pi * sx;
+            lx = cos(phi) * sin(theta);
+            ly = cos(theta);
+            lz = sin(phi) * sin(theta);
+        }
+        double iw = 1.0 / C[15];
+        org = d3(C[3] * iw, C[7] * iw, C[11] * iw);
+        dir = d3_normalize(d3(C[0] * lx + C[1] * ly + C[2] * lz, C[4] * lx + C[5] * ly + C[6] * lz, C[8] * lx + C[9] * ly + C[10] * lz));
     } else { // orthographic
         double px = (sx - 0.5) * 2.0, py = (sy - 0.5) * (-2.0) / aspect, pz = 0.0;
         D3 l = d3(I[0] * px + I[1] * py + I[2] * pz, I[3] * px + I[4] * py + I[5] * pz, I[6] * px + I[7] * py + I[8] * pz);
@@ -138,6 +162,36 @@ RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx, Real sy, const DRa
             d_screen->x += d_pt.x * 2;
             d_screen->y += d_pt.y * (-2 / aspect);
         }
+    } else if (cam.type == RB_CAMERA_FISHEYE || cam.type == RB_CAMERA_PANORAMA) {
+        // src/camera.h:343-498: camera matrix always, the screen position only when somebody asks for it
+        bool fish = cam.type == RB_CAMERA_FISHEYE;
+        Real x = fish ? 2 * (sx - Real(0.5)) : sx, y = fish ? 2 * (sy - Real(0.5)) : sy;
+        if (fish && x * x + y * y > 1) return;
+        Real r = sqrt(x * x + y * y);
+        Real phi = fish ? atan2(y, x) : Real(2 * RB_PI) * x, theta = fish ? r * Real(RB_PI) / 2 : Real(RB_PI) * y;
+        Real sp = sin(phi), cp = cos(phi), st = sin(theta), ct = cos(theta);
+        V3 dir = fish ? mk3(-cp * st, -sp * st, ct) : mk3(cp * st, ct, sp * st);
+        V3 world_dir = xfm_vector(C, dir);
+        V3 d_world_dir = d_normalize(world_dir, d_ray.dir);
+        V3 d_dir = zero3();
+        d_xfm_vector(C, dir, d_world_dir, d_C, d_dir);
+        V3 d_cam_org = zero3();
+        d_xfm_point(C, zero3(), d_ray.org, d_C, d_cam_org);
+        if (d_screen != nullptr) {
+            if (fish) {
+                Real d_cp = d_dir.x * (-st), d_sp = d_dir.y * (-st), d_st = d_dir.x * (-cp) + d_dir.y * (-sp), d_ct = d_dir.z;
+                Real d_phi = d_cp * (-sp) + d_sp * cp, d_theta = d_ct * (-st) + d_st * ct;
+                Real d_r = d_theta * (Real(RB_PI) / 2);
+                Real d_x = d_phi * (-y / (x * x + y * y)) + d_r * (x / r), d_y = d_phi * (x / (x * x + y * y)) + d_r * (y / r);
+                d_screen->x += 2 * d_x;
+                d_screen->y += 2 * d_y;
+            } else {
+                Real d_cp = d_dir.x * st, d_sp = d_dir.z * st, d_st = d_dir.x * cp + d_dir.z * sp, d_ct = d_dir.y;
+                Real d_phi = d_cp * (-sp) + d_sp * cp, d_theta = d_ct * (-st) + d_st * ct;
+                d_screen->x += d_phi * Real(2 * RB_PI);
+                d_screen->y += d_theta * Real(RB_PI);
+            }
+        }
     } else {
         // NOTE: the reference's adjoint uses pt.z = 1 here although the forward uses 0 (src/camera.h:283-285 vs :146-148);
         // reproduced for parity.
@@ -162,6 +216,15 @@ RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx, Real sy, const DRa
 
 // ---- screen projection of a world-space segment (primary edge sampling) ----
 RB_HD V2 cam_to_screen(const DevCamera& cam, V3 pt) {
+    if (cam.type == RB_CAMERA_FISHEYE) { // src/camera.h:533-543
+        V3 d = normalize(pt);
+        Real phi = atan2(d.y, d.x), r = acos(d.z) * 2 / Real(RB_PI);
+        return mk2(Real(0.5) * (-r * cos(phi) + 1), Real(0.5) * (-r * sin(phi) + 1));
+    }
+    if (cam.type == RB_CAMERA_PANORAMA) { // src/camera.h:544-553
+        V3 d = normalize(pt);
+        return mk2(atan2(d.z, d.x) / Real(2 * RB_PI), acos(d.y) / Real(RB_PI));
+    }
     M3 K = cam_m3(cam.intr);
     Real aspect = Real(cam.width) / Real(cam.height);
     V3 ip = mul(K, pt);
@@ -194,6 +257,22 @@ RB_HD bool cam_project(const DevCamera& cam, V3 p0, V3 p1, V2& pp0, V2& pp1) {
     return true;
 }
 RB_D void d_cam_to_screen(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt) {
+    if (cam.type == RB_CAMERA_FISHEYE) { // src/camera.h:669-697
+        V3 d = normalize(pt);
+        Real phi = atan2(d.y, d.x), r = acos(d.z) * 2 / Real(RB_PI);
+        Real dr = Real(-0.5) * (cos(phi) * dx + sin(phi) * dy), dphi = Real(0.5) * r * sin(phi) * dx - Real(0.5) * r * cos(phi) * dy;
+        Real dtheta = dr * (2 / Real(RB_PI));
+        Real q = d.x * d.x + d.y * d.y;
+        d_pt += d_normalize(pt, mk3(-dphi * d.y / q, dphi * d.x / q, -dtheta / sqrt(1 - d.z * d.z)));
+        return;
+    }
+    if (cam.type == RB_CAMERA_PANORAMA) { // src/camera.h:698-724
+        V3 d = normalize(pt);
+        Real d_phi = dx / Real(2 * RB_PI), d_theta = dy / Real(RB_PI);
+        Real q = d.x * d.x + d.z * d.z;
+        d_pt += d_normalize(pt, mk3(-d_phi * d.z / q, -d_theta / sqrt(1 - d.y * d.y), d_phi * d.x / q));
+        return;
+    }
     M3 K = cam_m3(cam.intr);
     Real aspect = Real(cam.width) / Real(cam.height);
     V3 ip = mul(K, pt);
@@ -266,5 +345,7 @@ RB_D void d_cam_project(const DevCamera& cam, V3 p0, V3 p1, Real dp0x, Real dp0y
 RB_HD bool cam_in_screen(const DevCamera& cam, V2 pt) {
     int xi = int(pt.x * cam.width), yi = int(pt.y * cam.height);
     if (xi < cam.vp_beg[0] || xi >= cam.vp_end[0] || yi < cam.vp_beg[1] || yi >= cam.vp_end[1]) return false;
+    if (cam.type == RB_CAMERA_FISHEYE) return rb_sq(pt.x - Real(0.5)) + rb_sq(pt.y - Real(0.5)) < Real(0.25); // src/camera.h:1059-1066
     return pt.x >= 0 && pt.x < 1 && pt.y >= 0 && pt.y < 1;
 }
+RB_HD bool ray_is_null(const Ray& r) { return r.dir.x == 0 && r.dir.y == 0 && r.dir.z == 0; }

@@ -101,6 +101,7 @@ RB_D V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, in
     primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
     Isect is = no_isect();
     V3 acc = zero3();
+    if (ray_is_null(ray)) return acc; // fisheye sample outside the image disc
     if (closest_hit(sc, ray, is)) {
         RayDiff rd_after;
         SurfacePoint sp = make_surface_point(sc.shapes[is.shape_id], is.tri_id, ray, rd, rd_after);
@@ -222,6 +223,7 @@ RB_D bool forward_sample_channels(const DevScene& sc, const RenderParams& rp, in
     D3 od, dd;
     primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
     Isect is = no_isect();
+    if (ray_is_null(ray)) return false;
     if (!closest_hit(sc, ray, is)) {
         if (rp.rad_off >= 0) {
             V3 L = weight * miss_emission(sc, ray.dir, rd);
@@ -281,8 +283,9 @@ RB_D int bwd_trace(const DevScene& sc, const RenderParams& rp, int pixel, int px
     if (act) {
         smp.init(rp.sampler_type, rp.seed, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
         primary_ray_for(sc, rp, px, py, smp, sx, sy, ray, rd, &od, &dd);
-        act = closest_hit(sc, ray, is);
-        if (!act) is.shape_id = -2; // "traced and missed" (as opposed to an idle lane)
+        bool null_ray = ray_is_null(ray);
+        act = !null_ray && closest_hit(sc, ray, is);
+        if (!act && !null_ray) is.shape_id = -2; // "traced and missed" (as opposed to an idle lane or a null ray)
     }
     RB_PHASE_SYNC();
     if (!act) {
@@ -446,6 +449,19 @@ RB_HD D2 cam_to_screen_d(const DevCamera& cam, D3 p) {
     double aspect = double(cam.width) / double(cam.height);
     double ix = K[0] * p.x + K[1] * p.y + K[2] * p.z, iy = K[3] * p.x + K[4] * p.y + K[5] * p.z, iz = K[6] * p.x + K[7] * p.y + K[8] * p.z;
     D2 r;
+    const double pi = 3.14159265358979323846;
+    if (cam.type == RB_CAMERA_FISHEYE || cam.type == RB_CAMERA_PANORAMA) {
+        D3 d = d3_normalize(p);
+        if (cam.type == RB_CAMERA_FISHEYE) {
+            double phi = atan2(d.y, d.x), rr = acos(d.z) * 2.0 / pi;
+            r.x = 0.5 * (-rr * cos(phi) + 1.0);
+            r.y = 0.5 * (-rr * sin(phi) + 1.0);
+        } else {
+            r.x = atan2(d.z, d.x) / (2 * pi);
+            r.y = acos(d.y) / pi;
+        }
+        return r;
+    }
     if (cam.type == RB_CAMERA_PERSPECTIVE) {
         r.x = (ix / iz + 1.0) * 0.5;
         r.y = (-(iy / iz) * aspect + 1.0) * 0.5;
@@ -473,6 +489,44 @@ RB_HD bool cam_project_d(const DevCamera& cam, D3 p0, D3 p1, D2& q0, D2& q1) {
     return true;
 }
 
+// Screen position -> direction in camera space and its adjoint, fisheye / panorama only (src/camera.h:858-890, :962-1037;
+// the panorama adjoint carries the reference's slips: sin(phi) where sin(theta) belongs, and the fisheye's factor 2).
+RB_HD D3 cam_screen_to_camera_d(const DevCamera& cam, D2 p) {
+    const double pi = 3.14159265358979323846;
+    if (cam.type == RB_CAMERA_FISHEYE) {
+        double x = 2.0 * (p.x - 0.5), y = 2.0 * (p.y - 0.5);
+        double phi = atan2(y, x), theta = sqrt(x * x + y * y) * pi / 2.0;
+        return d3(-cos(phi) * sin(theta), -sin(phi) * sin(theta), cos(theta));
+    }
+    double theta = pi * p.y, phi = 2 * pi * p.x;
+    return d3(cos(phi) * sin(theta), cos(theta), sin(phi) * sin(theta));
+}
+RB_HD D2 d_cam_screen_to_camera_d(const DevCamera& cam, D2 p, D3 d_dir) {
+    const double pi = 3.14159265358979323846;
+    D2 r;
+    if (cam.type == RB_CAMERA_FISHEYE) {
+        double x = 2.0 * (p.x - 0.5), y = 2.0 * (p.y - 0.5);
+        double rr = sqrt(x * x + y * y), phi = atan2(y, x), theta = rr * pi / 2.0;
+        double sp = sin(phi), cp = cos(phi), st = sin(theta), ct = cos(theta);
+        double d_cp = -d_dir.x * st, d_sp = -d_dir.y * st, d_st = -(d_dir.x * cp + d_dir.y * sp), d_ct = d_dir.z;
+        double d_phi = d_sp * cp - d_cp * sp, d_theta = d_st * ct - d_ct * st;
+        double d_r = d_theta * (pi / 2.0);
+        double d_x = d_phi * (-y / (x * x + y * y)) + d_r * (x / rr), d_y = d_phi * (x / (x * x + y * y)) + d_r * (y / rr);
+        r.x = d_x * 2;
+        r.y = d_y * 2;
+        return r;
+    }
+    double theta = pi * p.y, phi = 2 * pi * p.x;
+    double sp = sin(phi), cp = cos(phi), st = sin(theta), ct = cos(theta);
+    double d_cp = d_dir.x * st, d_sp = d_dir.z * sp, d_st = d_dir.x * cp + d_dir.z * sp, d_ct = d_dir.y;
+    double d_phi = d_sp * cp - d_cp * sp, d_theta = d_st * ct - d_ct * st;
+    r.x = d_phi * (2 * pi) * 2;
+    r.y = d_theta * pi * 2;
+    return r;
+}
+RB_HD D3 d3_cross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RB_HD bool cam_is_linear(const DevCamera& cam) { return cam.type == RB_CAMERA_PERSPECTIVE || cam.type == RB_CAMERA_ORTHOGRAPHIC; }
+
 // One primary-edge sample: edge sample index i (seeds the stream like a pixel index), spp sample s.
 // Edge and point on it chosen by primary-edge sample (i, s); false if the sample contributes nothing (edge behind the
 // camera, zero probability, point off screen).  `smp` is left positioned at the first light/bsdf dimension.
@@ -480,6 +534,8 @@ struct PrimEdgePick {
     int edge_id;
     double pmf, e_t;
     D2 q0, q1, ept;
+    D2 upper, lower; // screen positions of the two rays on either side of the edge
+    double jacobian; // 1 for linear projections (there the edge length and the gradient of the edge equation cancel)
 };
 RB_D bool primary_edge_pick(const DevScene& sc, const RenderParams& rp, long long i, int s, int dim_base, Sampler& smp, PrimEdgePick& pk) {
     smp.init(rp.sampler_type, rp.seed + 131071ULL, (int)i, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS,
@@ -493,9 +549,44 @@ RB_D bool primary_edge_pick(const DevScene& sc, const RenderParams& rp, long lon
     V3 v0 = edge_v0(sc.shapes, edge), v1 = edge_v1(sc.shapes, edge);
     if (!cam_project_d(sc.cam, d3(v0.x, v0.y, v0.z), d3(v1.x, v1.y, v1.z), pk.q0, pk.q1)) return false;
     if (pk.pmf <= 0) return false;
-    pk.ept.x = pk.q0.x + pk.e_t * (pk.q1.x - pk.q0.x);
-    pk.ept.y = pk.q0.y + pk.e_t * (pk.q1.y - pk.q0.y);
-    return cam_in_screen(sc.cam, mk2((Real)pk.ept.x, (Real)pk.ept.y));
+    if (cam_is_linear(sc.cam)) {
+        pk.ept.x = pk.q0.x + pk.e_t * (pk.q1.x - pk.q0.x);
+        pk.ept.y = pk.q0.y + pk.e_t * (pk.q1.y - pk.q0.y);
+        if (!cam_in_screen(sc.cam, mk2((Real)pk.ept.x, (Real)pk.ept.y))) return false;
+        // unit normal of the projected edge: get_normal(normalize(v0_ss - v1_ss)) = (d.y, -d.x); rays at +-1e-6 across it
+        double ddx = pk.q0.x - pk.q1.x, ddy = pk.q0.y - pk.q1.y;
+        double dl = sqrt(ddx * ddx + ddy * ddy);
+        double nx = ddy / dl, ny = -ddx / dl;
+        const double offset = 1e-6;
+        pk.upper.x = pk.ept.x + nx * offset;
+        pk.upper.y = pk.ept.y + ny * offset;
+        pk.lower.x = pk.ept.x - nx * offset;
+        pk.lower.y = pk.ept.y - ny * offset;
+        pk.jacobian = 1;
+        return true;
+    }
+    // Fisheye / panorama (src/edge.cpp:486-592): the edge is a straight segment on the film in CAMERA space, so the
+    // point is sampled there and projected back; the two rays leave the edge plane by an offset shrinking with distance.
+    D3 a = cam_screen_to_camera_d(sc.cam, pk.q0), b = cam_screen_to_camera_d(sc.cam, pk.q1);
+    D3 ab = d3(b.x - a.x, b.y - a.y, b.z - a.z);
+    D3 p3 = d3(a.x + pk.e_t * ab.x, a.y + pk.e_t * ab.y, a.z + pk.e_t * ab.z);
+    pk.ept = cam_to_screen_d(sc.cam, p3);
+    if (!cam_in_screen(sc.cam, mk2((Real)pk.ept.x, (Real)pk.ept.y))) return false;
+    D3 axb = d3_cross(a, b);
+    D3 hn = d3_normalize(axb);
+    D3 l0 = w2c_point(sc.cam, d3(v0.x, v0.y, v0.z)), l1 = w2c_point(sc.cam, d3(v1.x, v1.y, v1.z));
+    D3 el = d3(l0.x + pk.e_t * l1.x, l0.y + pk.e_t * l1.y, l0.z + pk.e_t * l1.z); // (v0 + t v1, as in the reference :527)
+    double offset = 1e-5f / sqrt(el.x * el.x + el.y * el.y + el.z * el.z);
+    pk.upper = cam_to_screen_d(sc.cam, d3_normalize(d3(p3.x + offset * hn.x, p3.y + offset * hn.y, p3.z + offset * hn.z)));
+    pk.lower = cam_to_screen_d(sc.cam, d3_normalize(d3(p3.x - offset * hn.x, p3.y - offset * hn.y, p3.z - offset * hn.z)));
+    D2 d_ept = d_cam_screen_to_camera_d(sc.cam, pk.ept, axb);
+    double dirac_jacobian = 1.0 / sqrt(d_ept.x * d_ept.x + d_ept.y * d_ept.y);
+    const double jac_offset = 1e-6;
+    D2 pd = cam_to_screen_d(sc.cam, d3(a.x + (pk.e_t + jac_offset) * ab.x, a.y + (pk.e_t + jac_offset) * ab.y, a.z + (pk.e_t + jac_offset) * ab.z));
+    // (finite difference divided by the RAY offset, not by jac_offset: src/edge.cpp:577)
+    double line_jacobian = sqrt(rb_sq((pd.x - pk.ept.x) / offset) + rb_sq((pd.y - pk.ept.y) / offset));
+    pk.jacobian = line_jacobian * dirac_jacobian;
+    return true;
 }
 // Sort key of a primary-edge sample: (edge, position along the edge).  Samples that are neighbours under this key
 // shoot nearly the same camera rays and scatter into the same two vertices; ~0u = contributes nothing.
@@ -520,18 +611,13 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
     const D2 q0 = pk.q0, q1 = pk.q1, ept = pk.ept;
     const Edge edge = sc.edges[pk.edge_id];
     V3 v0 = edge_v0(sc.shapes, edge), v1 = edge_v1(sc.shapes, edge);
-    // unit normal of the projected edge: get_normal(normalize(v0_ss - v1_ss)) = (d.y, -d.x)
-    double ddx = q0.x - q1.x, ddy = q0.y - q1.y;
-    double dl = sqrt(ddx * ddx + ddy * ddy);
-    double nx = ddy / dl, ny = -ddx / dl;
-    const double offset = 1e-6;
     int vp_w = rp.vp_w;
     int xi = rb_clampi(int(ept.x * sc.cam.width - sc.cam.vp_beg[0]), 0, sc.cam.vp_end[0] - sc.cam.vp_beg[0]);
     int yi = rb_clampi(int(ept.y * sc.cam.height - sc.cam.vp_beg[1]), 0, sc.cam.vp_end[1] - sc.cam.vp_beg[1]);
     const float* dpx_all = ka.d_image + (size_t)rp.nd * ((size_t)yi * vp_w + xi);
     const float* dpx = dpx_all + (rp.rad_dim >= 0 ? rp.rad_dim : 0);
     V3 d_color = rp.rad_dim >= 0 ? mk3(dpx[0], dpx[1], dpx[2]) : zero3();
-    V3 wgt = d_color / (Real)pmf;
+    V3 wgt = d_color * (Real)(pk.jacobian / pmf);
     // ray differential of the un-offset ray, shared by both sides (src/edge.cpp:594-608)
     Ray cray;
     RayDiff rd;
@@ -541,12 +627,11 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
     Isect hits[2];
     bool connected = false;
     for (int side = 0; side < 2; side++) {
-        double sgn = side == 0 ? 1.0 : -1.0;
         D3 o, d;
-        cam_sample_primary(sc.cam, ept.x + sgn * nx * offset, ept.y + sgn * ny * offset, o, d);
+        cam_sample_primary(sc.cam, side == 0 ? pk.upper.x : pk.lower.x, side == 0 ? pk.upper.y : pk.lower.y, o, d);
         rays[side] = make_ray(o, d);
         hits[side] = no_isect();
-        closest_hit(sc, rays[side], hits[side]);
+        if (!ray_is_null(rays[side])) closest_hit(sc, rays[side], hits[side]);
         // at least one side must see a face of the edge, otherwise the edge is hidden here and the sample is dropped
         // (primary_edge_weights_updater, src/edge.cpp:653-676)
         connected = connected || (hits[side].shape_id == edge.shape_id && (hits[side].tri_id == edge.f0 || hits[side].tri_id == edge.f1));
@@ -557,7 +642,7 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
         const Isect is = hits[side];
         V3 thr = side == 0 ? wgt : -wgt;
         if (!is.valid()) { // this side looks past the edge into the environment (src/primary_contribution.cpp:25-29)
-            if (rp.rad_dim >= 0) contrib += sum(weight * thr * miss_emission(sc, ray.dir, rd));
+            if (rp.rad_dim >= 0 && !ray_is_null(ray)) contrib += sum(weight * thr * miss_emission(sc, ray.dir, rd));
             continue;
         }
         RayDiff rd_after;
@@ -583,13 +668,24 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
                     for (int k = 0; k < w; k++) acc += vals[d + k] * (Real)dpx_all[d + k];
                 d += w;
             }
-            contrib += (side == 0 ? weight : -weight) * acc / (Real)pmf;
+            contrib += (side == 0 ? weight : -weight) * acc * (Real)(pk.jacobian / pmf);
         }
     }
     if (contrib == 0) return;
-    // Eq. 8: gradients of the edge equation w.r.t. the projected end points
-    Real d0x = (Real)(q1.y - ept.y) * contrib, d0y = (Real)(ept.x - q1.x) * contrib;
-    Real d1x = (Real)(ept.y - q0.y) * contrib, d1y = (Real)(q0.x - ept.x) * contrib;
+    // gradients of the edge equation w.r.t. the projected end points and the edge point
+    Real d0x, d0y, d1x, d1y, dex, dey;
+    if (cam_is_linear(sc.cam)) { // Eq. 8
+        d0x = (Real)(q1.y - ept.y) * contrib; d0y = (Real)(ept.x - q1.x) * contrib;
+        d1x = (Real)(ept.y - q0.y) * contrib; d1y = (Real)(q0.x - ept.x) * contrib;
+        dex = (Real)(q0.y - q1.y) * contrib; dey = (Real)(q1.x - q0.x) * contrib;
+    } else { // alpha(p) = dot(p, cross(v0_dir, v1_dir)) on the camera-space film (src/edge.cpp:737-757)
+        D3 a = cam_screen_to_camera_d(sc.cam, q0), b = cam_screen_to_camera_d(sc.cam, q1), e = cam_screen_to_camera_d(sc.cam, ept);
+        D2 g0 = d_cam_screen_to_camera_d(sc.cam, q0, d3_cross(b, e)), g1 = d_cam_screen_to_camera_d(sc.cam, q1, d3_cross(e, a));
+        D2 ge = d_cam_screen_to_camera_d(sc.cam, q1, d3_cross(a, b)); // (evaluated at v1_ss like the reference, :757)
+        d0x = (Real)g0.x * contrib; d0y = (Real)g0.y * contrib;
+        d1x = (Real)g1.x * contrib; d1y = (Real)g1.y * contrib;
+        dex = (Real)ge.x * contrib; dey = (Real)ge.y * contrib;
+    }
     V3 d_v0 = zero3(), d_v1 = zero3();
     d_cam_project(sc.cam, v0, v1, d0x, d0y, d1x, d1y, cam_acc, d_v0, d_v1);
     float* dv = ds.shapes[edge.shape_id].vertices;
@@ -598,7 +694,6 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
         agg_add3(dv + 3 * (size_t)edge.v1, d_v1);
     }
     if (ka.screen_grad) {
-        Real dex = (Real)(q0.y - q1.y) * contrib, dey = (Real)(q1.x - q0.x) * contrib;
         size_t pix = (size_t)yi * vp_w + xi;
         rb_red_add(&ka.screen_grad[2 * pix + 0], (float)dex);
         rb_red_add(&ka.screen_grad[2 * pix + 1], (float)dey);

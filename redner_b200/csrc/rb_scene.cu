@@ -396,8 +396,8 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
         return 1;
     }
     const rb_camera& c = desc->camera;
-    if (c.camera_type != RB_CAMERA_PERSPECTIVE && c.camera_type != RB_CAMERA_ORTHOGRAPHIC) {
-        rb_set_error("rb_scene_create: only perspective / orthographic cameras are implemented (fisheye, panorama: second wave)");
+    if (c.camera_type < RB_CAMERA_PERSPECTIVE || c.camera_type > RB_CAMERA_PANORAMA) {
+        rb_set_error("rb_scene_create: unknown camera type");
         return 1;
     }
     if (c.has_distortion) {

@@ -40,6 +40,10 @@ CASES = {
     # differentials up at the wrong index (written at [idx], read at [2 idx + side]: src/edge.cpp:443-444 vs :608), so the
     # filter footprint of anything an edge ray sees is stale data there; we use the differential of the edge point.
     "env_ball_flat_sky_primary_edges": dict(scene="env_ball_flat_sky", res=40, spp=8, mb=1, sampler="sobol", edges=1, seed=22, vertex_tol=5e-3),
+    # fisheye (equi-angular) and panorama cameras from inside the room, differentiable pose, primary edges sampled on the
+    # camera-space film (src/camera.h:154-197,343-498,533-553,669-724; src/edge.cpp:486-592,737-757)
+    "fisheye_room_primary_edges": dict(scene="fisheye_room", res=40, spp=4, mb=1, sampler="sobol", edges=1, seed=31, vertex_tol=5e-3),
+    "panorama_room_primary_edges": dict(scene="panorama_room", res=40, spp=4, mb=1, sampler="sobol", edges=1, seed=32, vertex_tol=5e-3),
     # normal-mapped ball with a mip-mapped specular texture and a differentiable uv_scale
     "nmap_room_sobol_mb2": dict(scene="nmap_room", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=11),
 }

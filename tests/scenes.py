@@ -70,11 +70,15 @@ def uv_sphere(device, radius, center, n_theta=12, n_phi=24, grad=False):
     return (_t(verts, device, grad=grad), _t(idx, device, torch.int32), _t(uvs, device), _t(normals, device))
 
 
-def glossy_room(device, resolution=(128, 128), grad=True, textured=True, nmap=False):
+def glossy_room(device, resolution=(128, 128), grad=True, textured=True, nmap=False, sphere_res=(12, 24), camera_type=0):
     """Open box (floor, back wall, side wall) with a glossy textured floor, a Phong-shaded sphere and two area lights."""
     g = torch.Generator().manual_seed(7)
     cam = api.Camera(position=torch.tensor([0.3, 1.4, -4.5]), look_at=torch.tensor([0.0, 0.6, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
                      fov=torch.tensor([40.0]), clip_near=1e-2, resolution=resolution)
+    if camera_type != 0:  # fisheye / panorama: from inside the room, differentiable pose
+        cam = api.Camera(position=torch.tensor([0.4, 1.2, -1.6], requires_grad=grad), look_at=torch.tensor([0.1, 0.7, 0.2], requires_grad=grad),
+                         up=torch.tensor([0.0, 1.0, 0.0], requires_grad=grad), fov=torch.tensor([40.0]), clip_near=1e-2, resolution=resolution,
+                         camera_type=camera_type)
     if textured:
         tex = (0.2 + 0.6 * torch.rand(16, 16, 3, generator=g)).to(device)
         rough = (0.05 + 0.3 * torch.rand(16, 16, 1, generator=g)).to(device)
@@ -105,7 +109,7 @@ def glossy_room(device, resolution=(128, 128), grad=True, textured=True, nmap=Fa
                      _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 1)
     side = api.Shape(_t([[-2.5, 0.0, -2.5], [-2.5, 3.0, -2.5], [-2.5, 0.0, 2.5], [-2.5, 3.0, 2.5]], device),
                      _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 1)
-    v, i, uv, n = uv_sphere(device, 0.7, (0.2, 0.7, 0.3), grad=grad)
+    v, i, uv, n = uv_sphere(device, 0.7, (0.2, 0.7, 0.3), n_theta=sphere_res[0], n_phi=sphere_res[1], grad=grad)
     ball = api.Shape(v, i, 2, uvs=uv, normals=n)
     l1 = api.Shape(_t([[-0.6, 2.9, -0.6], [-0.6, 2.9, 0.6], [0.6, 2.9, -0.6], [0.6, 2.9, 0.6]], device),
                    _t([[0, 2, 1], [1, 2, 3]], device, torch.int32), 3)
@@ -159,6 +163,19 @@ def env_ball(device, resolution=(64, 64), grad=True, constant_sky=False):
     return api.Scene(cam, [floor, ball, lamp], [m_floor, m_ball, m_light], lights, envmap=env)
 
 
+def hires_room(device, **kw):
+    """glossy_room with a 32 k-triangle ball (48 k edges): scene-build and traversal cost at the BASELINE C3 / C4 scale."""
+    return glossy_room(device, sphere_res=(90, 180), **kw)
+
+
+def fisheye_room(device, **kw):
+    return glossy_room(device, camera_type=2, **kw)
+
+
+def panorama_room(device, **kw):
+    return glossy_room(device, camera_type=3, **kw)
+
+
 def env_ball_flat_sky(device, **kw):
     return env_ball(device, constant_sky=True, **kw)
 
@@ -169,4 +186,4 @@ def nmap_room(device, **kw):
 
 
 SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
-          "nmap_room": nmap_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}
+          "nmap_room": nmap_room, "hires_room": hires_room, "fisheye_room": fisheye_room, "panorama_room": panorama_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}

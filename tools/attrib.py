@@ -35,4 +35,5 @@ for edges in [int(e) for e in os.environ.get("RB_EDGES", "0,1,2,3").split(",")]:
         st, v, h = c.scene.last_stage_stats()
     sub = " (trace %.2f sec %.2f sweep %.2f)" % (st["k_bwd_trace"], st["k_bwd_secondary"], st["k_bwd_sweep"]) if "k_bwd_trace" in st else ""
     print("%s %dx%dx%d mb=%d edges=%d: fwd %.2f ms | bwd %.2f%s | prim %.2f | vert/sample %.3f hits/sample %.3f" %
-          (scene, res, res, spp, mb, edges, f, st["k_backward"], sub, st["k_primary_edge"], v / (res * res * spp), h / (res * res * spp)))
+          (scene, res, res, spp, mb, edges, f, st["k_backward"], sub, st["k_primary_edge"], v / (res * res * spp), h / (res * res * spp)),
+          "| build ms", {k: round(x, 2) for k, x in c.scene.build_ms().items()})

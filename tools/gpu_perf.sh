@@ -12,6 +12,7 @@ for l in "" redner_b200/_variants/*.so; do
   echo "LIB=${l:-main}"
   RB_LIB=$l RB_EDGES=0,3 timeout 200 python tools/attrib.py shadow_blocker 512 64 1 2>&1 | tail -2 | cut -c1-170
   RB_LIB=$l RB_EDGES=3 timeout 200 python tools/attrib.py glossy_room 256 16 2 2>&1 | tail -1 | cut -c1-170
+  RB_LIB=$l RB_EDGES=3 timeout 300 python tools/attrib.py hires_room 512 16 2 2>&1 | tail -1 | cut -c1-220
 done
 echo "=== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 echo "=== compare full size"; timeout 600 python tools/compare.py shadow_blocker --res 512 --spp 64 --edges 0 2>&1 | tail -5
