@@ -44,6 +44,9 @@ CASES = {
     # camera-space film (src/camera.h:154-197,343-498,533-553,669-724; src/edge.cpp:486-592,737-757)
     "fisheye_room_primary_edges": dict(scene="fisheye_room", res=40, spp=4, mb=1, sampler="sobol", edges=1, seed=31, vertex_tol=5e-3),
     "panorama_room_primary_edges": dict(scene="panorama_room", res=40, spp=4, mb=1, sampler="sobol", edges=1, seed=32, vertex_tol=5e-3),
+    # orthographic camera: all primary-edge rays are parallel and graze the silhouettes, the pose gradient is the sum of those
+    # few samples -- the reference itself moves by up to 1e-3 between two runs on it (Embree's parallel BVH build)
+    "ortho_room_primary_edges": dict(scene="ortho_room", res=40, spp=4, mb=1, sampler="sobol", edges=1, seed=33, vertex_tol=5e-3, cam_tol=2e-2),
     # normal-mapped ball with a mip-mapped specular texture and a differentiable uv_scale
     "nmap_room_sobol_mb2": dict(scene="nmap_room", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=11),
 }

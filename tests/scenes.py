@@ -75,7 +75,11 @@ def glossy_room(device, resolution=(128, 128), grad=True, textured=True, nmap=Fa
     g = torch.Generator().manual_seed(7)
     cam = api.Camera(position=torch.tensor([0.3, 1.4, -4.5]), look_at=torch.tensor([0.0, 0.6, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
                      fov=torch.tensor([40.0]), clip_near=1e-2, resolution=resolution)
-    if camera_type != 0:  # fisheye / panorama: from inside the room, differentiable pose
+    if camera_type == 1:  # orthographic: same pose, the intrinsic matrix scales the film to the room
+        cam = api.Camera(position=torch.tensor([0.3, 1.4, -4.5], requires_grad=grad), look_at=torch.tensor([0.0, 0.6, 0.0], requires_grad=grad),
+                         up=torch.tensor([0.0, 1.0, 0.0], requires_grad=grad), clip_near=1e-2, resolution=resolution,
+                         intrinsic_mat=torch.tensor([[0.4, 0.0, 0.0], [0.0, 0.4, 0.0], [0.0, 0.0, 1.0]]), camera_type=1)
+    elif camera_type != 0:  # fisheye / panorama: from inside the room, differentiable pose
         cam = api.Camera(position=torch.tensor([0.4, 1.2, -1.6], requires_grad=grad), look_at=torch.tensor([0.1, 0.7, 0.2], requires_grad=grad),
                          up=torch.tensor([0.0, 1.0, 0.0], requires_grad=grad), fov=torch.tensor([40.0]), clip_near=1e-2, resolution=resolution,
                          camera_type=camera_type)
@@ -168,6 +172,10 @@ def hires_room(device, **kw):
     return glossy_room(device, sphere_res=(90, 180), **kw)
 
 
+def ortho_room(device, **kw):
+    return glossy_room(device, camera_type=1, **kw)
+
+
 def fisheye_room(device, **kw):
     return glossy_room(device, camera_type=2, **kw)
 
@@ -186,4 +194,4 @@ def nmap_room(device, **kw):
 
 
 SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
-          "nmap_room": nmap_room, "hires_room": hires_room, "fisheye_room": fisheye_room, "panorama_room": panorama_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}
+          "nmap_room": nmap_room, "hires_room": hires_room, "ortho_room": ortho_room, "fisheye_room": fisheye_room, "panorama_room": panorama_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}

@@ -47,6 +47,8 @@ def test_golden_case(rb, dev, name):
             assert np.linalg.norm(v.numpy()) < 1e-4, k
         elif k.endswith("vertices") and not exact_vertices:
             assert pu.rel_l2(v.numpy(), ref) < 0.5, k
+        elif k.startswith("cam.") and "cam_tol" in cfg:
+            assert pu.rel_l2(v.numpy(), ref) < cfg["cam_tol"], (k, pu.rel_l2(v.numpy(), ref))
         elif k.endswith("vertices") and "vertex_tol" in cfg:
             assert pu.rel_l2(v.numpy(), ref) < cfg["vertex_tol"], (k, pu.rel_l2(v.numpy(), ref))
         else:
