@@ -354,6 +354,7 @@ class RenderFunction(torch.autograd.Function):
         c.shape_args, c.mat_args, c.light_args = shape_args, mat_args, light_args
         c.num_samples, c.channels, c.viewport, c.device, c.backend, c.seed = ns, channels, viewport, device, rb, seed
         c.use_look_at = c2w is None
+        c.has_distortion = dist is not None
         return c
 
     @staticmethod
@@ -385,7 +386,8 @@ class RenderFunction(torch.autograd.Function):
         else:
             d_pos, d_look, d_up, d_c2w, d_w2c = None, None, None, z(4, 4), z(4, 4)
         d_intr_inv, d_intr = z(3, 3), z(3, 3)
-        d_camera = rb.DCamera(fp(d_pos), fp(d_look), fp(d_up), fp(d_c2w), fp(d_w2c), fp(d_intr_inv), fp(d_intr), rb.float_ptr(0))
+        d_dist = z(8) if c.has_distortion else None
+        d_camera = rb.DCamera(fp(d_pos), fp(d_look), fp(d_up), fp(d_c2w), fp(d_w2c), fp(d_intr_inv), fp(d_intr), fp(d_dist))
         d_shape_bufs, d_shapes = [], []
         for v, i, uv, n, uvi, ni, col, mid, lid in c.shape_args:
             bufs = (z(*v.shape), z(*uv.shape) if uv is not None else None, z(*n.shape) if n is not None else None, z(*col.shape) if col is not None else None)
@@ -426,7 +428,7 @@ class RenderFunction(torch.autograd.Function):
         out = [None]  # seed
         out += [None, None, None]  # counts
         cpu = lambda t: t.cpu() if t is not None else None  # noqa: E731
-        out += [cpu(d_pos), cpu(d_look), cpu(d_up), cpu(d_c2w), cpu(d_w2c), cpu(d_intr_inv), cpu(d_intr), None]
+        out += [cpu(d_pos), cpu(d_look), cpu(d_up), cpu(d_c2w), cpu(d_w2c), cpu(d_intr_inv), cpu(d_intr), cpu(d_dist)]
         out += [None, None, None, None]  # clip_near, resolution, viewport, camera_type
         for bufs in d_shape_bufs:
             out += [bufs[0], None, bufs[1], bufs[2], None, None, bufs[3], None, None]

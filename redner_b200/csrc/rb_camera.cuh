@@ -22,7 +22,118 @@ RB_HD D3 d3_normalize(D3 v) {
     return d3(v.x / l, v.y / l, v.z / l);
 }
 
-RB_HD void cam_sample_primary(const DevCamera& cam, double sx, double sy, D3& org, D3& dir) {
+struct D2 {
+    double x, y;
+};
+RB_HD D2 d2(double x, double y) { D2 r; r.x = x; r.y = y; return r; }
+
+// ---- Brown-Conrady lens distortion on normalised screen coordinates (src/camera_distortion.h) ----
+// distort: undistorted -> distorted position; optional forward-mode rows d(out.x)/d(pos), d(out.y)/d(pos).
+RB_HD D2 cam_distort(const DevCamera& cam, D2 pos, D2* dx_dpos = nullptr, D2* dy_dpos = nullptr) {
+    if (!cam.has_distortion) return pos;
+    const double* k = cam.distortion;
+    const double p0 = k[6], p1 = k[7];
+    double x = 2.0 * (pos.x - 0.5), y = 2.0 * (pos.y - 0.5);
+    double r = sqrt(x * x + y * y), r2 = r * r, r4 = r2 * r2, r6 = r4 * r2;
+    double num = 1 + k[0] * r2 + k[1] * r4 + k[2] * r6, den = 1 + k[3] * r2 + k[4] * r4 + k[5] * r6, rr = num / den;
+    double xx = x * rr + 2 * p0 * x * y + p1 * (r2 + 2 * x * x), yy = y * rr + p0 * (r2 + 2 * y * y) + 2 * p1 * x * y;
+    if (dx_dpos != nullptr && dy_dpos != nullptr) {
+        D2 dx = d2(2, 0), dy = d2(0, 2); // d(x)/d(pos), d(y)/d(pos)
+        D2 dr = d2((dx.x * x + dy.x * y) / r, (dx.y * x + dy.y * y) / r);
+        D2 dr2 = d2(2 * r * dr.x, 2 * r * dr.y), dr4 = d2(2 * r2 * dr2.x, 2 * r2 * dr2.y);
+        D2 dr6 = d2(r4 * dr2.x + dr4.x * r2, r4 * dr2.y + dr4.y * r2);
+        D2 dnum = d2(k[0] * dr2.x + k[1] * dr4.x + k[2] * dr6.x, k[0] * dr2.y + k[1] * dr4.y + k[2] * dr6.y);
+        D2 dden = d2(k[3] * dr2.x + k[4] * dr4.x + k[5] * dr6.x, k[3] * dr2.y + k[4] * dr4.y + k[5] * dr6.y);
+        D2 drr = d2((dnum.x * den - num * dden.x) / (den * den), (dnum.y * den - num * dden.y) / (den * den));
+        D2 dxx = d2(dx.x * rr + x * drr.x + 2 * p0 * (dx.x * y + x * dy.x) + p1 * (dr2.x + 4 * dx.x * x),
+                    dx.y * rr + x * drr.y + 2 * p0 * (dx.y * y + x * dy.y) + p1 * (dr2.y + 4 * dx.y * x));
+        D2 dyy = d2(dy.x * rr + y * drr.x + p0 * (dr2.x + 4 * dy.x * y) + 2 * p1 * (dx.x * y + x * dy.x),
+                    dy.y * rr + y * drr.y + p0 * (dr2.y + 4 * dy.y * y) + 2 * p1 * (dx.y * y + x * dy.y));
+        *dx_dpos = d2(dxx.x / 2, dxx.y / 2);
+        *dy_dpos = d2(dyy.x / 2, dyy.y / 2);
+    }
+    return d2((xx + 1) / 2, (yy + 1) / 2);
+}
+// Adjoint of cam_distort; d_params (8 doubles, may be null) receives the parameter gradient.
+RB_HD void d_cam_distort(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
+    if (!cam.has_distortion) {
+        d_pos = d_out; // (assignment, as in the reference :96-99)
+        return;
+    }
+    const double* k = cam.distortion;
+    const double p0 = k[6], p1 = k[7];
+    double x = 2.0 * (pos.x - 0.5), y = 2.0 * (pos.y - 0.5);
+    double r = sqrt(x * x + y * y), r2 = r * r, r4 = r2 * r2, r6 = r4 * r2;
+    double num = 1 + k[0] * r2 + k[1] * r4 + k[2] * r6, den = 1 + k[3] * r2 + k[4] * r4 + k[5] * r6, rr = num / den;
+    double d_k[6] = {0, 0, 0, 0, 0, 0}, d_p[2] = {0, 0};
+    double d_xx = d_out.x / 2, d_yy = d_out.y / 2;
+    double d_x = d_xx * (rr + 2 * p0 * y + 4 * p1 * x), d_rr = d_xx * x, d_y = d_xx * 2 * p0 * x;
+    d_p[0] += d_xx * 2 * x * y;
+    d_p[1] += d_xx * (r2 + 2 * x * x);
+    double d_r2 = d_xx * p1;
+    d_y += d_yy * (rr + 4 * p0 * y + 2 * p1 * x);
+    d_rr += d_yy * y;
+    d_p[0] += d_yy * (r2 + 2 * y * y);
+    d_r2 += d_yy * p0;
+    d_p[1] += d_yy * 2 * x * y;
+    d_x += d_yy * 2 * p1 * y;
+    double d_num = d_rr / den, d_den = -d_rr * rr / den;
+    d_k[0] += d_num * r2; d_r2 += d_num * k[0];
+    d_k[1] += d_num * r4; double d_r4 = d_num * k[1];
+    d_k[2] += d_num * r6; double d_r6 = d_num * k[2];
+    d_k[3] += d_den * r2; d_r2 += d_den * k[3];
+    d_k[4] += d_den * r4; d_r4 += d_den * k[4];
+    d_k[5] += d_den * r6; d_r6 += d_den * k[5];
+    d_r4 += d_r6 * r2;
+    d_r2 += d_r6 * r2; // (r2 where r4 belongs: as in the reference :160)
+    d_r2 += 2 * d_r4 * r2;
+    double d_r = 2 * d_r2 * r;
+    d_x += d_r * x / r;
+    d_y += d_r * y / r;
+    d_pos.x += d_x * 2;
+    d_pos.y += d_y * 2;
+    if (d_params != nullptr) {
+        for (int i = 0; i < 6; i++) d_params[i] += d_k[i];
+        d_params[6] += d_p[0];
+        d_params[7] += d_p[1];
+    }
+}
+// distorted -> undistorted position by Gauss-Newton (src/camera_distortion.h:171-198)
+RB_HD D2 cam_inverse_distort(const DevCamera& cam, D2 pos) {
+    if (!cam.has_distortion) return pos;
+    D2 result = pos;
+    double err = 0;
+    int iter = 0;
+    do {
+        D2 jx, jy;
+        D2 next = cam_distort(cam, result, &jx, &jy);
+        D2 res = d2(next.x - pos.x, next.y - pos.y);
+        err = fabs(res.x) + fabs(res.y);
+        double inv_det = 1 / (jx.x * jy.y - jx.y * jy.x);
+        result = d2(result.x - inv_det * (jy.y * res.x - jx.y * res.y), result.y - inv_det * (-jy.x * res.x + jx.x * res.y));
+    } while (err > 1e-3 && iter++ < 1000);
+    return result;
+}
+// Adjoint through the implicit function theorem (src/camera_distortion.h:200-258)
+RB_HD void d_cam_inverse_distort(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
+    if (!cam.has_distortion) {
+        d_pos = d_out;
+        return;
+    }
+    D2 result = cam_inverse_distort(cam, pos);
+    D2 fx, fy;
+    cam_distort(cam, result, &fx, &fy);
+    double inv_det = 1 / (fx.x * fy.y - fx.y * fy.x);
+    D2 d_result = d2(-inv_det * (fy.y * d_out.x - fy.x * d_out.y), -inv_det * (-fx.y * d_out.x + fx.x * d_out.y));
+    D2 unused = d2(0, 0);
+    if (d_params != nullptr) d_cam_distort(cam, result, d_result, d_params, unused);
+    d_pos.x -= d_result.x;
+    d_pos.y -= d_result.y;
+}
+
+RB_HD void cam_sample_primary(const DevCamera& cam, double sx_, double sy_, D3& org, D3& dir) {
+    D2 undist = cam_inverse_distort(cam, d2(sx_, sy_)); // (identity without a lens model)
+    const double sx = undist.x, sy = undist.y;
     const double* C = cam.c2w;
     const double* I = cam.intr_inv;
     double aspect = double(cam.width) / double(cam.height);
@@ -111,8 +222,9 @@ RB_HD M3 cam_m3(const double* a) {
 // Per-thread camera-gradient accumulator.  The reference does one atomic per scalar per pixel into the same
 // <= 30 addresses (src/camera.h:244-259) -- its worst contention point.  Here every thread owns a strided
 // column in shared memory; the block reduces once at kernel end and issues one double atomic per scalar.
-// Layout (RB_CAM_ACC floats): [0..15] d_cam_to_world, [16..31] d_world_to_cam, [32..40] d_intr_inv, [41..49] d_intr.
-#define RB_CAM_ACC 50
+// Layout (RB_CAM_ACC floats): [0..15] d_cam_to_world, [16..31] d_world_to_cam, [32..40] d_intr_inv, [41..49] d_intr,
+// [50..57] d_distortion.
+#define RB_CAM_ACC 58
 struct CamAcc {
     float* base; // shared memory, element k of this thread at base[k * stride]
     int stride;
@@ -135,11 +247,22 @@ struct CamAcc {
         for (int i = 0; i < 3; i++)
             for (int j = 0; j < 3; j++) add(41 + 3 * i + j, d.m[i][j]);
     }
+    RB_D void add_distortion(const double* d) {
+        for (int i = 0; i < 8; i++)
+            if (d[i] != 0) add(50 + i, (Real)d[i]);
+    }
 };
 
 // Adjoint of cam_sample_primary w.r.t. camera parameters (screen-position gradients are only needed for
 // distortion / screen_gradient_image; the latter is accumulated by the caller through d_screen).
-RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx, Real sy, const DRay& d_ray, CamAcc& acc, V2* d_screen) {
+RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx_, Real sy_, const DRay& d_ray, CamAcc& acc, V2* d_screen_out) {
+    // With a lens model the ray is generated at the UNDISTORTED position and the adjoint w.r.t. that position flows back
+    // through inverse_distort (parameters + original position), src/camera.h:205-206,262-277.
+    const D2 spos = d2(sx_, sy_);
+    const D2 undist = cam_inverse_distort(cam, spos);
+    const Real sx = (Real)undist.x, sy = (Real)undist.y;
+    V2 d_und = zero2();
+    V2* d_screen = (cam.has_distortion || d_screen_out != nullptr) ? &d_und : nullptr;
     M4 C = cam_m4(cam.c2w);
     M3 I = cam_m3(cam.intr_inv);
     Real aspect = Real(cam.width) / Real(cam.height);
@@ -212,10 +335,27 @@ RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx, Real sy, const DRa
     }
     acc.add_intr_inv(d_I);
     acc.add_c2w(d_C);
+    if (d_screen != nullptr) {
+        double d_par[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        D2 d_pos = d2(0, 0);
+        d_cam_inverse_distort(cam, spos, d2(d_und.x, d_und.y), cam.has_distortion ? d_par : nullptr, d_pos);
+        if (cam.has_distortion) acc.add_distortion(d_par);
+        if (d_screen_out != nullptr) {
+            d_screen_out->x += (Real)d_pos.x;
+            d_screen_out->y += (Real)d_pos.y;
+        }
+    }
 }
 
 // ---- screen projection of a world-space segment (primary edge sampling) ----
+RB_HD V2 cam_to_screen_undistorted(const DevCamera& cam, V3 pt);
 RB_HD V2 cam_to_screen(const DevCamera& cam, V3 pt) {
+    V2 q = cam_to_screen_undistorted(cam, pt);
+    if (!cam.has_distortion) return q;
+    D2 r = cam_distort(cam, d2(q.x, q.y));
+    return mk2((Real)r.x, (Real)r.y);
+}
+RB_HD V2 cam_to_screen_undistorted(const DevCamera& cam, V3 pt) {
     if (cam.type == RB_CAMERA_FISHEYE) { // src/camera.h:533-543
         V3 d = normalize(pt);
         Real phi = atan2(d.y, d.x), r = acos(d.z) * 2 / Real(RB_PI);
@@ -257,6 +397,15 @@ RB_HD bool cam_project(const DevCamera& cam, V3 p0, V3 p1, V2& pp0, V2& pp1) {
     return true;
 }
 RB_D void d_cam_to_screen(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt) {
+    if (cam.has_distortion) { // adjoint of the final distort(): parameters, and the undistorted position for the rest
+        V2 q = cam_to_screen_undistorted(cam, pt);
+        double d_par[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        D2 d_q = d2(0, 0);
+        d_cam_distort(cam, d2(q.x, q.y), d2(dx, dy), d_par, d_q);
+        acc.add_distortion(d_par);
+        dx = (Real)d_q.x;
+        dy = (Real)d_q.y;
+    }
     if (cam.type == RB_CAMERA_FISHEYE) { // src/camera.h:669-697
         V3 d = normalize(pt);
         Real phi = atan2(d.y, d.x), r = acos(d.z) * 2 / Real(RB_PI);

@@ -432,9 +432,6 @@ RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, in
 
 // ---- primary edges ----
 // Projection of an edge in double (the +-1e-6 offsets across the edge need more than fp32 screen coordinates).
-struct D2 {
-    double x, y;
-};
 RB_HD D3 w2c_point(const DevCamera& cam, D3 p) {
     const double* W = cam.w2c;
     double x = W[0] * p.x + W[1] * p.y + W[2] * p.z + W[3];
@@ -444,7 +441,9 @@ RB_HD D3 w2c_point(const DevCamera& cam, D3 p) {
     double iw = 1.0 / w;
     return d3(x * iw, y * iw, z * iw);
 }
-RB_HD D2 cam_to_screen_d(const DevCamera& cam, D3 p) {
+RB_HD D2 cam_to_screen_undistorted_d(const DevCamera& cam, D3 p);
+RB_HD D2 cam_to_screen_d(const DevCamera& cam, D3 p) { return cam_distort(cam, cam_to_screen_undistorted_d(cam, p)); }
+RB_HD D2 cam_to_screen_undistorted_d(const DevCamera& cam, D3 p) {
     const double* K = cam.intr;
     double aspect = double(cam.width) / double(cam.height);
     double ix = K[0] * p.x + K[1] * p.y + K[2] * p.z, iy = K[3] * p.x + K[4] * p.y + K[5] * p.z, iz = K[6] * p.x + K[7] * p.y + K[8] * p.z;
@@ -491,8 +490,16 @@ RB_HD bool cam_project_d(const DevCamera& cam, D3 p0, D3 p1, D2& q0, D2& q1) {
 
 // Screen position -> direction in camera space and its adjoint, fisheye / panorama only (src/camera.h:858-890, :962-1037;
 // the panorama adjoint carries the reference's slips: sin(phi) where sin(theta) belongs, and the fisheye's factor 2).
-RB_HD D3 cam_screen_to_camera_d(const DevCamera& cam, D2 p) {
+RB_HD D3 cam_screen_to_camera_d(const DevCamera& cam, D2 p_) {
     const double pi = 3.14159265358979323846;
+    const D2 p = cam_inverse_distort(cam, p_);
+    if (cam.type == RB_CAMERA_PERSPECTIVE || cam.type == RB_CAMERA_ORTHOGRAPHIC) { // src/camera.h:839-862
+        const double* I = cam.intr_inv;
+        double aspect = double(cam.width) / double(cam.height);
+        double px = (p.x - 0.5) * 2.0, py = (p.y - 0.5) * (-2.0) / aspect, pz = 1.0;
+        D3 d = d3(I[0] * px + I[1] * py + I[2] * pz, I[3] * px + I[4] * py + I[5] * pz, I[6] * px + I[7] * py + I[8] * pz);
+        return cam.type == RB_CAMERA_PERSPECTIVE ? d3(d.x / d.z, d.y / d.z, 1.0) : d3(d.x, d.y, 1.0);
+    }
     if (cam.type == RB_CAMERA_FISHEYE) {
         double x = 2.0 * (p.x - 0.5), y = 2.0 * (p.y - 0.5);
         double phi = atan2(y, x), theta = sqrt(x * x + y * y) * pi / 2.0;
@@ -501,9 +508,28 @@ RB_HD D3 cam_screen_to_camera_d(const DevCamera& cam, D2 p) {
     double theta = pi * p.y, phi = 2 * pi * p.x;
     return d3(cos(phi) * sin(theta), cos(theta), sin(phi) * sin(theta));
 }
-RB_HD D2 d_cam_screen_to_camera_d(const DevCamera& cam, D2 p, D3 d_dir) {
+RB_HD D2 d_cam_screen_to_camera_undistorted_d(const DevCamera& cam, D2 p, D3 d_dir);
+RB_HD D2 d_cam_screen_to_camera_d(const DevCamera& cam, D2 p_, D3 d_dir) {
+    D2 g = d_cam_screen_to_camera_undistorted_d(cam, cam_inverse_distort(cam, p_), d_dir);
+    D2 d_pos = d2(0, 0);
+    d_cam_inverse_distort(cam, p_, g, nullptr, d_pos); // (no parameter gradient on this path, src/camera.h:951-960)
+    return d_pos;
+}
+RB_HD D2 d_cam_screen_to_camera_undistorted_d(const DevCamera& cam, D2 p, D3 d_dir) {
     const double pi = 3.14159265358979323846;
     D2 r;
+    if (cam.type == RB_CAMERA_PERSPECTIVE || cam.type == RB_CAMERA_ORTHOGRAPHIC) { // src/camera.h:908-960
+        const double* I = cam.intr_inv;
+        double aspect = double(cam.width) / double(cam.height);
+        double px = (p.x - 0.5) * 2.0, py = (p.y - 0.5) * (-2.0) / aspect, pz = 1.0;
+        D3 d = d3(I[0] * px + I[1] * py + I[2] * pz, I[3] * px + I[4] * py + I[5] * pz, I[6] * px + I[7] * py + I[8] * pz);
+        D3 dd = cam.type == RB_CAMERA_PERSPECTIVE ? d3(d_dir.x / d.z, d_dir.y / d.z, -(d_dir.x * (d.x / d.z) / d.z + d_dir.y * (d.y / d.z) / d.z))
+                                                  : d3(d_dir.x, d_dir.y, 0.0);
+        double d_px = I[0] * dd.x + I[3] * dd.y + I[6] * dd.z, d_py = I[1] * dd.x + I[4] * dd.y + I[7] * dd.z;
+        r.x = d_px * 2;
+        r.y = d_py * (-2) / aspect;
+        return r;
+    }
     if (cam.type == RB_CAMERA_FISHEYE) {
         double x = 2.0 * (p.x - 0.5), y = 2.0 * (p.y - 0.5);
         double rr = sqrt(x * x + y * y), phi = atan2(y, x), theta = rr * pi / 2.0;
@@ -525,7 +551,7 @@ RB_HD D2 d_cam_screen_to_camera_d(const DevCamera& cam, D2 p, D3 d_dir) {
     return r;
 }
 RB_HD D3 d3_cross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-RB_HD bool cam_is_linear(const DevCamera& cam) { return cam.type == RB_CAMERA_PERSPECTIVE || cam.type == RB_CAMERA_ORTHOGRAPHIC; }
+RB_HD bool cam_is_linear(const DevCamera& cam) { return (cam.type == RB_CAMERA_PERSPECTIVE || cam.type == RB_CAMERA_ORTHOGRAPHIC) && !cam.has_distortion; }
 
 // One primary-edge sample: edge sample index i (seeds the stream like a pixel index), spp sample s.
 // Edge and point on it chosen by primary-edge sample (i, s); false if the sample contributes nothing (edge behind the
@@ -744,4 +770,6 @@ RB_HD void finish_camera(const DevCamera& cam, const double* acc, const rb_dcame
         for (int k = 0; k < 9; k++) out.intrinsic_mat_inv[k] += (float)acc[32 + k];
     if (out.intrinsic_mat)
         for (int k = 0; k < 9; k++) out.intrinsic_mat[k] += (float)acc[41 + k];
+    if (out.distortion)
+        for (int k = 0; k < 8; k++) out.distortion[k] += (float)acc[50 + k];
 }

@@ -400,10 +400,6 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
         rb_set_error("rb_scene_create: unknown camera type");
         return 1;
     }
-    if (c.has_distortion) {
-        rb_set_error("rb_scene_create: camera distortion parameters are not implemented yet (second wave)");
-        return 1;
-    }
     int count = 0;
     RB_CUDA_OK(cudaGetDeviceCount(&count));
     if (count <= 0) {

@@ -736,6 +736,8 @@ inline void host_setup_camera(const rb_camera& c, DevCamera& dc) {
     }
     dc.clip_near = c.clip_near;
     dc.type = c.camera_type;
+    dc.has_distortion = c.has_distortion;
+    for (int i = 0; i < 8; i++) dc.distortion[i] = c.has_distortion ? c.distortion[i] : 0.0;
     dc.vp_beg[0] = c.viewport_beg[0];
     dc.vp_beg[1] = c.viewport_beg[1];
     dc.vp_end[0] = c.viewport_end[0];

@@ -66,6 +66,8 @@ struct DevCamera {
     float clip_near;
     int type;
     int vp_beg[2], vp_end[2];
+    int has_distortion;   // Brown-Conrady lens model, src/camera_distortion.h
+    double distortion[8]; // k1..k6 (radial, rational), p1, p2 (tangential)
 };
 
 // ---- BVH (own LBVH; replaces Embree/OptiX Prime) ----

@@ -44,6 +44,9 @@ CASES = {
     # camera-space film (src/camera.h:154-197,343-498,533-553,669-724; src/edge.cpp:486-592,737-757)
     "fisheye_room_primary_edges": dict(scene="fisheye_room", res=40, spp=4, mb=1, sampler="sobol", edges=1, seed=31, vertex_tol=5e-3),
     "panorama_room_primary_edges": dict(scene="panorama_room", res=40, spp=4, mb=1, sampler="sobol", edges=1, seed=32, vertex_tol=5e-3),
+    # Brown-Conrady lens distortion (src/camera_distortion.h): rays through inverse_distort (Gauss-Newton), projection
+    # through distort, parameter gradients by the implicit function theorem, primary edges on the non-linear path
+    "distort_room_primary_edges": dict(scene="distort_room", res=40, spp=4, mb=1, sampler="sobol", edges=1, seed=34, vertex_tol=5e-3, cam_tol=5e-3),
     # orthographic camera: all primary-edge rays are parallel and graze the silhouettes, the pose gradient is the sum of those
     # few samples -- the reference itself moves by up to 1e-3 between two runs on it (Embree's parallel BVH build)
     "ortho_room_primary_edges": dict(scene="ortho_room", res=40, spp=4, mb=1, sampler="sobol", edges=1, seed=33, vertex_tol=5e-3, cam_tol=2e-2),
@@ -71,7 +74,7 @@ STAT_CASES = {
 def collect_grads(scene):
     out = {}
     cam = scene.camera
-    for k in ("position", "look_at", "up"):
+    for k in ("position", "look_at", "up", "distortion_params"):
         t = getattr(cam, k)
         if t is not None and t.grad is not None:
             out["cam." + k] = t.grad.detach().cpu().clone()

@@ -70,11 +70,15 @@ def uv_sphere(device, radius, center, n_theta=12, n_phi=24, grad=False):
     return (_t(verts, device, grad=grad), _t(idx, device, torch.int32), _t(uvs, device), _t(normals, device))
 
 
-def glossy_room(device, resolution=(128, 128), grad=True, textured=True, nmap=False, sphere_res=(12, 24), camera_type=0):
+def glossy_room(device, resolution=(128, 128), grad=True, textured=True, nmap=False, sphere_res=(12, 24), camera_type=0, distortion=False):
     """Open box (floor, back wall, side wall) with a glossy textured floor, a Phong-shaded sphere and two area lights."""
     g = torch.Generator().manual_seed(7)
     cam = api.Camera(position=torch.tensor([0.3, 1.4, -4.5]), look_at=torch.tensor([0.0, 0.6, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
                      fov=torch.tensor([40.0]), clip_near=1e-2, resolution=resolution)
+    if distortion:  # Brown-Conrady lens model with differentiable parameters and pose
+        cam = api.Camera(position=torch.tensor([0.3, 1.4, -4.5], requires_grad=grad), look_at=torch.tensor([0.0, 0.6, 0.0], requires_grad=grad),
+                         up=torch.tensor([0.0, 1.0, 0.0], requires_grad=grad), fov=torch.tensor([40.0]), clip_near=1e-2, resolution=resolution,
+                         distortion_params=torch.tensor([0.12, -0.05, 0.01, 0.02, 0.01, -0.004, 0.01, -0.015], requires_grad=grad))
     if camera_type == 1:  # orthographic: same pose, the intrinsic matrix scales the film to the room
         cam = api.Camera(position=torch.tensor([0.3, 1.4, -4.5], requires_grad=grad), look_at=torch.tensor([0.0, 0.6, 0.0], requires_grad=grad),
                          up=torch.tensor([0.0, 1.0, 0.0], requires_grad=grad), clip_near=1e-2, resolution=resolution,
@@ -176,6 +180,10 @@ def ortho_room(device, **kw):
     return glossy_room(device, camera_type=1, **kw)
 
 
+def distort_room(device, **kw):
+    return glossy_room(device, distortion=True, **kw)
+
+
 def fisheye_room(device, **kw):
     return glossy_room(device, camera_type=2, **kw)
 
@@ -194,4 +202,4 @@ def nmap_room(device, **kw):
 
 
 SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
-          "nmap_room": nmap_room, "hires_room": hires_room, "ortho_room": ortho_room, "fisheye_room": fisheye_room, "panorama_room": panorama_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}
+          "nmap_room": nmap_room, "hires_room": hires_room, "ortho_room": ortho_room, "distort_room": distort_room, "fisheye_room": fisheye_room, "panorama_room": panorama_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}
