@@ -29,8 +29,13 @@ RB_HD D2 d2(double x, double y) { D2 r; r.x = x; r.y = y; return r; }
 
 // ---- Brown-Conrady lens distortion on normalised screen coordinates (src/camera_distortion.h) ----
 // distort: undistorted -> distorted position; optional forward-mode rows d(out.x)/d(pos), d(out.y)/d(pos).
+// (The bodies are out-of-line: scenes without a lens model -- almost all -- only pay the test of has_distortion.)
+RB_FN D2 cam_distort_impl(const DevCamera& cam, D2 pos, D2* dx_dpos, D2* dy_dpos);
 RB_HD D2 cam_distort(const DevCamera& cam, D2 pos, D2* dx_dpos = nullptr, D2* dy_dpos = nullptr) {
     if (!cam.has_distortion) return pos;
+    return cam_distort_impl(cam, pos, dx_dpos, dy_dpos);
+}
+RB_FN D2 cam_distort_impl(const DevCamera& cam, D2 pos, D2* dx_dpos, D2* dy_dpos) {
     const double* k = cam.distortion;
     const double p0 = k[6], p1 = k[7];
     double x = 2.0 * (pos.x - 0.5), y = 2.0 * (pos.y - 0.5);
@@ -55,11 +60,15 @@ RB_HD D2 cam_distort(const DevCamera& cam, D2 pos, D2* dx_dpos = nullptr, D2* dy
     return d2((xx + 1) / 2, (yy + 1) / 2);
 }
 // Adjoint of cam_distort; d_params (8 doubles, may be null) receives the parameter gradient.
+RB_FN void d_cam_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos);
 RB_HD void d_cam_distort(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
     if (!cam.has_distortion) {
         d_pos = d_out; // (assignment, as in the reference :96-99)
         return;
     }
+    d_cam_distort_impl(cam, pos, d_out, d_params, d_pos);
+}
+RB_FN void d_cam_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
     const double* k = cam.distortion;
     const double p0 = k[6], p1 = k[7];
     double x = 2.0 * (pos.x - 0.5), y = 2.0 * (pos.y - 0.5);
@@ -99,8 +108,12 @@ RB_HD void d_cam_distort(const DevCamera& cam, D2 pos, D2 d_out, double* d_param
     }
 }
 // distorted -> undistorted position by Gauss-Newton (src/camera_distortion.h:171-198)
+RB_FN D2 cam_inverse_distort_impl(const DevCamera& cam, D2 pos);
 RB_HD D2 cam_inverse_distort(const DevCamera& cam, D2 pos) {
     if (!cam.has_distortion) return pos;
+    return cam_inverse_distort_impl(cam, pos);
+}
+RB_FN D2 cam_inverse_distort_impl(const DevCamera& cam, D2 pos) {
     D2 result = pos;
     double err = 0;
     int iter = 0;
@@ -115,11 +128,15 @@ RB_HD D2 cam_inverse_distort(const DevCamera& cam, D2 pos) {
     return result;
 }
 // Adjoint through the implicit function theorem (src/camera_distortion.h:200-258)
+RB_FN void d_cam_inverse_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos);
 RB_HD void d_cam_inverse_distort(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
     if (!cam.has_distortion) {
         d_pos = d_out;
         return;
     }
+    d_cam_inverse_distort_impl(cam, pos, d_out, d_params, d_pos);
+}
+RB_FN void d_cam_inverse_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
     D2 result = cam_inverse_distort(cam, pos);
     D2 fx, fy;
     cam_distort(cam, result, &fx, &fy);

@@ -563,6 +563,31 @@ struct PrimEdgePick {
     D2 upper, lower; // screen positions of the two rays on either side of the edge
     double jacobian; // 1 for linear projections (there the edge length and the gradient of the edge equation cancel)
 };
+// Fisheye / panorama / distorted cameras, out of line (cold for the usual pinhole camera).
+RB_FN bool primary_edge_pick_nonlinear(const DevScene& sc, V3 v0, V3 v1, PrimEdgePick& pk) {
+    // src/edge.cpp:486-592: the edge is a straight segment on the film in CAMERA space, so the
+    // point is sampled there and projected back; the two rays leave the edge plane by an offset shrinking with distance.
+    D3 a = cam_screen_to_camera_d(sc.cam, pk.q0), b = cam_screen_to_camera_d(sc.cam, pk.q1);
+    D3 ab = d3(b.x - a.x, b.y - a.y, b.z - a.z);
+    D3 p3 = d3(a.x + pk.e_t * ab.x, a.y + pk.e_t * ab.y, a.z + pk.e_t * ab.z);
+    pk.ept = cam_to_screen_d(sc.cam, p3);
+    if (!cam_in_screen(sc.cam, mk2((Real)pk.ept.x, (Real)pk.ept.y))) return false;
+    D3 axb = d3_cross(a, b);
+    D3 hn = d3_normalize(axb);
+    D3 l0 = w2c_point(sc.cam, d3(v0.x, v0.y, v0.z)), l1 = w2c_point(sc.cam, d3(v1.x, v1.y, v1.z));
+    D3 el = d3(l0.x + pk.e_t * l1.x, l0.y + pk.e_t * l1.y, l0.z + pk.e_t * l1.z); // (v0 + t v1, as in the reference :527)
+    double offset = 1e-5f / sqrt(el.x * el.x + el.y * el.y + el.z * el.z);
+    pk.upper = cam_to_screen_d(sc.cam, d3_normalize(d3(p3.x + offset * hn.x, p3.y + offset * hn.y, p3.z + offset * hn.z)));
+    pk.lower = cam_to_screen_d(sc.cam, d3_normalize(d3(p3.x - offset * hn.x, p3.y - offset * hn.y, p3.z - offset * hn.z)));
+    D2 d_ept = d_cam_screen_to_camera_d(sc.cam, pk.ept, axb);
+    double dirac_jacobian = 1.0 / sqrt(d_ept.x * d_ept.x + d_ept.y * d_ept.y);
+    const double jac_offset = 1e-6;
+    D2 pd = cam_to_screen_d(sc.cam, d3(a.x + (pk.e_t + jac_offset) * ab.x, a.y + (pk.e_t + jac_offset) * ab.y, a.z + (pk.e_t + jac_offset) * ab.z));
+    // (finite difference divided by the RAY offset, not by jac_offset: src/edge.cpp:577)
+    double line_jacobian = sqrt(rb_sq((pd.x - pk.ept.x) / offset) + rb_sq((pd.y - pk.ept.y) / offset));
+    pk.jacobian = line_jacobian * dirac_jacobian;
+    return true;
+}
 RB_D bool primary_edge_pick(const DevScene& sc, const RenderParams& rp, long long i, int s, int dim_base, Sampler& smp, PrimEdgePick& pk) {
     smp.init(rp.sampler_type, rp.seed + 131071ULL, (int)i, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS,
              (unsigned long long)s * edge_draws_per_sample(sc, rp));
@@ -591,28 +616,7 @@ RB_D bool primary_edge_pick(const DevScene& sc, const RenderParams& rp, long lon
         pk.jacobian = 1;
         return true;
     }
-    // Fisheye / panorama (src/edge.cpp:486-592): the edge is a straight segment on the film in CAMERA space, so the
-    // point is sampled there and projected back; the two rays leave the edge plane by an offset shrinking with distance.
-    D3 a = cam_screen_to_camera_d(sc.cam, pk.q0), b = cam_screen_to_camera_d(sc.cam, pk.q1);
-    D3 ab = d3(b.x - a.x, b.y - a.y, b.z - a.z);
-    D3 p3 = d3(a.x + pk.e_t * ab.x, a.y + pk.e_t * ab.y, a.z + pk.e_t * ab.z);
-    pk.ept = cam_to_screen_d(sc.cam, p3);
-    if (!cam_in_screen(sc.cam, mk2((Real)pk.ept.x, (Real)pk.ept.y))) return false;
-    D3 axb = d3_cross(a, b);
-    D3 hn = d3_normalize(axb);
-    D3 l0 = w2c_point(sc.cam, d3(v0.x, v0.y, v0.z)), l1 = w2c_point(sc.cam, d3(v1.x, v1.y, v1.z));
-    D3 el = d3(l0.x + pk.e_t * l1.x, l0.y + pk.e_t * l1.y, l0.z + pk.e_t * l1.z); // (v0 + t v1, as in the reference :527)
-    double offset = 1e-5f / sqrt(el.x * el.x + el.y * el.y + el.z * el.z);
-    pk.upper = cam_to_screen_d(sc.cam, d3_normalize(d3(p3.x + offset * hn.x, p3.y + offset * hn.y, p3.z + offset * hn.z)));
-    pk.lower = cam_to_screen_d(sc.cam, d3_normalize(d3(p3.x - offset * hn.x, p3.y - offset * hn.y, p3.z - offset * hn.z)));
-    D2 d_ept = d_cam_screen_to_camera_d(sc.cam, pk.ept, axb);
-    double dirac_jacobian = 1.0 / sqrt(d_ept.x * d_ept.x + d_ept.y * d_ept.y);
-    const double jac_offset = 1e-6;
-    D2 pd = cam_to_screen_d(sc.cam, d3(a.x + (pk.e_t + jac_offset) * ab.x, a.y + (pk.e_t + jac_offset) * ab.y, a.z + (pk.e_t + jac_offset) * ab.z));
-    // (finite difference divided by the RAY offset, not by jac_offset: src/edge.cpp:577)
-    double line_jacobian = sqrt(rb_sq((pd.x - pk.ept.x) / offset) + rb_sq((pd.y - pk.ept.y) / offset));
-    pk.jacobian = line_jacobian * dirac_jacobian;
-    return true;
+    return primary_edge_pick_nonlinear(sc, v0, v1, pk);
 }
 // Sort key of a primary-edge sample: (edge, position along the edge).  Samples that are neighbours under this key
 // shoot nearly the same camera rays and scatter into the same two vertices; ~0u = contributes nothing.

@@ -18,14 +18,15 @@ for r in rows[hi + 1:]:
     d[r[mn]] += v
     if r[mn] == 'gpu__time_duration.sum': d['launches'] += 1
 tot = sum(d['gpu__time_duration.sum'] for d in per.values())
-print('%-48s %5s %10s %6s %10s %10s %12s' % ('kernel', 'n', 'time ms', '%', 'dram rd MB', 'dram wr MB', 'warp instr'))
 traffic = {}
+for k, d in per.items():
+    traffic[k] = d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0)
+if len(sys.argv) > 2:
+    json.dump({"source": "ncu --profile-from-start off, tools/one_step.py (one fwd+bwd step of C2), dram__bytes_read.sum + dram__bytes_write.sum summed over "
+                         "the launches of each kernel", "dram_bytes_per_step": traffic}, open(sys.argv[2], 'w'), indent=1)
+print('%-48s %5s %10s %6s %10s %10s %12s' % ('kernel', 'n', 'time ms', '%', 'dram rd MB', 'dram wr MB', 'warp instr'))
 for k, d in sorted(per.items(), key=lambda kv: -kv[1]['gpu__time_duration.sum']):
     t = d['gpu__time_duration.sum'] / 1e6
     rd, wr = d.get('dram__bytes_read.sum', 0), d.get('dram__bytes_write.sum', 0)
     print('%-48s %5d %10.3f %5.1f%% %10.1f %10.1f %12.4g' % (k, d['launches'], t, 100 * d['gpu__time_duration.sum'] / tot, rd / 1e6, wr / 1e6, d.get('smsp__inst_executed.sum', 0)))
-    traffic[k] = rd + wr
 print('total %.3f ms (serialised, cold-cache per-launch times: shares are meaningful, absolutes are not)' % (tot / 1e6))
-if len(sys.argv) > 2:
-    json.dump({"source": "ncu --profile-from-start off, tools/one_step.py (one fwd+bwd step of C2), dram__bytes_read.sum + dram__bytes_write.sum summed over "
-                         "the launches of each kernel", "dram_bytes_per_step": traffic}, open(sys.argv[2], 'w'), indent=1)
