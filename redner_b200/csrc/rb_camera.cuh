@@ -148,7 +148,7 @@ RB_FN void d_cam_inverse_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, do
     d_pos.y -= d_result.y;
 }
 
-RB_HD void cam_sample_primary(const DevCamera& cam, double sx_, double sy_, D3& org, D3& dir) {
+RB_FN void cam_sample_primary_any(const DevCamera& cam, double sx_, double sy_, D3& org, D3& dir) {
     D2 undist = cam_inverse_distort(cam, d2(sx_, sy_)); // (identity without a lens model)
     const double sx = undist.x, sy = undist.y;
     const double* C = cam.c2w;
@@ -197,6 +197,24 @@ RB_HD void cam_sample_primary(const DevCamera& cam, double sx_, double sy_, D3& 
         org = d3(tx * iw, ty * iw, tz * iw);
         dir = d3_normalize(d3(C[2], C[6], C[10]));
     }
+}
+
+// The common camera (pinhole, no lens model) stays inline in every kernel; everything else is one out-of-line call.
+RB_HD void cam_sample_primary(const DevCamera& cam, double sx, double sy, D3& org, D3& dir) {
+    if (cam.type != RB_CAMERA_PERSPECTIVE || cam.has_distortion) {
+        cam_sample_primary_any(cam, sx, sy, org, dir);
+        return;
+    }
+    const double* C = cam.c2w;
+    const double* I = cam.intr_inv;
+    double aspect = double(cam.width) / double(cam.height);
+    double iw = 1.0 / C[15];
+    org = d3(C[3] * iw, C[7] * iw, C[11] * iw);
+    double px = (sx - 0.5) * 2.0, py = (sy - 0.5) * (-2.0) / aspect, pz = 1.0;
+    D3 d = d3(I[0] * px + I[1] * py + I[2] * pz, I[3] * px + I[4] * py + I[5] * pz, I[6] * px + I[7] * py + I[8] * pz);
+    D3 n = d3_normalize(d);
+    D3 w = d3(C[0] * n.x + C[1] * n.y + C[2] * n.z, C[4] * n.x + C[5] * n.y + C[6] * n.z, C[8] * n.x + C[9] * n.y + C[10] * n.z);
+    dir = d3_normalize(w);
 }
 
 RB_HD Ray make_ray(D3 o, D3 d) {
@@ -272,7 +290,7 @@ struct CamAcc {
 
 // Adjoint of cam_sample_primary w.r.t. camera parameters (screen-position gradients are only needed for
 // distortion / screen_gradient_image; the latter is accumulated by the caller through d_screen).
-RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx_, Real sy_, const DRay& d_ray, CamAcc& acc, V2* d_screen_out) {
+RB_DFN void d_cam_sample_primary_any(const DevCamera& cam, Real sx_, Real sy_, const DRay& d_ray, CamAcc& acc, V2* d_screen_out) {
     // With a lens model the ray is generated at the UNDISTORTED position and the adjoint w.r.t. that position flows back
     // through inverse_distort (parameters + original position), src/camera.h:205-206,262-277.
     const D2 spos = d2(sx_, sy_);
@@ -364,6 +382,36 @@ RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx_, Real sy_, const D
     }
 }
 
+RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx, Real sy, const DRay& d_ray, CamAcc& acc, V2* d_screen) {
+    if (cam.type != RB_CAMERA_PERSPECTIVE || cam.has_distortion) {
+        d_cam_sample_primary_any(cam, sx, sy, d_ray, acc, d_screen);
+        return;
+    }
+    M4 C = cam_m4(cam.c2w);
+    M3 I = cam_m3(cam.intr_inv);
+    Real aspect = Real(cam.width) / Real(cam.height);
+    M4 d_C = zero_m4();
+    M3 d_I = zero_m3();
+    V3 pt = mk3((sx - Real(0.5)) * 2, (sy - Real(0.5)) * (-2) / aspect, 1);
+    V3 dir = mul(I, pt);
+    V3 n_dir = normalize(dir);
+    V3 world_dir = xfm_vector(C, n_dir);
+    V3 d_world_dir = d_normalize(world_dir, d_ray.dir);
+    V3 d_n_dir = zero3();
+    d_xfm_vector(C, n_dir, d_world_dir, d_C, d_n_dir);
+    V3 d_dir = d_normalize(dir, d_n_dir);
+    d_outer_acc(d_I, d_dir, pt);
+    V3 d_cam_org = zero3();
+    d_xfm_point(C, zero3(), d_ray.org, d_C, d_cam_org);
+    if (d_screen != nullptr) {
+        V3 d_pt = mul_t(d_dir, I);
+        d_screen->x += d_pt.x * 2;
+        d_screen->y += d_pt.y * (-2 / aspect);
+    }
+    acc.add_intr_inv(d_I);
+    acc.add_c2w(d_C);
+}
+
 // ---- screen projection of a world-space segment (primary edge sampling) ----
 RB_HD V2 cam_to_screen_undistorted(const DevCamera& cam, V3 pt);
 RB_HD V2 cam_to_screen(const DevCamera& cam, V3 pt) {
@@ -413,7 +461,24 @@ RB_HD bool cam_project(const DevCamera& cam, V3 p0, V3 p1, V2& pp0, V2& pp1) {
     pp1 = cam_to_screen(cam, b);
     return true;
 }
+RB_DFN void d_cam_to_screen_any(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt);
 RB_D void d_cam_to_screen(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt) {
+    if (cam.type != RB_CAMERA_PERSPECTIVE || cam.has_distortion) {
+        d_cam_to_screen_any(cam, pt, dx, dy, acc, d_pt);
+        return;
+    }
+    M3 K = cam_m3(cam.intr);
+    Real aspect = Real(cam.width) / Real(cam.height);
+    V3 ip = mul(K, pt);
+    M3 d_K = zero_m3();
+    V2 q = mk2(ip.x / ip.z, ip.y / ip.z);
+    V2 d_q = mk2(dx * Real(0.5), dy * Real(-0.5) * aspect);
+    V3 d_ip = mk3(d_q.x / ip.z, d_q.y / ip.z, -(d_q.x * q.x / ip.z + d_q.y * q.y / ip.z));
+    d_outer_acc(d_K, d_ip, pt);
+    acc.add_intr(d_K);
+    d_pt += mul_t(d_ip, K);
+}
+RB_DFN void d_cam_to_screen_any(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt) {
     if (cam.has_distortion) { // adjoint of the final distort(): parameters, and the undistorted position for the rest
         V2 q = cam_to_screen_undistorted(cam, pt);
         double d_par[8] = {0, 0, 0, 0, 0, 0, 0, 0};

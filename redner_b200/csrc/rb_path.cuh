@@ -142,67 +142,75 @@ RB_D Real mis_power2(Real p_other, Real p_this) {
 // throughput factor for the next vertex.
 RB_D V3 vertex_estimate(const DevScene& sc, const rb_material& mat, const SurfacePoint& sp, V3 wi, Real min_rough, const LightSampleRec& ls,
                         const SurfacePoint& lp, const Isect& bis, const SurfacePoint& bp, V3 bdir, V3& scatter_factor, bool& scatter_ok) {
+    // Both estimators exist for two kinds of light (area light / environment map).  Each first settles the direction and
+    // what the light contributes along it, then ONE bsdf_eval / bsdf_pdf pair serves either kind (the BSDF with its texture
+    // lookups is the bulk of this function's code).
     V3 nee = zero3();
-    if (ls.unoccluded && !ls.isect.valid()) {
-        // environment light (src/path_contribution.cpp:51-67); the lookup is unfiltered (zero ray differential)
-        if (sc.has_envmap) {
-            V3 wo = light_rec_env_dir(ls);
-            Real pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
+    if (ls.unoccluded) {
+        V3 wo = zero3(), Le = zero3();
+        Real pdf_nee = 0, G = 1;
+        bool on = false;
+        if (ls.isect.valid()) { // area light, src/path_contribution.cpp:28-49
+            const rb_shape& lshape = sc.shapes[ls.isect.shape_id];
+            V3 dir = lp.position - sp.position;
+            Real dist_sq = length_sq(dir);
+            wo = dir / sqrt(dist_sq);
+            if (dist_sq > Real(1e-20) && lshape.light_id >= 0) {
+                const DevLight& light = sc.lights[lshape.light_id];
+                if (light.two_sided || dot(-wo, lp.shading_frame.n) > 0) {
+                    G = fabs(dot(wo, lp.geom_normal)) / dist_sq;
+                    pdf_nee = (Real)(sc.light_pmf[lshape.light_id] / sc.light_areas[lshape.light_id]);
+                    Le = mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
+                    on = true;
+                }
+            }
+        } else if (sc.has_envmap) { // environment light (:51-67); the lookup is unfiltered (zero ray differential)
+            wo = light_rec_env_dir(ls);
+            pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
             if (pdf_nee > 0) {
-                V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
-                V3 Le = envmap_eval(sc.env, wo, zero_raydiff());
-                Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
-                nee = (mis_power2(pdf_b, pdf_nee) / pdf_nee) * f * Le;
+                Le = envmap_eval(sc.env, wo, zero_raydiff());
+                on = true;
             }
         }
-    } else if (ls.unoccluded) {
-        const rb_shape& lshape = sc.shapes[ls.isect.shape_id];
-        V3 dir = lp.position - sp.position;
-        Real dist_sq = length_sq(dir);
-        V3 wo = dir / sqrt(dist_sq);
-        if (dist_sq > Real(1e-20) && lshape.light_id >= 0) {
-            const DevLight& light = sc.lights[lshape.light_id];
-            if (light.two_sided || dot(-wo, lp.shading_frame.n) > 0) {
-                V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
-                Real G = fabs(dot(wo, lp.geom_normal)) / dist_sq;
-                Real pdf_nee = (Real)(sc.light_pmf[lshape.light_id] / sc.light_areas[lshape.light_id]);
-                Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough) * G;
-                Real w = mis_power2(pdf_b, pdf_nee);
-                nee = (w * G / pdf_nee) * f * mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
-            }
+        if (on) {
+            V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+            Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough) * G;
+            nee = (mis_power2(pdf_b, pdf_nee) * G / pdf_nee) * f * Le;
         }
     }
     V3 scatter = zero3();
     scatter_factor = zero3();
     scatter_ok = false;
-    if (bis.valid()) {
-        const rb_shape& bshape = sc.shapes[bis.shape_id];
-        V3 dir = bp.position - sp.position;
-        Real dist_sq = length_sq(dir);
-        V3 wo = dir / sqrt(dist_sq);
-        Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
-        if (dist_sq > Real(1e-20) && pdf_b > Real(1e-20)) {
-            V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
-            if (bshape.light_id >= 0) {
-                const DevLight& light = sc.lights[bshape.light_id];
-                if (light.two_sided || dot(-wo, bp.shading_frame.n) > 0) {
-                    Real G = fabs(dot(wo, bp.geom_normal)) / dist_sq;
-                    Real pdf_nee = (Real)(sc.light_pmf[bshape.light_id] * (1.0 / sc.light_areas[bshape.light_id])) / G;
-                    Real w = mis_power2(pdf_nee, pdf_b);
-                    scatter = (w / pdf_b) * f * mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
-                }
-            }
-            scatter_factor = f / pdf_b;
-            scatter_ok = true;
+    const bool hit = bis.valid();
+    if (hit || sc.has_envmap) {
+        V3 wo = bdir;
+        Real dist_sq = 1;
+        if (hit) {
+            V3 dir = bp.position - sp.position;
+            dist_sq = length_sq(dir);
+            wo = dir / sqrt(dist_sq);
         }
-    } else if (sc.has_envmap) {
-        // the BSDF ray left the scene (src/path_contribution.cpp:99-118); bdir is zero when the BSDF sample failed
-        Real pdf_b = bsdf_pdf(mat, sp, wi, bdir, min_rough);
-        if (length_sq(bdir) > 0 && pdf_b > Real(1e-20)) {
-            V3 f = bsdf_eval(mat, sp, wi, bdir, min_rough);
-            V3 Le = envmap_eval(sc.env, bdir, zero_raydiff());
-            Real pdf_nee = envmap_pdf(sc.env, bdir) * (Real)sc.light_pmf[sc.num_lights - 1];
-            scatter = (mis_power2(pdf_nee, pdf_b) / pdf_b) * f * Le;
+        Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
+        // (hit: src/path_contribution.cpp:71-98; miss: :99-118 -- bdir is zero when the BSDF sample failed)
+        if ((hit ? dist_sq > Real(1e-20) : length_sq(wo) > 0) && pdf_b > Real(1e-20)) {
+            V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+            if (hit) {
+                const rb_shape& bshape = sc.shapes[bis.shape_id];
+                if (bshape.light_id >= 0) {
+                    const DevLight& light = sc.lights[bshape.light_id];
+                    if (light.two_sided || dot(-wo, bp.shading_frame.n) > 0) {
+                        Real G = fabs(dot(wo, bp.geom_normal)) / dist_sq;
+                        Real pdf_nee = (Real)(sc.light_pmf[bshape.light_id] * (1.0 / sc.light_areas[bshape.light_id])) / G;
+                        scatter = (mis_power2(pdf_nee, pdf_b) / pdf_b) * f * mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
+                    }
+                }
+                scatter_factor = f / pdf_b;
+                scatter_ok = true;
+            } else {
+                V3 Le = envmap_eval(sc.env, wo, zero_raydiff());
+                Real pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
+                scatter = (mis_power2(pdf_nee, pdf_b) / pdf_b) * f * Le;
+            }
         }
     }
     return nee + scatter;
@@ -342,122 +350,124 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
     V3 wo_b = zero3(), d_f_b = zero3(), d_wo_b = zero3(), dir_b = zero3();
     Real dist_sq_l = 1, d_dist_sq_l = 0, dist_sq_b = 1, d_cos_l = 0;
     V3 d_lv[3] = {zero3(), zero3(), zero3()};
-    // ---- next event estimation (pre)
-    if (cur.light.unoccluded && !cur.light.isect.valid()) {
-        // environment light (src/path_contribution.cpp:295-337): no dependence of the direction on the vertex position
-        if (sc.has_envmap) {
-            V3 wo = light_rec_env_dir(cur.light);
-            Real pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
+    // ---- next event estimation (pre): area light (src/path_contribution.cpp:212-293) or environment map (:295-337).
+    // Direction and light-side quantities first, then ONE bsdf_eval / bsdf_pdf pair for either kind.
+    if (cur.light.unoccluded) {
+        const bool area = cur.light.isect.valid();
+        const Isect& lis = cur.light.isect;
+        SurfacePoint lp = zero_point();
+        V3 wo = zero3(), dir = zero3(), Le = zero3();
+        Real dist_sq = 1, pdf_nee = 0;
+        bool ok = false;
+        if (area) {
+            const rb_shape& lshape = sc.shapes[lis.shape_id];
+            lp = sample_light_triangle(lshape, lis.tri_id, cur.light.uv);
+            dir = lp.position - p;
+            dist_sq = length_sq(dir);
+            wo = dir / sqrt(dist_sq);
+            if (lshape.light_id >= 0) {
+                const DevLight& light = sc.lights[lshape.light_id];
+                if (light.two_sided || dot(-wo, lp.shading_frame.n) > 0) {
+                    Le = mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
+                    pdf_nee = (Real)(sc.light_pmf[lshape.light_id] * (1.0 / sc.light_areas[lshape.light_id]));
+                    ok = true;
+                }
+            }
+        } else if (sc.has_envmap) {
+            wo = light_rec_env_dir(cur.light);
+            pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
             if (pdf_nee > 0) {
-                V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
-                V3 Le = envmap_eval(sc.env, wo, zero_raydiff());
-                Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
-                Real wgt = mis_power2(pdf_b, pdf_nee) / pdf_nee;
-                V3 d_nee = d_contrib * thr;
-                out.d_thr += d_contrib * (wgt * f * Le);
-                RayDiff d_rd0 = zero_raydiff();
-                d_envmap_eval(sc.env, wo, zero_raydiff(), wgt * (d_nee * f), ds.env_values, ds.env_w2e, d_wo_l, d_rd0);
-                on_l = env_l = true;
-                wo_l = wo;
-                d_f_l = wgt * (d_nee * Le);
+                Le = envmap_eval(sc.env, wo, zero_raydiff());
+                ok = true;
             }
         }
-    } else if (cur.light.unoccluded) {
-        const Isect& lis = cur.light.isect;
-        const rb_shape& lshape = sc.shapes[lis.shape_id];
-        SurfacePoint lp = sample_light_triangle(lshape, lis.tri_id, cur.light.uv);
-        V3 dir = lp.position - p;
-        Real dist_sq = length_sq(dir);
-        V3 wo = dir / sqrt(dist_sq);
-        if (lshape.light_id >= 0) {
-            const DevLight& light = sc.lights[lshape.light_id];
-            if (light.two_sided || dot(-wo, lp.shading_frame.n) > 0) {
-                V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+        if (ok) {
+            V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
+            Real pdf_b0 = bsdf_pdf(mat, sp, wi, wo, min_rough);
+            V3 d_nee = d_contrib * thr;
+            if (area) {
+                const rb_shape& lshape = sc.shapes[lis.shape_id];
                 Real cos_l = dot(wo, lp.geom_normal);
                 Real G = fabs(cos_l) / dist_sq;
-                V3 Le = mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
-                Real pdf_nee = (Real)(sc.light_pmf[lshape.light_id] * (1.0 / sc.light_areas[lshape.light_id]));
-                Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough) * G;
-                Real mis = mis_power2(pdf_b, pdf_nee);
-                V3 nee = (mis * G / pdf_nee) * f * Le;
-                V3 d_nee = d_contrib * thr;
-                out.d_thr += d_contrib * nee;
+                Real mis = mis_power2(pdf_b0 * G, pdf_nee);
+                out.d_thr += d_contrib * ((mis * G / pdf_nee) * f * Le);
                 Real wgt = mis / pdf_nee;
                 // derivatives of the MIS weight and of the light-selection pmf are ignored (src/path_contribution.cpp:239)
                 Real d_wgt = G * sum(d_nee * f * Le);
                 Real d_pdf_nee = -d_wgt * wgt / pdf_nee;
                 Real d_G = wgt * sum(d_nee * f * Le);
-                V3 d_Le = wgt * G * (d_nee * f);
                 Real d_area = -d_pdf_nee * pdf_nee / shape_tri_area(lshape, lis.tri_id);
                 d_shape_tri_area(lshape, lis.tri_id, d_area, d_lv);
-                agg_add3(ds.light_intensity[lshape.light_id], d_Le);
+                agg_add3(ds.light_intensity[lshape.light_id], wgt * G * (d_nee * f));
                 d_cos_l = cos_l > 0 ? d_G / dist_sq : -d_G / dist_sq;
-                on_l = true;
-                wo_l = wo;
                 dir_l = dir;
                 dist_sq_l = dist_sq;
                 d_dist_sq_l = -d_G * G / dist_sq;
                 d_f_l = wgt * G * (d_nee * Le);
                 d_wo_l = d_cos_l * lp.geom_normal;
+            } else { // no dependence of the direction on the vertex position
+                Real wgt = mis_power2(pdf_b0, pdf_nee) / pdf_nee;
+                out.d_thr += d_contrib * (wgt * f * Le);
+                RayDiff d_rd0 = zero_raydiff();
+                d_envmap_eval(sc.env, wo, zero_raydiff(), wgt * (d_nee * f), ds.env_values, ds.env_w2e, d_wo_l, d_rd0);
+                env_l = true;
+                d_f_l = wgt * (d_nee * Le);
             }
+            on_l = true;
+            wo_l = wo;
         }
     }
-    // ---- BSDF-sampled continuation (pre)
+    // ---- BSDF-sampled continuation (pre): the ray hit something (:339-518) or left the scene into the map (:520-590)
     SurfacePoint bp;
-    if (nxt != nullptr && nxt->isect.valid()) {
+    if (nxt != nullptr && (nxt->isect.valid() || sc.has_envmap)) {
+        const bool hit = nxt->isect.valid();
         const Isect& bis = nxt->isect;
-        const rb_shape& bshape = sc.shapes[bis.shape_id];
-        RayDiff rd_after;
-        bp = make_surface_point(bshape, bis.tri_id, nxt->ray, nxt->rd_in, rd_after);
-        V3 dir = bp.position - p;
-        Real dist_sq = length_sq(dir);
-        V3 wo = dir / sqrt(dist_sq);
+        V3 wo = nxt->ray.dir, dir = zero3();
+        Real dist_sq = 1;
+        if (hit) {
+            RayDiff rd_after;
+            bp = make_surface_point(sc.shapes[bis.shape_id], bis.tri_id, nxt->ray, nxt->rd_in, rd_after);
+            dir = bp.position - p;
+            dist_sq = length_sq(dir);
+            wo = dir / sqrt(dist_sq);
+        }
         Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
-        if (pdf_b > 0) {
+        if (pdf_b > 0 && (hit || length_sq(wo) > 0)) {
             V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
-            V3 factor = f / pdf_b;
-            out.d_thr += next.d_thr * factor;
-            V3 d_factor = next.d_thr * thr;
-            // the derivative w.r.t. pdf_bsdf is dropped on purpose (src/path_contribution.cpp:369-376)
-            V3 d_f = d_factor / pdf_b;
-            if (bshape.light_id >= 0) {
-                const DevLight& light = sc.lights[bshape.light_id];
-                if (light.two_sided || dot(-wo, bp.shading_frame.n) > 0) {
-                    Real G = fabs(dot(wo, bp.geom_normal)) / dist_sq;
-                    V3 Le = mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
-                    Real pdf_nee = (Real)(sc.light_pmf[bshape.light_id] * (1.0 / sc.light_areas[bshape.light_id])) / G;
-                    Real mis = mis_power2(pdf_nee, pdf_b);
-                    V3 scatter = (mis / pdf_b) * f * Le;
-                    V3 d_scatter = d_contrib * thr;
-                    out.d_thr += d_contrib * scatter;
-                    Real wgt = mis / pdf_b;
-                    d_f += wgt * (d_scatter * Le);
-                    agg_add3(ds.light_intensity[bshape.light_id], wgt * (d_scatter * f));
+            V3 d_scatter = d_contrib * thr;
+            if (hit) {
+                const rb_shape& bshape = sc.shapes[bis.shape_id];
+                out.d_thr += next.d_thr * (f / pdf_b);
+                // the derivative w.r.t. pdf_bsdf is dropped on purpose (src/path_contribution.cpp:369-376)
+                V3 d_f = (next.d_thr * thr) / pdf_b;
+                if (bshape.light_id >= 0) {
+                    const DevLight& light = sc.lights[bshape.light_id];
+                    if (light.two_sided || dot(-wo, bp.shading_frame.n) > 0) {
+                        Real G = fabs(dot(wo, bp.geom_normal)) / dist_sq;
+                        V3 Le = mk3(light.intensity[0], light.intensity[1], light.intensity[2]);
+                        Real pdf_nee = (Real)(sc.light_pmf[bshape.light_id] * (1.0 / sc.light_areas[bshape.light_id])) / G;
+                        Real wgt = mis_power2(pdf_nee, pdf_b) / pdf_b;
+                        out.d_thr += d_contrib * (wgt * f * Le);
+                        d_f += wgt * (d_scatter * Le);
+                        agg_add3(ds.light_intensity[bshape.light_id], wgt * (d_scatter * f));
+                    }
                 }
+                dir_b = dir;
+                dist_sq_b = dist_sq;
+                d_f_b = d_f;
+                d_wo_b = next.d_ray.dir;
+            } else { // nothing flows back into the sampling procedure
+                V3 Le = envmap_eval(sc.env, wo, zero_raydiff());
+                Real pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
+                Real wgt = mis_power2(pdf_nee, pdf_b) / pdf_b;
+                out.d_thr += d_contrib * (wgt * f * Le);
+                RayDiff d_rd0 = zero_raydiff();
+                d_envmap_eval(sc.env, wo, zero_raydiff(), wgt * (d_scatter * f), ds.env_values, ds.env_w2e, d_wo_b, d_rd0);
+                env_b = true;
+                d_f_b = wgt * (d_scatter * Le);
             }
             on_b = true;
             wo_b = wo;
-            dir_b = dir;
-            dist_sq_b = dist_sq;
-            d_f_b = d_f;
-            d_wo_b = next.d_ray.dir;
-        }
-    } else if (nxt != nullptr && sc.has_envmap) {
-        // the BSDF ray left the scene (src/path_contribution.cpp:520-590); nothing flows back into the sampling procedure
-        V3 wo = nxt->ray.dir;
-        Real pdf_b = bsdf_pdf(mat, sp, wi, wo, min_rough);
-        if (length_sq(wo) > 0 && pdf_b > 0) {
-            V3 f = bsdf_eval(mat, sp, wi, wo, min_rough);
-            V3 Le = envmap_eval(sc.env, wo, zero_raydiff());
-            Real pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
-            Real wgt = mis_power2(pdf_nee, pdf_b) / pdf_b;
-            V3 d_scatter = d_contrib * thr;
-            out.d_thr += d_contrib * (wgt * f * Le);
-            RayDiff d_rd0 = zero_raydiff();
-            d_envmap_eval(sc.env, wo, zero_raydiff(), wgt * (d_scatter * f), ds.env_values, ds.env_w2e, d_wo_b, d_rd0);
-            on_b = env_b = true;
-            wo_b = wo;
-            d_f_b = wgt * (d_scatter * Le);
         }
     }
     // ---- shared BSDF adjoint

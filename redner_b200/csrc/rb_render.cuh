@@ -116,7 +116,7 @@ RB_D V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, in
 // Values of every non-radiance, non-id channel at a first hit, at their float offsets in vals[0..nd) (unweighted;
 // src/primary_contribution.cpp:36-253).  Radiance and id slots are left untouched.
 #define RB_MAX_ND 64
-RB_D void channel_values_at_hit(const DevScene& sc, const RenderParams& rp, const Isect& is, const SurfacePoint& sp, const Ray& ray, Real* vals) {
+RB_DFN void channel_values_at_hit(const DevScene& sc, const RenderParams& rp, const Isect& is, const SurfacePoint& sp, const Ray& ray, Real* vals) {
     const rb_shape& shape = sc.shapes[is.shape_id];
     const rb_material& mat = sc.materials[shape.material_id];
     int d = 0;
@@ -160,7 +160,7 @@ RB_D void channel_values_at_hit(const DevScene& sc, const RenderParams& rp, cons
 }
 // Adjoint of channel_values_at_hit (src/primary_contribution.cpp:486-692): d_vals[0..nd) are the (already weighted)
 // adjoints of the channel values; results go to the surface-point adjoint, the ray origin (depth) and the textures.
-RB_D void d_channel_values_at_hit(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const Isect& is, const SurfacePoint& sp, const Ray& ray,
+RB_DFN void d_channel_values_at_hit(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const Isect& is, const SurfacePoint& sp, const Ray& ray,
                                   const Real* d_vals, SurfacePoint& d_sp, V3& d_ray_org) {
     const rb_shape& shape = sc.shapes[is.shape_id];
     const rb_material& mat = sc.materials[shape.material_id];
@@ -441,6 +441,20 @@ RB_HD D3 w2c_point(const DevCamera& cam, D3 p) {
     double iw = 1.0 / w;
     return d3(x * iw, y * iw, z * iw);
 }
+RB_FN D2 cam_to_screen_sphere_d(const DevCamera& cam, D3 p) { // fisheye / panorama, src/camera.h:533-553
+    const double pi = 3.14159265358979323846;
+    D3 d = d3_normalize(p);
+    D2 r;
+    if (cam.type == RB_CAMERA_FISHEYE) {
+        double phi = atan2(d.y, d.x), rr = acos(d.z) * 2.0 / pi;
+        r.x = 0.5 * (-rr * cos(phi) + 1.0);
+        r.y = 0.5 * (-rr * sin(phi) + 1.0);
+    } else {
+        r.x = atan2(d.z, d.x) / (2 * pi);
+        r.y = acos(d.y) / pi;
+    }
+    return r;
+}
 RB_HD D2 cam_to_screen_undistorted_d(const DevCamera& cam, D3 p);
 RB_HD D2 cam_to_screen_d(const DevCamera& cam, D3 p) { return cam_distort(cam, cam_to_screen_undistorted_d(cam, p)); }
 RB_HD D2 cam_to_screen_undistorted_d(const DevCamera& cam, D3 p) {
@@ -448,19 +462,7 @@ RB_HD D2 cam_to_screen_undistorted_d(const DevCamera& cam, D3 p) {
     double aspect = double(cam.width) / double(cam.height);
     double ix = K[0] * p.x + K[1] * p.y + K[2] * p.z, iy = K[3] * p.x + K[4] * p.y + K[5] * p.z, iz = K[6] * p.x + K[7] * p.y + K[8] * p.z;
     D2 r;
-    const double pi = 3.14159265358979323846;
-    if (cam.type == RB_CAMERA_FISHEYE || cam.type == RB_CAMERA_PANORAMA) {
-        D3 d = d3_normalize(p);
-        if (cam.type == RB_CAMERA_FISHEYE) {
-            double phi = atan2(d.y, d.x), rr = acos(d.z) * 2.0 / pi;
-            r.x = 0.5 * (-rr * cos(phi) + 1.0);
-            r.y = 0.5 * (-rr * sin(phi) + 1.0);
-        } else {
-            r.x = atan2(d.z, d.x) / (2 * pi);
-            r.y = acos(d.y) / pi;
-        }
-        return r;
-    }
+    if (cam.type == RB_CAMERA_FISHEYE || cam.type == RB_CAMERA_PANORAMA) return cam_to_screen_sphere_d(cam, p);
     if (cam.type == RB_CAMERA_PERSPECTIVE) {
         r.x = (ix / iz + 1.0) * 0.5;
         r.y = (-(iy / iz) * aspect + 1.0) * 0.5;
@@ -563,6 +565,14 @@ struct PrimEdgePick {
     D2 upper, lower; // screen positions of the two rays on either side of the edge
     double jacobian; // 1 for linear projections (there the edge length and the gradient of the edge equation cancel)
 };
+// Gradients of the edge equation alpha(p) = dot(p, cross(v0_dir, v1_dir)) on the camera-space film w.r.t. the two projected
+// end points and the edge point (src/edge.cpp:737-757), out of line.
+RB_FN void primary_edge_grad_nonlinear(const DevCamera& cam, D2 q0, D2 q1, D2 ept, double* g) {
+    D3 a = cam_screen_to_camera_d(cam, q0), b = cam_screen_to_camera_d(cam, q1), e = cam_screen_to_camera_d(cam, ept);
+    D2 g0 = d_cam_screen_to_camera_d(cam, q0, d3_cross(b, e)), g1 = d_cam_screen_to_camera_d(cam, q1, d3_cross(e, a));
+    D2 ge = d_cam_screen_to_camera_d(cam, q1, d3_cross(a, b)); // (evaluated at v1_ss like the reference, :757)
+    g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y; g[4] = ge.x; g[5] = ge.y;
+}
 // Fisheye / panorama / distorted cameras, out of line (cold for the usual pinhole camera).
 RB_FN bool primary_edge_pick_nonlinear(const DevScene& sc, V3 v0, V3 v1, PrimEdgePick& pk) {
     // src/edge.cpp:486-592: the edge is a straight segment on the film in CAMERA space, so the
@@ -708,13 +718,12 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
         d0x = (Real)(q1.y - ept.y) * contrib; d0y = (Real)(ept.x - q1.x) * contrib;
         d1x = (Real)(ept.y - q0.y) * contrib; d1y = (Real)(q0.x - ept.x) * contrib;
         dex = (Real)(q0.y - q1.y) * contrib; dey = (Real)(q1.x - q0.x) * contrib;
-    } else { // alpha(p) = dot(p, cross(v0_dir, v1_dir)) on the camera-space film (src/edge.cpp:737-757)
-        D3 a = cam_screen_to_camera_d(sc.cam, q0), b = cam_screen_to_camera_d(sc.cam, q1), e = cam_screen_to_camera_d(sc.cam, ept);
-        D2 g0 = d_cam_screen_to_camera_d(sc.cam, q0, d3_cross(b, e)), g1 = d_cam_screen_to_camera_d(sc.cam, q1, d3_cross(e, a));
-        D2 ge = d_cam_screen_to_camera_d(sc.cam, q1, d3_cross(a, b)); // (evaluated at v1_ss like the reference, :757)
-        d0x = (Real)g0.x * contrib; d0y = (Real)g0.y * contrib;
-        d1x = (Real)g1.x * contrib; d1y = (Real)g1.y * contrib;
-        dex = (Real)ge.x * contrib; dey = (Real)ge.y * contrib;
+    } else {
+        double g[6];
+        primary_edge_grad_nonlinear(sc.cam, q0, q1, ept, g);
+        d0x = (Real)g[0] * contrib; d0y = (Real)g[1] * contrib;
+        d1x = (Real)g[2] * contrib; d1y = (Real)g[3] * contrib;
+        dex = (Real)g[4] * contrib; dey = (Real)g[5] * contrib;
     }
     V3 d_v0 = zero3(), d_v1 = zero3();
     d_cam_project(sc.cam, v0, v1, d0x, d0y, d1x, d1y, cam_acc, d_v0, d_v1);
