@@ -274,11 +274,6 @@ class RenderFunction(torch.autograd.Function):
         else:
             args.append(None)
         args += [num_samples, max_bounces, channels, sampler_type]
-        if scene.envmap is not None and use_secondary_edge_sampling and vis and getattr(backend, "__name__", "").startswith("redner_b200"):
-            import warnings
-            warnings.warn("redner_b200: secondary edge sampling is switched off for scenes with an environment map (the reference differentiates "
-                          "sky-side edge rays at stale hit points; see DESIGN.md section 7); interior terms and primary edges are rendered")
-            use_secondary_edge_sampling = False
         args += [use_primary_edge_sampling and vis, use_secondary_edge_sampling and vis]
         args += [sample_pixel_center, device, backend]
         return args

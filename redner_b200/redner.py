@@ -324,6 +324,13 @@ class Scene:  # src/redner.cpp:62-73, src/scene.cpp:63-307
         d.use_gpu = int(bool(use_gpu))
         d.gpu_index = int(gpu_index)
         d.use_primary_edge_sampling = int(bool(use_primary_edge_sampling))
+        if envmap is not None and use_secondary_edge_sampling:
+            # The C ABI rejects this combination (the reference differentiates sky-side edge rays at stale hit points, DESIGN.md
+            # section 7).  pyredner switches both edge samplers on by default, so the shim degrades loudly instead of failing.
+            import warnings
+            warnings.warn("redner_b200: secondary edge sampling is switched off for this scene (environment map); interior terms and "
+                          "primary edges are rendered and differentiated")
+            use_secondary_edge_sampling = False
         d.use_secondary_edge_sampling = int(bool(use_secondary_edge_sampling))
         h = C.c_void_p()
         if lib.rb_scene_create(C.byref(d), C.byref(h)) != 0:
