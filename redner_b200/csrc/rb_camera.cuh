@@ -29,13 +29,13 @@ RB_HD D2 d2(double x, double y) { D2 r; r.x = x; r.y = y; return r; }
 
 // ---- Brown-Conrady lens distortion on normalised screen coordinates (src/camera_distortion.h) ----
 // distort: undistorted -> distorted position; optional forward-mode rows d(out.x)/d(pos), d(out.y)/d(pos).
-// (The bodies are out-of-line: scenes without a lens model -- almost all -- only pay the test of has_distortion.)
-RB_FN D2 cam_distort_impl(const DevCamera& cam, D2 pos, D2* dx_dpos, D2* dy_dpos);
+// (Bodies behind RB_COLD, see rb_math.cuh.)
+RB_COLD D2 cam_distort_impl(const DevCamera& cam, D2 pos, D2* dx_dpos, D2* dy_dpos);
 RB_HD D2 cam_distort(const DevCamera& cam, D2 pos, D2* dx_dpos = nullptr, D2* dy_dpos = nullptr) {
     if (!cam.has_distortion) return pos;
     return cam_distort_impl(cam, pos, dx_dpos, dy_dpos);
 }
-RB_FN D2 cam_distort_impl(const DevCamera& cam, D2 pos, D2* dx_dpos, D2* dy_dpos) {
+RB_COLD D2 cam_distort_impl(const DevCamera& cam, D2 pos, D2* dx_dpos, D2* dy_dpos) {
     const double* k = cam.distortion;
     const double p0 = k[6], p1 = k[7];
     double x = 2.0 * (pos.x - 0.5), y = 2.0 * (pos.y - 0.5);
@@ -60,7 +60,7 @@ RB_FN D2 cam_distort_impl(const DevCamera& cam, D2 pos, D2* dx_dpos, D2* dy_dpos
     return d2((xx + 1) / 2, (yy + 1) / 2);
 }
 // Adjoint of cam_distort; d_params (8 doubles, may be null) receives the parameter gradient.
-RB_FN void d_cam_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos);
+RB_COLD void d_cam_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos);
 RB_HD void d_cam_distort(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
     if (!cam.has_distortion) {
         d_pos = d_out; // (assignment, as in the reference :96-99)
@@ -68,7 +68,7 @@ RB_HD void d_cam_distort(const DevCamera& cam, D2 pos, D2 d_out, double* d_param
     }
     d_cam_distort_impl(cam, pos, d_out, d_params, d_pos);
 }
-RB_FN void d_cam_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
+RB_COLD void d_cam_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
     const double* k = cam.distortion;
     const double p0 = k[6], p1 = k[7];
     double x = 2.0 * (pos.x - 0.5), y = 2.0 * (pos.y - 0.5);
@@ -108,12 +108,12 @@ RB_FN void d_cam_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_
     }
 }
 // distorted -> undistorted position by Gauss-Newton (src/camera_distortion.h:171-198)
-RB_FN D2 cam_inverse_distort_impl(const DevCamera& cam, D2 pos);
+RB_COLD D2 cam_inverse_distort_impl(const DevCamera& cam, D2 pos);
 RB_HD D2 cam_inverse_distort(const DevCamera& cam, D2 pos) {
     if (!cam.has_distortion) return pos;
     return cam_inverse_distort_impl(cam, pos);
 }
-RB_FN D2 cam_inverse_distort_impl(const DevCamera& cam, D2 pos) {
+RB_COLD D2 cam_inverse_distort_impl(const DevCamera& cam, D2 pos) {
     D2 result = pos;
     double err = 0;
     int iter = 0;
@@ -128,7 +128,7 @@ RB_FN D2 cam_inverse_distort_impl(const DevCamera& cam, D2 pos) {
     return result;
 }
 // Adjoint through the implicit function theorem (src/camera_distortion.h:200-258)
-RB_FN void d_cam_inverse_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos);
+RB_COLD void d_cam_inverse_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos);
 RB_HD void d_cam_inverse_distort(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
     if (!cam.has_distortion) {
         d_pos = d_out;
@@ -136,7 +136,7 @@ RB_HD void d_cam_inverse_distort(const DevCamera& cam, D2 pos, D2 d_out, double*
     }
     d_cam_inverse_distort_impl(cam, pos, d_out, d_params, d_pos);
 }
-RB_FN void d_cam_inverse_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
+RB_COLD void d_cam_inverse_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
     D2 result = cam_inverse_distort(cam, pos);
     D2 fx, fy;
     cam_distort(cam, result, &fx, &fy);
@@ -148,7 +148,7 @@ RB_FN void d_cam_inverse_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, do
     d_pos.y -= d_result.y;
 }
 
-RB_FN void cam_sample_primary_any(const DevCamera& cam, double sx_, double sy_, D3& org, D3& dir) {
+RB_COLD void cam_sample_primary_any(const DevCamera& cam, double sx_, double sy_, D3& org, D3& dir) {
     D2 undist = cam_inverse_distort(cam, d2(sx_, sy_)); // (identity without a lens model)
     const double sx = undist.x, sy = undist.y;
     const double* C = cam.c2w;
@@ -199,7 +199,7 @@ RB_FN void cam_sample_primary_any(const DevCamera& cam, double sx_, double sy_, 
     }
 }
 
-// The common camera (pinhole, no lens model) stays inline in every kernel; everything else is one out-of-line call.
+// The common camera (pinhole, no lens model) has its own short path; everything else goes through the general one.
 RB_HD void cam_sample_primary(const DevCamera& cam, double sx, double sy, D3& org, D3& dir) {
     if (cam.type != RB_CAMERA_PERSPECTIVE || cam.has_distortion) {
         cam_sample_primary_any(cam, sx, sy, org, dir);
@@ -290,7 +290,7 @@ struct CamAcc {
 
 // Adjoint of cam_sample_primary w.r.t. camera parameters (screen-position gradients are only needed for
 // distortion / screen_gradient_image; the latter is accumulated by the caller through d_screen).
-RB_DFN void d_cam_sample_primary_any(const DevCamera& cam, Real sx_, Real sy_, const DRay& d_ray, CamAcc& acc, V2* d_screen_out) {
+RB_COLD_D void d_cam_sample_primary_any(const DevCamera& cam, Real sx_, Real sy_, const DRay& d_ray, CamAcc& acc, V2* d_screen_out) {
     // With a lens model the ray is generated at the UNDISTORTED position and the adjoint w.r.t. that position flows back
     // through inverse_distort (parameters + original position), src/camera.h:205-206,262-277.
     const D2 spos = d2(sx_, sy_);
@@ -461,7 +461,7 @@ RB_HD bool cam_project(const DevCamera& cam, V3 p0, V3 p1, V2& pp0, V2& pp1) {
     pp1 = cam_to_screen(cam, b);
     return true;
 }
-RB_DFN void d_cam_to_screen_any(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt);
+RB_COLD_D void d_cam_to_screen_any(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt);
 RB_D void d_cam_to_screen(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt) {
     if (cam.type != RB_CAMERA_PERSPECTIVE || cam.has_distortion) {
         d_cam_to_screen_any(cam, pt, dx, dy, acc, d_pt);
@@ -478,7 +478,7 @@ RB_D void d_cam_to_screen(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc&
     acc.add_intr(d_K);
     d_pt += mul_t(d_ip, K);
 }
-RB_DFN void d_cam_to_screen_any(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt) {
+RB_COLD_D void d_cam_to_screen_any(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt) {
     if (cam.has_distortion) { // adjoint of the final distort(): parameters, and the undistorted position for the rest
         V2 q = cam_to_screen_undistorted(cam, pt);
         double d_par[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -30,6 +30,16 @@ typedef float Real;
 #endif
 #define RB_FN inline __host__ __device__ __noinline__
 #define RB_DFN inline __device__ __noinline__
+// Rarely used features (environment map, non-pinhole cameras, lens model, G-buffer channels).  Measured on B200: taking them
+// out of line made the hot kernels SLOWER (ABI calls spill the caller's live state: k_primary_edge 7.5 -> 7.7 ms, k_bwd_sweep
+// 5.1 -> 5.8 ms, DRAM writes of the step x3), so they are inlined like everything else unless RB_COLD_OUTLINE is defined.
+#ifdef RB_COLD_OUTLINE
+#define RB_COLD RB_FN
+#define RB_COLD_D RB_DFN
+#else
+#define RB_COLD RB_HD
+#define RB_COLD_D RB_D
+#endif
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846

@@ -116,7 +116,7 @@ RB_D V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, in
 // Values of every non-radiance, non-id channel at a first hit, at their float offsets in vals[0..nd) (unweighted;
 // src/primary_contribution.cpp:36-253).  Radiance and id slots are left untouched.
 #define RB_MAX_ND 64
-RB_DFN void channel_values_at_hit(const DevScene& sc, const RenderParams& rp, const Isect& is, const SurfacePoint& sp, const Ray& ray, Real* vals) {
+RB_COLD_D void channel_values_at_hit(const DevScene& sc, const RenderParams& rp, const Isect& is, const SurfacePoint& sp, const Ray& ray, Real* vals) {
     const rb_shape& shape = sc.shapes[is.shape_id];
     const rb_material& mat = sc.materials[shape.material_id];
     int d = 0;
@@ -160,7 +160,7 @@ RB_DFN void channel_values_at_hit(const DevScene& sc, const RenderParams& rp, co
 }
 // Adjoint of channel_values_at_hit (src/primary_contribution.cpp:486-692): d_vals[0..nd) are the (already weighted)
 // adjoints of the channel values; results go to the surface-point adjoint, the ray origin (depth) and the textures.
-RB_DFN void d_channel_values_at_hit(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const Isect& is, const SurfacePoint& sp, const Ray& ray,
+RB_COLD_D void d_channel_values_at_hit(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const Isect& is, const SurfacePoint& sp, const Ray& ray,
                                   const Real* d_vals, SurfacePoint& d_sp, V3& d_ray_org) {
     const rb_shape& shape = sc.shapes[is.shape_id];
     const rb_material& mat = sc.materials[shape.material_id];
@@ -441,7 +441,7 @@ RB_HD D3 w2c_point(const DevCamera& cam, D3 p) {
     double iw = 1.0 / w;
     return d3(x * iw, y * iw, z * iw);
 }
-RB_FN D2 cam_to_screen_sphere_d(const DevCamera& cam, D3 p) { // fisheye / panorama, src/camera.h:533-553
+RB_COLD D2 cam_to_screen_sphere_d(const DevCamera& cam, D3 p) { // fisheye / panorama, src/camera.h:533-553
     const double pi = 3.14159265358979323846;
     D3 d = d3_normalize(p);
     D2 r;
@@ -566,15 +566,15 @@ struct PrimEdgePick {
     double jacobian; // 1 for linear projections (there the edge length and the gradient of the edge equation cancel)
 };
 // Gradients of the edge equation alpha(p) = dot(p, cross(v0_dir, v1_dir)) on the camera-space film w.r.t. the two projected
-// end points and the edge point (src/edge.cpp:737-757), out of line.
-RB_FN void primary_edge_grad_nonlinear(const DevCamera& cam, D2 q0, D2 q1, D2 ept, double* g) {
+// end points and the edge point (src/edge.cpp:737-757).
+RB_COLD void primary_edge_grad_nonlinear(const DevCamera& cam, D2 q0, D2 q1, D2 ept, double* g) {
     D3 a = cam_screen_to_camera_d(cam, q0), b = cam_screen_to_camera_d(cam, q1), e = cam_screen_to_camera_d(cam, ept);
     D2 g0 = d_cam_screen_to_camera_d(cam, q0, d3_cross(b, e)), g1 = d_cam_screen_to_camera_d(cam, q1, d3_cross(e, a));
     D2 ge = d_cam_screen_to_camera_d(cam, q1, d3_cross(a, b)); // (evaluated at v1_ss like the reference, :757)
     g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y; g[4] = ge.x; g[5] = ge.y;
 }
-// Fisheye / panorama / distorted cameras, out of line (cold for the usual pinhole camera).
-RB_FN bool primary_edge_pick_nonlinear(const DevScene& sc, V3 v0, V3 v1, PrimEdgePick& pk) {
+// Fisheye / panorama / distorted cameras (cold for the usual pinhole camera).
+RB_COLD bool primary_edge_pick_nonlinear(const DevScene& sc, V3 v0, V3 v1, PrimEdgePick& pk) {
     // src/edge.cpp:486-592: the edge is a straight segment on the film in CAMERA space, so the
     // point is sampled there and projected back; the two rays leave the edge plane by an offset shrinking with distance.
     D3 a = cam_screen_to_camera_d(sc.cam, pk.q0), b = cam_screen_to_camera_d(sc.cam, pk.q1);
