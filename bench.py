@@ -16,7 +16,7 @@ differentiable path tracer.  metric = fwd+bwd megasamples/s = W*H*spp / (t_forwa
   e2e    the same metric through the public API (redner_b200.api.RenderFunction) starting from HOST tensors in pinned
          memory: host->device copies of every scene tensor, scene construction, forward, loss, backward and the
          device->host read of the loss and of all gradients are inside the timed region;
-  roofline      dominant kernel (k_backward), algorithmic bytes of SURVEY.md section 8(d) over its CUDA-event duration;
+  roofline      dominant kernel / stage of the step, algorithmic bytes of SURVEY.md section 8(d) over its CUDA-event duration;
   cpu_baseline  the unmodified reference (oracle/_ref, CPU/Embree, all host cores) on a bounded sample of the same
                 workload (rank 0, N = 1 only).
 

@@ -21,8 +21,8 @@ RB_D void rb_red_add(float* addr, float v) { atomicAdd(addr, v); } // result unu
 // reconverged, __activemask() degenerates to single lanes and every lane issues its own atomics (measured: 7x slower).
 // The peers of one address form a linked list in lane order; pointer doubling turns every lane's value into the
 // suffix sum of its list in ceil(log2 n) rounds, so the lowest lane ends with the group total.  One code path for
-// every group shape and no __fns(): the previous rank-based tree made this helper ~45% of k_backward's 1.6 MB of
-// SASS, which then ran instruction-fetch bound (profiles/r01_ncu_k_backward_summary.txt).
+// every group shape and no __fns(): the previous rank-based tree made this helper ~45% of the (then fused) backward kernel's 1.6 MB of
+// SASS, which then ran instruction-fetch bound (profiles/r01_ncu_fused_k_backward_summary.txt).
 RB_D void warp_agg_add3(float* addr, float x, float y, float z) {
     unsigned active = __activemask();
     unsigned peers = __match_any_sync(active, (unsigned long long)addr);

@@ -1,15 +1,17 @@
 // Render kernels and the rb_render driver (reference: render(), src/pathtracer.cpp:177-958).
 //
-// Execution model.  The reference runs a host-driven wavefront: ~20 launches and 2 host syncs per bounce per
-// sample, with every per-path field (5.5 - 9.4 KB/pixel in double) streamed through managed memory between
-// stage functors.  Here the whole per-sample pipeline is ONE persistent kernel per pass:
-//   k_forward        camera sample -> primary hit -> emission -> bounce loop -> pixel
-//   k_backward       forward replay (compact per-vertex records, L2-resident) -> reverse sweep over the path with
-//                    the hand-derived adjoints -> first-hit / camera adjoint   [+ secondary edge sampling]
-//   k_primary_edge   one thread per primary-edge sample: edge pick, two offset rays, two full sub-paths, Eq. 8
-// A warp owns 32/L pixels with L lanes per pixel (L = min(32, 2^floor(log2 spp))); lanes of a pixel are its
+// Execution model.  The reference runs a host-driven wavefront: ~20 launches and 2 host syncs per
+// bounce per sample, with every per-path field (5.5 - 9.4 KB/pixel in double) streamed through managed memory between
+// stage functors.  Here a path lives in registers inside a kernel and only a 128-byte record per path vertex crosses kernels:
+//   forward    k_forward / k_forward_channels   camera sample -> primary hit -> emission -> bounce loop -> pixel
+//   backward   per band of samples:  k_bwd_trace (primal replay, records) -> scan + k_bwd_compact (path / vertex lists)
+//              -> k_bwd_sec_pick -> radix sort by edge -> k_bwd_sec_shade (boundary terms) -> k_bwd_sweep (reverse sweep,
+//              first-hit and camera adjoints);  then k_prim_keys -> radix sort -> k_primary_edge;  k_finish_camera
+// Every kernel is small enough for the GPC instruction cache and walks the stages of a sample block-synchronously
+// (RB_PHASE_SYNC): a fused megakernel of the same code ran instruction-fetch bound at 6 % issue utilisation.
+// Forward: a warp owns 32/L pixels with L lanes per pixel (L = min(32, 2^floor(log2 spp))); lanes of a pixel are its
 // samples, so rays of a warp are coherent in the BVH, the pixel is reduced with shuffles and written by one lane
-// without atomics (deterministic image), and gradient atomics are aggregated per warp before they reach L2.
+// without atomics (deterministic image).  Gradient atomics are aggregated per warp before they reach L2.
 // The per-sample logic itself lives in rb_render.cuh.
 #include <cuda_runtime.h>
 
@@ -43,7 +45,7 @@
 #define RB_BAND_BYTES (1ULL << 30) // scratch budget of one backward band (records + lists)
 #endif
 #ifndef RB_MIN_BLOCKS_BWD
-#define RB_MIN_BLOCKS_BWD 4
+#define RB_MIN_BLOCKS_BWD 4 // k_primary_edge
 #endif
 
 // j-th owned row -> viewport row, for the round-robin stripe partition
@@ -471,7 +473,7 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
     RB_CUDA_OK(cudaGetDevice(&prev));
     RB_CUDA_OK(cudaSetDevice(scene->device));
     cudaStream_t stream = (cudaStream_t)stream_;
-    // per-kernel CUDA events on the render stream: [0] start, [1] after k_forward, [2] after k_backward,
+    // per-kernel CUDA events on the render stream: [0] start, [1] after k_forward, [2] after the backward bands,
     // [3] after k_primary_edge, [4] after k_finish_camera
     cudaEvent_t ev[5];
     for (int i = 0; i < 5; i++) RB_CUDA_OK(cudaEventCreate(&ev[i]));

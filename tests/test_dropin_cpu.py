@@ -47,3 +47,37 @@ def test_unmodified_pyredner_runs_on_the_dropin_module():
     last = out.stdout.strip().splitlines()[-1]
     # on a CPU-only machine the call must arrive at rb_scene_create and be refused loudly; on a GPU box it renders
     assert last.startswith("RENDERED") or ("ABI-ERROR" in last and "no CPU path" in last), last
+
+
+ENV_SCRIPT = r'''
+import sys, types
+sys.path.insert(0, %(dropin)r)
+sys.path.insert(0, %(ref)r)
+sys.path.insert(0, %(root)r)
+for name in ("skimage", "skimage.io", "skimage.transform", "imageio"):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules["skimage"].io = sys.modules["skimage.io"]
+sys.modules["skimage"].transform = sys.modules["skimage.transform"]
+import torch, pyredner
+from redner_b200 import api
+g = torch.Generator().manual_seed(3)
+sky = 0.1 + 2.0 * torch.rand(12, 24, 3, generator=g)
+e2w = torch.tensor([[0.8, 0.0, 0.6, 0.0], [0.0, 1.0, 0.0, 0.0], [-0.6, 0.0, 0.8, 0.0], [0.0, 0.0, 0.0, 1.0]])
+pyredner.set_use_gpu(False)
+a = pyredner.EnvironmentMap(sky.clone(), e2w.clone())
+b = api.EnvironmentMap(sky.clone(), e2w.clone())
+assert torch.equal(a.sample_cdf_xs, b.sample_cdf_xs) and torch.equal(a.sample_cdf_ys, b.sample_cdf_ys), "sampling tables differ"
+assert abs(a.pdf_norm - b.pdf_norm) <= 1e-12 * abs(a.pdf_norm), (a.pdf_norm, b.pdf_norm)
+assert torch.equal(a.world_to_env, b.world_to_env)
+assert len(a.values.mipmap) == len(b.values.mipmap) and all(torch.allclose(x, y, atol=1e-7) for x, y in zip(a.values.mipmap, b.values.mipmap))
+print("ENVMAP-TABLES-OK")
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pyredner")), reason="reference checkout not present")
+def test_envmap_preprocessing_matches_pyredner():
+    """api.EnvironmentMap builds the importance-sampling tables, pdf normalisation and mip pyramid that the reference's Python
+    layer hands to the native EnvironmentMap (pyredner/envmap.py:36-61, pyredner/texture.py)."""
+    code = ENV_SCRIPT % {"dropin": os.path.join(ROOT, "redner_b200", "dropin"), "ref": REF, "root": ROOT}
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ENVMAP-TABLES-OK" in out.stdout, (out.stdout[-500:], out.stderr[-1500:])

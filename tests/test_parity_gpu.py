@@ -90,6 +90,25 @@ def test_band_size_does_not_change_gradients(rb, dev, monkeypatch):
         assert pu.rel_l2(g_many[k].numpy(), g_one[k].numpy()) < 1e-5, k
 
 
+def test_reference_intersection_known_answer(rb, dev):
+    """The reference's own known-answer test for the closest-hit query (test_scene_intersect, src/scene.cpp:761-848): triangle
+    (-1,0,1), (1,0,1), (0,1,1); the ray from the origin along +z hits shape 0 / triangle 0 at (0, 0, 1), the ray along -z hits
+    nothing.  Driven through the public boundary: a one-pixel pinhole camera at the origin and the G-buffer channels."""
+    tri = api.Shape(torch.tensor([[-1.0, 0.0, 1.0], [1.0, 0.0, 1.0], [0.0, 1.0, 1.0]], device=dev), torch.tensor([[0, 1, 2]], dtype=torch.int32, device=dev), 0)
+    mat = api.Material(diffuse_reflectance=torch.tensor([0.5, 0.5, 0.5], device=dev))
+    chans = [rb.channels.alpha, rb.channels.position, rb.channels.shape_id, rb.channels.triangle_id, rb.channels.depth]
+    for look_z, hit in ((1.0, True), (-1.0, False)):
+        cam = api.Camera(position=torch.tensor([0.0, 1e-3, 0.0]), look_at=torch.tensor([0.0, 1e-3, look_z]), up=torch.tensor([0.0, 1.0, 0.0]),
+                         fov=torch.tensor([1.0]), clip_near=1e-4, resolution=(1, 1))
+        sc = api.Scene(cam, [tri], [mat], [])
+        args = api.RenderFunction.serialize_scene(sc, 1, 0, channels=chans, device=dev, backend=rb, sample_pixel_center=True)
+        px = api.RenderFunction.apply(1, *args).cpu().numpy()[0, 0]
+        if hit:
+            assert px[0] == 1.0 and np.allclose(px[1:4], [0.0, 1e-3, 1.0], atol=1e-6) and px[4] == 0.0 and px[5] == 0.0 and abs(px[6] - 1.0) < 1e-6
+        else:
+            assert np.all(px == 0.0)
+
+
 def test_gbuffer_backward_without_radiance_skips_path_tracing(rb, dev):
     """Deferred set-up (no radiance channel): gradients flow through the first hit and the primary edges only; the
     boundary (secondary-edge) stage and the bounce replay must not run, whatever max_bounces says."""

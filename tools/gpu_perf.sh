@@ -4,7 +4,7 @@
 # usage: tools/gpu_perf.sh [kernel-regex-for-ncu|none]
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-KREGEX=${1:-k_backward}
+KREGEX=${1:-k_primary_edge}
 nvidia-smi -L
 echo "=== variants (per-stage ms: fwd | bwd | primary edge | camera)"
 for l in "" redner_b200/_variants/*.so; do
