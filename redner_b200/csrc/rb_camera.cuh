@@ -32,7 +32,7 @@ RB_HD D2 d2(double x, double y) { D2 r; r.x = x; r.y = y; return r; }
 // (Bodies behind RB_COLD, see rb_math.cuh.)
 RB_COLD D2 cam_distort_impl(const DevCamera& cam, D2 pos, D2* dx_dpos, D2* dy_dpos);
 RB_HD D2 cam_distort(const DevCamera& cam, D2 pos, D2* dx_dpos = nullptr, D2* dy_dpos = nullptr) {
-    if (!cam.has_distortion) return pos;
+    if (!RB_CAM_DISTORT(cam)) return pos;
     return cam_distort_impl(cam, pos, dx_dpos, dy_dpos);
 }
 RB_COLD D2 cam_distort_impl(const DevCamera& cam, D2 pos, D2* dx_dpos, D2* dy_dpos) {
@@ -62,7 +62,7 @@ RB_COLD D2 cam_distort_impl(const DevCamera& cam, D2 pos, D2* dx_dpos, D2* dy_dp
 // Adjoint of cam_distort; d_params (8 doubles, may be null) receives the parameter gradient.
 RB_COLD void d_cam_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos);
 RB_HD void d_cam_distort(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
-    if (!cam.has_distortion) {
+    if (!RB_CAM_DISTORT(cam)) {
         d_pos = d_out; // (assignment, as in the reference :96-99)
         return;
     }
@@ -110,7 +110,7 @@ RB_COLD void d_cam_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* 
 // distorted -> undistorted position by Gauss-Newton (src/camera_distortion.h:171-198)
 RB_COLD D2 cam_inverse_distort_impl(const DevCamera& cam, D2 pos);
 RB_HD D2 cam_inverse_distort(const DevCamera& cam, D2 pos) {
-    if (!cam.has_distortion) return pos;
+    if (!RB_CAM_DISTORT(cam)) return pos;
     return cam_inverse_distort_impl(cam, pos);
 }
 RB_COLD D2 cam_inverse_distort_impl(const DevCamera& cam, D2 pos) {
@@ -130,7 +130,7 @@ RB_COLD D2 cam_inverse_distort_impl(const DevCamera& cam, D2 pos) {
 // Adjoint through the implicit function theorem (src/camera_distortion.h:200-258)
 RB_COLD void d_cam_inverse_distort_impl(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos);
 RB_HD void d_cam_inverse_distort(const DevCamera& cam, D2 pos, D2 d_out, double* d_params, D2& d_pos) {
-    if (!cam.has_distortion) {
+    if (!RB_CAM_DISTORT(cam)) {
         d_pos = d_out;
         return;
     }
@@ -201,7 +201,7 @@ RB_COLD void cam_sample_primary_any(const DevCamera& cam, double sx_, double sy_
 
 // The common camera (pinhole, no lens model) has its own short path; everything else goes through the general one.
 RB_HD void cam_sample_primary(const DevCamera& cam, double sx, double sy, D3& org, D3& dir) {
-    if (cam.type != RB_CAMERA_PERSPECTIVE || cam.has_distortion) {
+    if (RB_CAM_GENERAL(cam)) {
         cam_sample_primary_any(cam, sx, sy, org, dir);
         return;
     }
@@ -297,7 +297,7 @@ RB_COLD_D void d_cam_sample_primary_any(const DevCamera& cam, Real sx_, Real sy_
     const D2 undist = cam_inverse_distort(cam, spos);
     const Real sx = (Real)undist.x, sy = (Real)undist.y;
     V2 d_und = zero2();
-    V2* d_screen = (cam.has_distortion || d_screen_out != nullptr) ? &d_und : nullptr;
+    V2* d_screen = (RB_CAM_DISTORT(cam) || d_screen_out != nullptr) ? &d_und : nullptr;
     M4 C = cam_m4(cam.c2w);
     M3 I = cam_m3(cam.intr_inv);
     Real aspect = Real(cam.width) / Real(cam.height);
@@ -373,8 +373,8 @@ RB_COLD_D void d_cam_sample_primary_any(const DevCamera& cam, Real sx_, Real sy_
     if (d_screen != nullptr) {
         double d_par[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         D2 d_pos = d2(0, 0);
-        d_cam_inverse_distort(cam, spos, d2(d_und.x, d_und.y), cam.has_distortion ? d_par : nullptr, d_pos);
-        if (cam.has_distortion) acc.add_distortion(d_par);
+        d_cam_inverse_distort(cam, spos, d2(d_und.x, d_und.y), RB_CAM_DISTORT(cam) ? d_par : nullptr, d_pos);
+        if (RB_CAM_DISTORT(cam)) acc.add_distortion(d_par);
         if (d_screen_out != nullptr) {
             d_screen_out->x += (Real)d_pos.x;
             d_screen_out->y += (Real)d_pos.y;
@@ -383,7 +383,7 @@ RB_COLD_D void d_cam_sample_primary_any(const DevCamera& cam, Real sx_, Real sy_
 }
 
 RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx, Real sy, const DRay& d_ray, CamAcc& acc, V2* d_screen) {
-    if (cam.type != RB_CAMERA_PERSPECTIVE || cam.has_distortion) {
+    if (RB_CAM_GENERAL(cam)) {
         d_cam_sample_primary_any(cam, sx, sy, d_ray, acc, d_screen);
         return;
     }
@@ -416,24 +416,24 @@ RB_D void d_cam_sample_primary(const DevCamera& cam, Real sx, Real sy, const DRa
 RB_HD V2 cam_to_screen_undistorted(const DevCamera& cam, V3 pt);
 RB_HD V2 cam_to_screen(const DevCamera& cam, V3 pt) {
     V2 q = cam_to_screen_undistorted(cam, pt);
-    if (!cam.has_distortion) return q;
+    if (!RB_CAM_DISTORT(cam)) return q;
     D2 r = cam_distort(cam, d2(q.x, q.y));
     return mk2((Real)r.x, (Real)r.y);
 }
 RB_HD V2 cam_to_screen_undistorted(const DevCamera& cam, V3 pt) {
-    if (cam.type == RB_CAMERA_FISHEYE) { // src/camera.h:533-543
+    if (RB_CAM_GENERAL(cam) && cam.type == RB_CAMERA_FISHEYE) { // src/camera.h:533-543
         V3 d = normalize(pt);
         Real phi = atan2(d.y, d.x), r = acos(d.z) * 2 / Real(RB_PI);
         return mk2(Real(0.5) * (-r * cos(phi) + 1), Real(0.5) * (-r * sin(phi) + 1));
     }
-    if (cam.type == RB_CAMERA_PANORAMA) { // src/camera.h:544-553
+    if (RB_CAM_GENERAL(cam) && cam.type == RB_CAMERA_PANORAMA) { // src/camera.h:544-553
         V3 d = normalize(pt);
         return mk2(atan2(d.z, d.x) / Real(2 * RB_PI), acos(d.y) / Real(RB_PI));
     }
     M3 K = cam_m3(cam.intr);
     Real aspect = Real(cam.width) / Real(cam.height);
     V3 ip = mul(K, pt);
-    if (cam.type == RB_CAMERA_PERSPECTIVE) {
+    if (!RB_CAM_GENERAL(cam) || cam.type == RB_CAMERA_PERSPECTIVE) {
         Real x = (ip.x / ip.z + 1) * Real(0.5);
         Real y = (-(ip.y / ip.z) * aspect + 1) * Real(0.5);
         return mk2(x, y);
@@ -463,7 +463,7 @@ RB_HD bool cam_project(const DevCamera& cam, V3 p0, V3 p1, V2& pp0, V2& pp1) {
 }
 RB_COLD_D void d_cam_to_screen_any(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt);
 RB_D void d_cam_to_screen(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt) {
-    if (cam.type != RB_CAMERA_PERSPECTIVE || cam.has_distortion) {
+    if (RB_CAM_GENERAL(cam)) {
         d_cam_to_screen_any(cam, pt, dx, dy, acc, d_pt);
         return;
     }
@@ -479,7 +479,7 @@ RB_D void d_cam_to_screen(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc&
     d_pt += mul_t(d_ip, K);
 }
 RB_COLD_D void d_cam_to_screen_any(const DevCamera& cam, V3 pt, Real dx, Real dy, CamAcc& acc, V3& d_pt) {
-    if (cam.has_distortion) { // adjoint of the final distort(): parameters, and the undistorted position for the rest
+    if (RB_CAM_DISTORT(cam)) { // adjoint of the final distort(): parameters, and the undistorted position for the rest
         V2 q = cam_to_screen_undistorted(cam, pt);
         double d_par[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         D2 d_q = d2(0, 0);
@@ -576,7 +576,7 @@ RB_D void d_cam_project(const DevCamera& cam, V3 p0, V3 p1, Real dp0x, Real dp0y
 RB_HD bool cam_in_screen(const DevCamera& cam, V2 pt) {
     int xi = int(pt.x * cam.width), yi = int(pt.y * cam.height);
     if (xi < cam.vp_beg[0] || xi >= cam.vp_end[0] || yi < cam.vp_beg[1] || yi >= cam.vp_end[1]) return false;
-    if (cam.type == RB_CAMERA_FISHEYE) return rb_sq(pt.x - Real(0.5)) + rb_sq(pt.y - Real(0.5)) < Real(0.25); // src/camera.h:1059-1066
+    if (RB_CAM_GENERAL(cam) && cam.type == RB_CAMERA_FISHEYE) return rb_sq(pt.x - Real(0.5)) + rb_sq(pt.y - Real(0.5)) < Real(0.25); // src/camera.h:1059-1066
     return pt.x >= 0 && pt.x < 1 && pt.y >= 0 && pt.y < 1;
 }
 RB_HD bool ray_is_null(const Ray& r) { return r.dir.x == 0 && r.dir.y == 0 && r.dir.z == 0; }

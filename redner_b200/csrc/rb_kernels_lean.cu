@@ -1,0 +1,67 @@
+// Feature-free instantiation of the render kernels: the very same source (rb_kernels_body.cuh and every per-sample header)
+// compiled with RB_LEAN, i.e. with "no environment map, pinhole camera without lens model, channels == [radiance]" as
+// compile-time facts, inside namespace rb_lean.  rb_render launches these when the scene and the options allow it; the
+// general kernels in rb_kernels.cu cover everything else.  Measured on C2: see DESIGN.md section 6.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/redner_b200.h"
+#include "rb_lean_api.h"
+
+#define RB_LEAN 1
+namespace rb_lean {
+#include "rb_render.cuh"
+#include "rb_kernels_body.cuh"
+} // namespace rb_lean
+
+namespace rb_lean_api {
+using rb_lean::DevScene;
+using rb_lean::KernelArgs;
+int grid(Kernel k, int device) {
+    const void* f = nullptr;
+    int block = RB_BLOCK;
+    switch (k) {
+        case K_FORWARD: f = (const void*)rb_lean::k_forward; break;
+        case K_BWD_TRACE: f = (const void*)rb_lean::k_bwd_trace; break;
+        case K_BWD_SEC_PICK: f = (const void*)rb_lean::k_bwd_sec_pick; break;
+        case K_BWD_SEC_SHADE: f = (const void*)rb_lean::k_bwd_sec_shade; break;
+        case K_BWD_SWEEP: f = (const void*)rb_lean::k_bwd_sweep; break;
+        case K_PRIM_KEYS: f = (const void*)rb_lean::k_prim_keys; block = 256; break;
+        case K_PRIMARY_EDGE: f = (const void*)rb_lean::k_primary_edge; break;
+    }
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, block, 0);
+    return sms * (per_sm < 1 ? 1 : per_sm);
+}
+void forward(const void* sc, const void* ka, int grid, cudaStream_t stream) {
+    rb_lean::k_forward<<<grid, RB_BLOCK, 0, stream>>>(*(const DevScene*)sc, *(const KernelArgs*)ka);
+}
+void bwd_trace(const void* sc, const void* ka, int grid, cudaStream_t stream) {
+    rb_lean::k_bwd_trace<<<grid, RB_BLOCK, 0, stream>>>(*(const DevScene*)sc, *(const KernelArgs*)ka);
+}
+void bwd_sec_pick(const void* sc, const void* ka, int grid, cudaStream_t stream) {
+    rb_lean::k_bwd_sec_pick<<<grid, RB_BLOCK, 0, stream>>>(*(const DevScene*)sc, *(const KernelArgs*)ka);
+}
+void bwd_sec_shade(const void* sc, const void* ka, int grid, cudaStream_t stream) {
+    rb_lean::k_bwd_sec_shade<<<grid, RB_BLOCK, 0, stream>>>(*(const DevScene*)sc, *(const KernelArgs*)ka);
+}
+void bwd_sweep(const void* sc, const void* ka, int grid, cudaStream_t stream) {
+    rb_lean::k_bwd_sweep<<<grid, RB_BLOCK, 0, stream>>>(*(const DevScene*)sc, *(const KernelArgs*)ka);
+}
+void prim_keys(const void* sc, const void* ka, int dim_base, long long t0, int n, unsigned* keys, unsigned* vals, int grid, cudaStream_t stream) {
+    rb_lean::k_prim_keys<<<grid, 256, 0, stream>>>(*(const DevScene*)sc, *(const KernelArgs*)ka, dim_base, t0, n, keys, vals);
+}
+void primary_edge(const void* sc, const void* ka, int dim_base, long long t0, int n, const unsigned* keys, const unsigned* vals, int grid, cudaStream_t stream) {
+    rb_lean::k_primary_edge<<<grid, RB_BLOCK, 0, stream>>>(*(const DevScene*)sc, *(const KernelArgs*)ka, dim_base, t0, n, keys, vals);
+}
+} // namespace rb_lean_api

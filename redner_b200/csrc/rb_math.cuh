@@ -41,6 +41,21 @@ typedef float Real;
 #define RB_COLD_D RB_D
 #endif
 
+// Feature tests.  rb_kernels_lean.cu compiles the same kernels a second time with RB_LEAN defined: no environment map, pinhole
+// camera without lens model, channels == [radiance] -- the configuration of nearly every optimisation loop.  There the
+// tests are compile-time constants and the rarely used code disappears from the instruction stream.
+#ifdef RB_LEAN
+#define RB_ENVMAP(sc) false
+#define RB_CAM_GENERAL(cam) false
+#define RB_CAM_DISTORT(cam) false
+#define RB_ONLY_RADIANCE(rp) true
+#else
+#define RB_ENVMAP(sc) ((sc).has_envmap != 0)
+#define RB_CAM_GENERAL(cam) ((cam).type != RB_CAMERA_PERSPECTIVE || (cam).has_distortion != 0)
+#define RB_CAM_DISTORT(cam) ((cam).has_distortion != 0)
+#define RB_ONLY_RADIANCE(rp) ((rp).only_radiance != 0)
+#endif
+
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
 #endif

@@ -77,7 +77,7 @@ RB_D D3 hit_point_d(const rb_shape& s, int tri, D3 o, D3 d) {
 // point `p_d`, then rounded once -- src/scene.cpp:692-741).
 RB_D void sample_light(const DevScene& sc, D3 p_d, double light_sel, double tri_sel, double su, double sv, LightSampleRec& rec, SurfacePoint& lp) {
     int light_id = cdf_pick(sc.light_cdf, sc.num_lights, light_sel);
-    if (sc.has_envmap && light_id == sc.num_lights - 1) {
+    if (RB_ENVMAP(sc) && light_id == sc.num_lights - 1) {
         // environment map: direction by importance sampling, shadow ray to infinity (src/scene.cpp:703-711)
         V3 dir = envmap_sample(sc.env, su, sv);
         light_rec_set_env_dir(rec, dir);
@@ -129,7 +129,7 @@ RB_D V3 hit_emission(const DevScene& sc, const Isect& is, const SurfacePoint& sp
 
 // Radiance of the environment map seen along a ray that left the scene (src/primary_contribution.cpp:25-29).
 RB_D V3 miss_emission(const DevScene& sc, V3 dir, const RayDiff& rd) {
-    if (!sc.has_envmap || !sc.env.directly_visible) return zero3();
+    if (!RB_ENVMAP(sc) || !sc.env.directly_visible) return zero3();
     return envmap_eval(sc.env, dir, rd);
 }
 
@@ -164,7 +164,7 @@ RB_D V3 vertex_estimate(const DevScene& sc, const rb_material& mat, const Surfac
                     on = true;
                 }
             }
-        } else if (sc.has_envmap) { // environment light (:51-67); the lookup is unfiltered (zero ray differential)
+        } else if (RB_ENVMAP(sc)) { // environment light (:51-67); the lookup is unfiltered (zero ray differential)
             wo = light_rec_env_dir(ls);
             pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
             if (pdf_nee > 0) {
@@ -182,7 +182,7 @@ RB_D V3 vertex_estimate(const DevScene& sc, const rb_material& mat, const Surfac
     scatter_factor = zero3();
     scatter_ok = false;
     const bool hit = bis.valid();
-    if (hit || sc.has_envmap) {
+    if (hit || RB_ENVMAP(sc)) {
         V3 wo = bdir;
         Real dist_sq = 1;
         if (hit) {
@@ -373,7 +373,7 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
                     ok = true;
                 }
             }
-        } else if (sc.has_envmap) {
+        } else if (RB_ENVMAP(sc)) {
             wo = light_rec_env_dir(cur.light);
             pdf_nee = envmap_pdf(sc.env, wo) * (Real)sc.light_pmf[sc.num_lights - 1];
             if (pdf_nee > 0) {
@@ -419,7 +419,7 @@ RB_D VertexAdjoint d_vertex(const DevScene& sc, const DevDScene& ds, const Verte
     }
     // ---- BSDF-sampled continuation (pre): the ray hit something (:339-518) or left the scene into the map (:520-590)
     SurfacePoint bp;
-    if (nxt != nullptr && (nxt->isect.valid() || sc.has_envmap)) {
+    if (nxt != nullptr && (nxt->isect.valid() || RB_ENVMAP(sc))) {
         const bool hit = nxt->isect.valid();
         const Isect& bis = nxt->isect;
         V3 wo = nxt->ray.dir, dir = zero3();

@@ -290,7 +290,7 @@ RB_D int bwd_trace(const DevScene& sc, const RenderParams& rp, int pixel, int px
     RB_PHASE_SYNC();
     if (!act) {
         // a primary ray that leaves the scene still has an adjoint when it sees the environment map
-        if (is.shape_id == -2 && sc.has_envmap && sc.env.directly_visible && rp.rad_off >= 0) {
+        if (is.shape_id == -2 && RB_ENVMAP(sc) && sc.env.directly_visible && rp.rad_off >= 0) {
             VertexRec& r = recs[0];
             r.ray = ray;
             r.rd_in = rd;
@@ -374,7 +374,7 @@ RB_D void bwd_sweep(const DevScene& sc, const KernelArgs& ka, int pixel, int px,
             }
         }
         // G-buffer channels of the first hit (src/primary_contribution.cpp:486-692)
-        if (!rp.only_radiance) {
+        if (!RB_ONLY_RADIANCE(rp)) {
             Real d_vals[RB_MAX_ND];
             for (int i = 0; i < rp.nd; i++) d_vals[i] = weight * dpx_all[i];
             d_channel_values_at_hit(sc, ds, rp, is, sp, ray, d_vals, adj.d_point, d_ray.org);
@@ -456,14 +456,14 @@ RB_COLD D2 cam_to_screen_sphere_d(const DevCamera& cam, D3 p) { // fisheye / pan
     return r;
 }
 RB_HD D2 cam_to_screen_undistorted_d(const DevCamera& cam, D3 p);
-RB_HD D2 cam_to_screen_d(const DevCamera& cam, D3 p) { return cam_distort(cam, cam_to_screen_undistorted_d(cam, p)); }
+RB_HD D2 cam_to_screen_d(const DevCamera& cam, D3 p) { return cam_distort(cam, cam_to_screen_undistorted_d(cam, p)); } // (cam_distort: identity without a lens model)
 RB_HD D2 cam_to_screen_undistorted_d(const DevCamera& cam, D3 p) {
     const double* K = cam.intr;
     double aspect = double(cam.width) / double(cam.height);
     double ix = K[0] * p.x + K[1] * p.y + K[2] * p.z, iy = K[3] * p.x + K[4] * p.y + K[5] * p.z, iz = K[6] * p.x + K[7] * p.y + K[8] * p.z;
     D2 r;
-    if (cam.type == RB_CAMERA_FISHEYE || cam.type == RB_CAMERA_PANORAMA) return cam_to_screen_sphere_d(cam, p);
-    if (cam.type == RB_CAMERA_PERSPECTIVE) {
+    if (RB_CAM_GENERAL(cam) && (cam.type == RB_CAMERA_FISHEYE || cam.type == RB_CAMERA_PANORAMA)) return cam_to_screen_sphere_d(cam, p);
+    if (!RB_CAM_GENERAL(cam) || cam.type == RB_CAMERA_PERSPECTIVE) {
         r.x = (ix / iz + 1.0) * 0.5;
         r.y = (-(iy / iz) * aspect + 1.0) * 0.5;
     } else {
@@ -553,7 +553,7 @@ RB_HD D2 d_cam_screen_to_camera_undistorted_d(const DevCamera& cam, D2 p, D3 d_d
     return r;
 }
 RB_HD D3 d3_cross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-RB_HD bool cam_is_linear(const DevCamera& cam) { return (cam.type == RB_CAMERA_PERSPECTIVE || cam.type == RB_CAMERA_ORTHOGRAPHIC) && !cam.has_distortion; }
+RB_HD bool cam_is_linear(const DevCamera& cam) { return !RB_CAM_GENERAL(cam) || ((cam.type == RB_CAMERA_PERSPECTIVE || cam.type == RB_CAMERA_ORTHOGRAPHIC) && !cam.has_distortion); }
 
 // One primary-edge sample: edge sample index i (seeds the stream like a pixel index), spp sample s.
 // Edge and point on it chosen by primary-edge sample (i, s); false if the sample contributes nothing (edge behind the
@@ -693,7 +693,7 @@ RB_D void primary_edge_sample(const DevScene& sc, const KernelArgs& ka, long lon
             V3 Lb = trace_bounces<false>(sc, sub, ray, rd, is, thr, Real(0), 0, rp.max_bounces, nullptr, 0, nullptr);
             contrib += sum(weight * Lb);
         }
-        if (!rp.only_radiance) {
+        if (!RB_ONLY_RADIANCE(rp)) {
             // every other channel enters the edge integrand with its own d_image component as the multiplier
             // (channel_multipliers, src/edge.cpp:476-481; src/primary_contribution.cpp:256-435)
             Real vals[RB_MAX_ND];

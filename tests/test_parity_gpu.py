@@ -90,6 +90,18 @@ def test_band_size_does_not_change_gradients(rb, dev, monkeypatch):
         assert pu.rel_l2(g_many[k].numpy(), g_one[k].numpy()) < 1e-5, k
 
 
+def test_lean_and_general_kernels_agree(rb, dev, monkeypatch):
+    """Scenes without environment map / special camera / G-buffer run a second, feature-free instantiation of the kernels
+    (rb_kernels_lean.cu).  Same source, same samples: image bit-identical, gradients equal up to the order of the atomics."""
+    cfg = dict(pu.CASES["glossy_room_sobol_mb2"], edges=1)
+    img_lean, g_lean = pu.render_case(rb, dev, cfg, 9)
+    monkeypatch.setenv("RB_NO_LEAN", "1")
+    img_gen, g_gen = pu.render_case(rb, dev, cfg, 9)
+    assert pu.rel_l2(img_lean.numpy(), img_gen.numpy()) < 1e-6
+    for k in g_gen:
+        assert pu.rel_l2(g_lean[k].numpy(), g_gen[k].numpy()) < 1e-4, k
+
+
 def test_reference_intersection_known_answer(rb, dev):
     """The reference's own known-answer test for the closest-hit query (test_scene_intersect, src/scene.cpp:761-848): triangle
     (-1,0,1), (1,0,1), (0,1,1); the ray from the origin along +z hits shape 0 / triangle 0 at (0, 0, 1), the ray along -z hits

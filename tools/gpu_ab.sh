@@ -1,0 +1,9 @@
+#!/usr/bin/env bash
+# Quick A/B of library variants on one box: stage times of C2 with both edge samplers.
+cd "$(dirname "$0")/.."
+for l in "" redner_b200/_variants/*.so; do
+  [ -z "$l" ] || [ -f "$l" ] || continue
+  echo "LIB=${l:-main}"
+  RB_LIB=$l RB_EDGES=3 timeout 200 python tools/attrib.py shadow_blocker 512 64 1 2>&1 | tail -1 | cut -c1-150
+  RB_LIB=$l RB_EDGES=3 timeout 200 python tools/attrib.py glossy_room 256 16 2 2>&1 | tail -1 | cut -c1-150
+done
