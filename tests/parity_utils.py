@@ -84,7 +84,7 @@ def collect_grads(scene):
             if t is not None and t.grad is not None:
                 out["shape%d.%s" % (i, k)] = t.grad.detach().cpu().clone()
     for i, m in enumerate(scene.materials):
-        for k in ("diffuse_reflectance", "specular_reflectance", "roughness", "normal_map"):
+        for k in ("diffuse_reflectance", "specular_reflectance", "roughness", "normal_map", "generic_texture"):
             t = getattr(m, k)
             if t is not None and t.texels.grad is not None:
                 out["mat%d.%s" % (i, k)] = t.texels.grad.detach().cpu().clone()

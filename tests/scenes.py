@@ -171,6 +171,42 @@ def env_ball(device, resolution=(64, 64), grad=True, constant_sky=False):
     return api.Scene(cam, [floor, ball, lamp], [m_floor, m_ball, m_light], lights, envmap=env)
 
 
+def corner_ball(device, resolution=(32, 36), variant="plain", grad=True):
+    """Small scene that exercises the less travelled inputs of the boundary: separate uv / normal index buffers, vertex
+    colours (`vcolor`), a viewport crop (`viewport`), a generic texture (`generic`), a light the camera cannot see
+    (`invisible`), two-sided materials and lights, a differentiable camera pose; non-square image."""
+    g = torch.Generator().manual_seed(5)
+
+    def T(x, gr=False, dt=torch.float32):
+        t = torch.tensor(x, dtype=dt)
+        return t.to(device).requires_grad_(True) if gr and grad else t.to(device)
+
+    def C(x):  # camera parameters live on the host
+        return torch.tensor(x, dtype=torch.float32, requires_grad=grad)
+    vp = (4, 6, 28, 30) if variant == "viewport" else None
+    cam = api.Camera(position=C([0.2, 1.3, -4.0]), look_at=C([0.0, 0.6, 0.0]), up=C([0.0, 1.0, 0.0]), fov=torch.tensor([45.0]), clip_near=1e-2,
+                     resolution=resolution, viewport=vp)
+    v, i, uv, n = uv_sphere(device, 0.7, (0.1, 0.7, 0.2), grad=grad)
+    cols = torch.rand(v.shape[0], 3, generator=g).to(device).requires_grad_(grad)
+    perm = torch.randperm(uv.shape[0], generator=g)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(uv.shape[0])
+    uv2, n2 = uv.detach().cpu()[perm].to(device).requires_grad_(grad), n.detach().cpu()[perm].to(device).requires_grad_(grad)
+    idx2 = inv[i.cpu().long()].int().to(device)
+    gen = torch.rand(8, 8, 5, generator=g).to(device).requires_grad_(grad)
+    m_ball = api.Material(diffuse_reflectance=T([0.4, 0.4, 0.4]), use_vertex_color=(variant == "vcolor"),
+                          generic_texture=api.Texture(gen) if variant == "generic" else None, specular_reflectance=T([0.3, 0.3, 0.3], True), roughness=T([0.3], True))
+    m_floor = api.Material(diffuse_reflectance=T([0.5, 0.45, 0.4], True), two_sided=True)
+    m_l = api.Material(diffuse_reflectance=T([0.0, 0.0, 0.0]))
+    ball = api.Shape(v, i, 0, uvs=uv2, normals=n2, uv_indices=idx2, normal_indices=idx2.clone(), colors=cols)
+    floor = api.Shape(T([[-2.5, 0.0, -2.5], [-2.5, 0.0, 2.5], [2.5, 0.0, -2.5], [2.5, 0.0, 2.5]], True), T([[0, 1, 2], [1, 3, 2]], dt=torch.int32), 1)
+    l1 = api.Shape(T([[-0.6, 2.9, -0.6], [-0.6, 2.9, 0.6], [0.6, 2.9, -0.6], [0.6, 2.9, 0.6]]), T([[0, 2, 1], [1, 2, 3]], dt=torch.int32), 2)
+    l2 = api.Shape(T([[1.8, 0.8, -1.5], [1.8, 1.6, -1.5], [2.2, 0.8, -0.9]]), T([[0, 1, 2]], dt=torch.int32), 2)
+    lights = [api.AreaLight(2, torch.tensor([20.0, 19.0, 18.0], requires_grad=grad)),
+              api.AreaLight(3, torch.tensor([8.0, 10.0, 14.0], requires_grad=grad), two_sided=True, directly_visible=(variant != "invisible"))]
+    return api.Scene(cam, [ball, floor, l1, l2], [m_ball, m_floor, m_l], lights)
+
+
 def hires_room(device, **kw):
     """glossy_room with a 32 k-triangle ball (48 k edges): scene-build and traversal cost at the BASELINE C3 / C4 scale."""
     return glossy_room(device, sphere_res=(90, 180), **kw)
@@ -202,4 +238,4 @@ def nmap_room(device, **kw):
 
 
 SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
-          "nmap_room": nmap_room, "hires_room": hires_room, "ortho_room": ortho_room, "distort_room": distort_room, "fisheye_room": fisheye_room, "panorama_room": panorama_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}
+          "nmap_room": nmap_room, "corner_ball": corner_ball, "hires_room": hires_room, "ortho_room": ortho_room, "distort_room": distort_room, "fisheye_room": fisheye_room, "panorama_room": panorama_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}

@@ -166,6 +166,41 @@ def test_live_reference_if_present(rb, dev):
         assert pu.rel_l2(g_c[k].numpy(), g_r[k].numpy()) < GRAD_TOL, k
 
 
+CORNERS = [  # (variant, channels, max_bounces, primary edges, sample_pixel_center)
+    ("vcolor", ["radiance", "vertex_color", "diffuse_reflectance"], 1, True, False),
+    ("viewport", ["radiance"], 2, True, False),
+    ("plain", ["radiance", "uv", "shading_normal"], 1, False, True),
+    ("generic", ["radiance", "generic_texture"], 1, False, False),  # (the reference corrupts its heap with generic textures + edges)
+    ("invisible", ["radiance"], 3, True, False),
+]
+
+
+@pytest.mark.parametrize("variant,chans,mb,edges,center", CORNERS)
+def test_corner_features_against_live_reference(rb, dev, variant, chans, mb, edges, center):
+    """Index buffers for uvs / normals, vertex colours, viewport crops, generic textures, pixel-centre sampling, invisible and
+    two-sided lights, deeper paths: image and every gradient against the compiled reference, where it travelled."""
+    import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref did not travel with this snapshot")
+    ref = ref_loader.load()
+    out = []
+    for backend, device in ((ref, torch.device("cpu")), (rb, dev)):
+        sc = scenes.corner_ball(device, variant=variant)
+        ch = [getattr(backend.channels, c) for c in chans]
+        args = api.RenderFunction.serialize_scene(sc, 4, mb, channels=ch, sampler_type=backend.SamplerType.sobol, device=device, backend=backend,
+                                                  use_primary_edge_sampling=edges, use_secondary_edge_sampling=False, sample_pixel_center=center)
+        img = api.RenderFunction.apply(3, *args)
+        w = torch.linspace(0.5, 1.5, img.shape[-1], device=img.device)
+        (img * w).pow(2).sum().backward()
+        out.append((img.detach().cpu().numpy(), pu.collect_grads(sc)))
+    (img_r, g_r), (img_c, g_c) = out
+    assert img_r.shape == img_c.shape and pu.rel_l2(img_c, img_r) < IMG_TOL
+    assert set(g_r) == set(g_c)
+    for k in g_r:
+        if np.linalg.norm(g_r[k].numpy()) > 1e-9:
+            assert pu.rel_l2(g_c[k].numpy(), g_r[k].numpy()) < (5e-3 if edges and (k.endswith("vertices") or k.startswith("cam.")) else GRAD_TOL), k
+
+
 def _render(rb, dev, res, spp, seed=1, intensity_scale=1.0, partition=None, edges=0, scene_fn=scenes.shadow_blocker):
     sc = scene_fn(dev, resolution=(res, res))
     if intensity_scale != 1.0:
