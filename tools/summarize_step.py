@@ -11,7 +11,7 @@ for r in rows[hi + 1:]:
     if len(r) <= mv: continue
     name = r[kn].split('(')[0]
     if 'cub' in name: name = 'cub::' + name.split('::')[-1].split('<')[0]
-    name = name.replace('void ', '')[:48]
+    name = name.replace('void ', '').replace('rb_lean::', '')[:48]  # (the lean instantiation shares the stage names)
     d = per.setdefault(name, collections.defaultdict(float))
     try: v = float(r[mv].replace(',', ''))
     except ValueError: continue
