@@ -4,10 +4,13 @@
 //   camera matrices in double                      src/camera.h:44-55, src/transform.h:9-27
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rb_edge.cuh"
@@ -394,7 +397,18 @@ struct HostTreeBuilder {
         unsigned char optimal[128];
         double a[128], c_opt[128];
         unsigned num_subsets = (1u << cnt) - 1;
-        for (unsigned s = 1; s <= num_subsets; s++) a[s] = subset_area(cnt, lv, s);
+        {
+            // a[s] = area(union(leaf 0, leaves of s)): built incrementally, box[s] = box[s without its lowest leaf] + that leaf
+            // (min / max are exact and associative, so this equals the reference's from-scratch union, subset_area above)
+            HNode box[128];
+            box[0] = n[lv[0]];
+            for (unsigned s = 1; s <= num_subsets; s++) {
+                int low = __builtin_ctz(s);
+                box[s] = box[s & (s - 1u)];
+                if (low != 0) merge_into(box[s], box[s], n[lv[low]]);
+                a[s] = area(box[s]);
+            }
+        }
         for (int i = 0; i < cnt; i++) c_opt[1u << i] = n[lv[i]].cost;
         for (int k = 2; k <= cnt; k++)
             for (unsigned s = 1; s <= num_subsets; s++)
@@ -421,6 +435,32 @@ struct HostTreeBuilder {
         unsigned char right = (unsigned char)((~left) & mask);
         restruct(root, 1, lv, inner, right, optimal, index, cnt);
         refresh(root);
+    }
+    // The reference runs the treelet pass bottom-up in parallel: every thread starts at a leaf and climbs, the SECOND thread to
+    // arrive at a node optimises it (src/edge_tree.cpp:685-707).  A node's treelet lies in its own subtree, concurrently
+    // processed nodes sit in disjoint subtrees, and a node's result depends on its (finished) subtree only -- so the tree
+    // is the same as with the serial post-order below, which small scenes keep using.
+    void optimize_parallel(int num_threads) {
+        const int LB = std::max(L - 1, 1);
+        std::vector<std::atomic<int>> arrived(LB);
+        for (auto& x : arrived) x.store(0, std::memory_order_relaxed);
+        auto worker = [&](int j0, int j1) {
+            for (int j = j0; j < j1; j++) {
+                int cur = n[LB + j].parent;
+                while (cur != -1) {
+                    if (arrived[cur].fetch_add(1, std::memory_order_acq_rel) == 0) break; // first arrival: the sibling subtree is not done
+                    treelet_optimize(cur);
+                    cur = n[cur].parent;
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        int per = (L + num_threads - 1) / num_threads;
+        for (int t = 0; t < num_threads; t++) {
+            int j0 = t * per, j1 = std::min(L, j0 + per);
+            if (j0 < j1) pool.emplace_back(worker, j0, j1);
+        }
+        for (auto& th : pool) th.join();
     }
     void optimize_postorder(int root) {
         // every internal node is optimised after both of its (already optimised) child subtrees, which is the order the
@@ -521,7 +561,11 @@ struct HostTreeBuilder {
                 n[i].wlen = n[n[i].child[0]].wlen + n[n[i].child[1]].wlen;
             }
         }
-        optimize_postorder(0);
+        int threads = 1;
+        if (L >= 8192) threads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* env = getenv("RB_TREE_THREADS")) threads = std::max(1, atoi(env)); // (test hook)
+        if (threads > 1) optimize_parallel(threads);
+        else optimize_postorder(0);
         return 0;
     }
 };
