@@ -1,0 +1,59 @@
+"""CPU check of the DEVICE code's arithmetic: the rb_*.cuh headers the sm_100a kernels are built from are compiled
+with g++ (tools/cpu_emu: plain loops instead of kernels, host pointers behind the same C ABI) and every golden case
+-- images and gradients produced by the unmodified reference -- must be met with the tolerances of the GPU suite.
+
+This is test infrastructure, not a CPU path of the product (redner_b200/ cannot load it, tests/test_abi_cpu.py
+pins that); it lets a change to the per-sample code be checked against the reference before a GPU is available.
+Launch structure, compaction, sorting, atomics and the lean instantiation are only covered by `-m gpu`.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+import parity_utils as pu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tools", "cpu_emu")
+CSRC = os.path.join(ROOT, "redner_b200", "csrc")
+
+
+def _source_hash():
+    h = hashlib.sha1()
+    files = [os.path.join(EMU_DIR, f) for f in ("emu.cpp", "emu_shim.h", "build.sh")]
+    files += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".hpp", ".h"))]
+    files.append(os.path.join(ROOT, "include", "redner_b200.h"))
+    for f in files:
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:12]
+
+
+@pytest.fixture(scope="module")
+def emulator():
+    if shutil.which("g++") is None or not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("needs g++ and the CUDA headers")
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libredner_b200_emu_%s.so" % _source_hash())
+    if not os.path.exists(so):
+        env = dict(os.environ, RB_EMU_OUT=so + ".tmp", RB_EMU_OPT="-O1")
+        subprocess.run(["bash", os.path.join(EMU_DIR, "build.sh")], check=True, env=env, timeout=900)
+        os.replace(so + ".tmp", so)
+    return so
+
+
+def _check(so, names):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_check.py"), so] + names, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert [l for l in r.stdout.splitlines() if l.startswith("ok ")] == ["ok " + n for n in names]
+
+
+def test_device_headers_meet_every_golden_case(emulator):
+    _check(emulator, list(pu.CASES))
+
+
+def test_device_headers_meet_the_gbuffer_goldens(emulator):
+    _check(emulator, list(pu.GBUFFER_CASES))

@@ -1,7 +1,7 @@
 // DEVELOPMENT AID ONLY -- host stand-ins for the handful of CUDA device intrinsics used by redner_b200/csrc/*.cuh so
 // that the per-sample render logic can be compiled with g++ and stepped through / compared against the oracle in a
-// container without a GPU.  Nothing under tools/cpu_emu is part of the product: redner_b200/ never loads it, the
-// tests and bench never time it.
+// container without a GPU.  Nothing under tools/cpu_emu is part of the product: redner_b200/ never loads it and the bench
+// never runs it; tests/test_device_code_cpu.py checks this build of the device headers against the golden fixtures.
 #pragma once
 #include <cmath>
 #include <cstdint>
