@@ -72,6 +72,18 @@ extern "C" void rb_release_scratch(void) {
         }
     cudaSetDevice(prev);
 }
+// Destroys the timing events and restores the caller's current device on EVERY exit path of rb_render (RB_CUDA_OK returns).
+struct RenderGuard {
+    int prev_device = -1;
+    cudaEvent_t ev[5] = {};
+    int num_ev = 0;
+    std::vector<cudaEvent_t> band_events; // 4 per backward band: start, after trace, after compaction+secondary, after sweep
+    ~RenderGuard() {
+        for (cudaEvent_t e : band_events) cudaEventDestroy(e);
+        for (int i = 0; i < num_ev; i++) cudaEventDestroy(ev[i]);
+        if (prev_device >= 0) cudaSetDevice(prev_device);
+    }
+};
 static int pick_grid(const void* kernel, int device, int* blocks_per_sm_out) {
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -161,23 +173,23 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
     ka.d_image = d_image;
     ka.screen_grad = screen_grad;
 
+    RenderGuard guard;
     int prev = 0;
     RB_CUDA_OK(cudaGetDevice(&prev));
     RB_CUDA_OK(cudaSetDevice(scene->device));
+    guard.prev_device = prev;
     cudaStream_t stream = (cudaStream_t)stream_;
     // per-kernel CUDA events on the render stream: [0] start, [1] after k_forward, [2] after the backward bands,
     // [3] after k_primary_edge, [4] after k_finish_camera
-    cudaEvent_t ev[5];
-    for (int i = 0; i < 5; i++) RB_CUDA_OK(cudaEventCreate(&ev[i]));
+    cudaEvent_t* ev = guard.ev;
+    for (int i = 0; i < 5; i++) {
+        RB_CUDA_OK(cudaEventCreate(&ev[i]));
+        guard.num_ev = i + 1;
+    }
     int launches = 0;
     double host_stats[2] = {0, 0};
-    std::unique_lock<std::mutex> scratch_lock(g_scratch_mutex, std::defer_lock);
-    std::vector<cudaEvent_t> band_events; // 4 per backward band: start, after trace, after compaction+secondary, after sweep
-    auto cleanup = [&]() {
-        for (cudaEvent_t e : band_events) cudaEventDestroy(e);
-        for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
-        cudaSetDevice(prev);
-    };
+    std::unique_lock<std::mutex> scratch_lock(g_scratch_mutex, std::defer_lock); // (released before the guard runs)
+    std::vector<cudaEvent_t>& band_events = guard.band_events;
     RB_CUDA_OK(cudaEventRecord(ev[0], stream));
     if (image != nullptr) {
         if (only_radiance) {
@@ -202,7 +214,6 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         if (d_scene->num_shapes != (int)scene->shapes.size() || d_scene->num_materials != (int)scene->materials.size() ||
             d_scene->num_lights != (int)scene->lights.size()) {
             rb_set_error("rb_render: d_scene does not match the scene (shape / material / light counts)");
-            cleanup();
             return 1;
         }
         // ---- scratch layout: gradient descriptors | camera accumulators | band (records, boundary terms, lists, scan)
@@ -255,7 +266,6 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         char* scratch = scratch_ensure(scene->device, scratch_bytes);
         if (!scratch) {
             rb_set_error("rb_render: out of device memory for the backward scratch");
-            cleanup();
             return 1;
         }
         rb_dshape* d_shapes = (rb_dshape*)(scratch + o_shapes);
@@ -279,7 +289,6 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             ka.ds.env_w2e = d_scene->envmap->world_to_env;
         } else if (scene->dev.has_envmap) {
             rb_set_error("rb_render: the scene has an environment map but d_scene has no envmap gradient buffers");
-            cleanup();
             return 1;
         }
 
@@ -395,7 +404,6 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             }
     scene->last_path_vertices = host_stats[0];
     scene->last_primary_hits = host_stats[1];
-    cleanup();
     if (err != cudaSuccess) {
         rb_set_error(std::string("rb_render: kernel failure: ") + cudaGetErrorString(err));
         return 1;

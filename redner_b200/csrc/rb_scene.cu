@@ -265,6 +265,14 @@ int rb_build_bvh(rb_scene* sc, cudaStream_t stream) {
     RB_CUDA_OK(cudaGetLastError());
     sc->dev.bvh_nodes = nodes;
     sc->dev.bvh_tris = tris;
+    // builder temporaries (~100 B / triangle) go back to the pool in stream order; the scene keeps nodes + triangles only
+    void* temps[] = {d_offs, d_bounds, keys, keys_sorted, vals, vals_sorted, parent_inner, parent_leaf, flags, leaf_box, inner_box, tmp};
+    for (void* p : temps) {
+        auto it = std::find(sc->allocs.begin(), sc->allocs.end(), p);
+        if (it == sc->allocs.end()) continue;
+        sc->allocs.erase(it);
+        RB_CUDA_OK(cudaFreeAsync(p, stream));
+    }
     return 0;
 }
 
