@@ -410,7 +410,8 @@ def render(scene, options, rendered_image, d_rendered_image, d_scene, screen_gra
     if stream is None:
         try:
             import torch
-            stream = torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0
+            # (the stream of the SCENE's device: a stream handle of another device would be invalid there)
+            stream = torch.cuda.current_stream(scene.gpu_index if scene.gpu_index >= 0 else None).cuda_stream if torch.cuda.is_available() else 0
         except Exception:
             stream = 0
     rc = lib.rb_render(scene._handle, C.byref(o), _addr(rendered_image) or None, _addr(d_rendered_image) or None,
