@@ -386,7 +386,10 @@ RB_D void bwd_sweep(const DevScene& sc, const KernelArgs& ka, int pixel, int px,
         scatter_vertex_grads(sc, ds, is, d_vp, d_vn, d_vuv, d_vc);
     } else {
         // the primary ray left the scene: environment map seen directly (src/primary_contribution.cpp:469-483)
-        d_envmap_eval(sc.env, ray.dir, rd, d_emission, ds.env_values, ds.env_w2e, d_ray.dir, d_prd);
+        // Only the direction adjoint reaches the camera: the reference feeds the footprint adjoint of a primary ray to the
+        // camera through d_intersect_shape, i.e. for hits only (src/primary_intersection.cpp:9-16,:30-41).
+        RayDiff d_footprint = zero_raydiff();
+        d_envmap_eval(sc.env, ray.dir, rd, d_emission, ds.env_values, ds.env_w2e, d_ray.dir, d_footprint);
     }
     const Real delta = Real(1e-3);
     Real psx = Real(0.5) / sc.cam.width, psy = Real(0.5) / sc.cam.height;

@@ -36,6 +36,10 @@ CASES = {
     # environment map: importance-sampled light + BSDF-miss lookups with MIS, sky seen directly by the camera, gradients of
     # the map's texels and of its rotation (src/envmap.h, src/path_contribution.cpp:51-118,295-337,520-590)
     "env_ball_sobol_mb2": dict(scene="env_ball", res=40, spp=8, mb=2, sampler="sobol", edges=0, seed=21),
+    # the sky seen directly through a fisheye lens with a differentiable pose: of a primary ray that leaves the scene only the
+    # direction adjoint reaches the camera, the footprint adjoint does not (src/primary_intersection.cpp:9-16,:30-41); low
+    # resolution so that the sky is filtered from coarse mip levels and the footprint matters
+    "env_ball_fisheye_camera": dict(scene="env_ball_fisheye", res=16, spp=4, mb=0, sampler="sobol", edges=0, seed=23),
     # primary edges against the sky.  Sample-exact only for a sky without mip dependence: the reference looks edge rays'
     # differentials up at the wrong index (written at [idx], read at [2 idx + side]: src/edge.cpp:443-444 vs :608), so the
     # filter footprint of anything an edge ray sees is stale data there; we use the differential of the edge point.

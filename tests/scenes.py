@@ -143,12 +143,15 @@ def random_soup(device, num_tris=2000, resolution=(256, 256), seed=3, grad=False
     return api.Scene(cam, [soup, floor, light], [m, m_l], [api.AreaLight(2, torch.tensor([30.0, 30.0, 30.0]))])
 
 
-def env_ball(device, resolution=(64, 64), grad=True, constant_sky=False):
+def env_ball(device, resolution=(64, 64), grad=True, constant_sky=False, camera_type=0, cam_grad=False):
     """A glossy ball and a textured floor under an environment map (plus one small area light, so that light selection
-    mixes both kinds); the camera sees the sky directly."""
+    mixes both kinds); the camera sees the sky directly.  `cam_grad`: differentiable pose (the sky's gradient w.r.t. the
+    camera flows through the primary rays that leave the scene)."""
     g = torch.Generator().manual_seed(11)
-    cam = api.Camera(position=torch.tensor([0.2, 1.1, -4.0]), look_at=torch.tensor([0.0, 0.6, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
-                     fov=torch.tensor([45.0]), clip_near=1e-2, resolution=resolution)
+    pose = [[0.2, 1.1, -4.0], [0.0, 0.6, 0.0]] if camera_type == 0 else [[0.1, 0.9, -1.6], [0.0, 0.7, 0.0]]
+    cam = api.Camera(position=torch.tensor(pose[0], requires_grad=cam_grad), look_at=torch.tensor(pose[1], requires_grad=cam_grad),
+                     up=torch.tensor([0.0, 1.0, 0.0], requires_grad=cam_grad), fov=torch.tensor([45.0]), clip_near=1e-2, resolution=resolution,
+                     camera_type=camera_type)
     sky = (0.2 + 1.5 * torch.rand(16, 32, 3, generator=g))
     if constant_sky:  # same image size, one colour: no dependence on the mip level
         sky = torch.ones(16, 32, 3) * torch.tensor([0.6, 0.7, 0.9])
@@ -232,10 +235,14 @@ def env_ball_flat_sky(device, **kw):
     return env_ball(device, constant_sky=True, **kw)
 
 
+def env_ball_fisheye(device, **kw):
+    return env_ball(device, camera_type=2, cam_grad=True, **kw)
+
+
 def nmap_room(device, **kw):
     """glossy_room with a normal-mapped, specular-textured ball (normal-map and uv_scale adjoints)."""
     return glossy_room(device, nmap=True, **kw)
 
 
-SCENES = {"single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
+SCENES = {"env_ball_fisheye": env_ball_fisheye, "single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
           "nmap_room": nmap_room, "corner_ball": corner_ball, "hires_room": hires_room, "ortho_room": ortho_room, "distort_room": distort_room, "fisheye_room": fisheye_room, "panorama_room": panorama_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}
