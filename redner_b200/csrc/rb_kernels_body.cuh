@@ -224,12 +224,9 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SEC) k_bwd_sec_pick(co
             int e = ka.vert_list[t];
             int ts = e / ka.rec_per_sample, d = e - ts * ka.rec_per_sample;
             SampleId id = band_sample(rp, ka.band_i0 + ts);
-            // fair strategy coin shared by the RB_BLOCK vertices this block works on (neighbours in the list): both
-            // strategies are long and different, a block-wide choice keeps its warps in the same code and equally loaded
-            unsigned long long h = rb_hash64shift(((unsigned long long)(ka.band_i0 / RB_BLOCK + t_base / RB_BLOCK) << 20) ^ (rp.seed << 44) ^ 0x9e3779b97f4a7c15ULL);
             VertexRec cur = ka.records[e];
             EdgePick pk;
-            bool ok = bwd_secondary_pick(sc, ka, id.pixel, id.s, d, cur, (int)((h >> 17) & 1ULL), pk);
+            bool ok = bwd_secondary_pick(sc, ka, id.pixel, id.s, d, cur, pk);
             if (ok) ka.picks[t] = pk;
             ka.sec_keys[t] = ok ? (unsigned)pk.edge_id : (unsigned)sc.num_edges;
             ka.sec_vals[t] = (unsigned)t;

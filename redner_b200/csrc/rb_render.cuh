@@ -307,16 +307,25 @@ RB_D int bwd_trace(const DevScene& sc, const RenderParams& rp, int pixel, int px
     return nrec;
 }
 // Boundary (visibility) term at vertex `depth` of the path of (pixel, s), src/pathtracer.cpp:500-707, in two steps (see
-// rb_secondary.cuh).  `coin` picks the edge-sampling strategy and should be uniform over the calling block.
+// rb_secondary.cuh).
+#ifdef RB_EMU_REF_STREAMS
+// Host emulator only: the reference indexes the boundary-sample stream of a vertex by the RANK of its pixel in the compacted
+// active list of that depth (src/pathtracer.cpp:504-505).  A sequential emulator can know that rank (tools/cpu_emu fills
+// this table per sample), which makes the boundary terms comparable sample by sample; kernels cannot.
+static const int* rb_emu_rank = nullptr; // rank of the current (pixel, sample) at each depth
+#endif
 RB_D Sampler bwd_edge_sampler(const DevScene& sc, const RenderParams& rp, int pixel, int s, int depth, int consumed) {
     Sampler es;
+#ifdef RB_EMU_REF_STREAMS
+    if (rb_emu_rank != nullptr) pixel = rb_emu_rank[depth];
+#endif
     es.init(rp.sampler_type, rp.seed + 131071ULL, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * edge_draws_per_sample(sc, rp));
     es.skip(secondary_edge_dim_base(rp, depth) + consumed);
     return es;
 }
-RB_D bool bwd_secondary_pick(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur, int coin, EdgePick& pk) {
+RB_D bool bwd_secondary_pick(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur, EdgePick& pk) {
     Sampler es = bwd_edge_sampler(sc, ka.rp, pixel, s, depth, 0);
-    return secondary_edge_pick(sc, cur, es, coin, pk);
+    return secondary_edge_pick(sc, cur, es, pk);
 }
 // Returns d(position of the vertex).
 RB_D V3 bwd_secondary_shade(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur, const EdgePick& pk) {
@@ -326,9 +335,9 @@ RB_D V3 bwd_secondary_shade(const DevScene& sc, const KernelArgs& ka, int pixel,
     secondary_edge_shade(sc, ka.ds, rp, cur, depth, bwd_edge_sampler(sc, rp, pixel, s, depth, 4), mk3(dpx[0], dpx[1], dpx[2]), pk, d_position);
     return d_position;
 }
-RB_D V3 bwd_secondary(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur, int coin) {
+RB_D V3 bwd_secondary(const DevScene& sc, const KernelArgs& ka, int pixel, int s, int depth, const VertexRec& cur) {
     EdgePick pk;
-    if (!bwd_secondary_pick(sc, ka, pixel, s, depth, cur, coin, pk)) return zero3();
+    if (!bwd_secondary_pick(sc, ka, pixel, s, depth, cur, pk)) return zero3();
     return bwd_secondary_shade(sc, ka, pixel, s, depth, cur, pk);
 }
 // Reverse sweep (src/pathtracer.cpp:431-714) + first-hit and camera adjoints.  `dpos` (may be null) holds the
@@ -424,10 +433,7 @@ RB_D int backward_sample(const DevScene& sc, const KernelArgs& ka, int pixel, in
     V3 dpos[RB_MAX_SWEEP_DEPTH];
     bool sec = sc.use_secondary_edge && sc.num_edges > 0 && rp.rad_dim >= 0;
     for (int d = 0; d < nrec && d < RB_MAX_SWEEP_DEPTH; d++) {
-        int Lp = ka.lanes_per_pixel > 0 ? ka.lanes_per_pixel : 1;
-        unsigned long long h = rb_hash64shift(((unsigned long long)(unsigned)((long long)pixel * Lp / 32) << 24) ^ ((unsigned long long)d << 16) ^ (rp.seed << 44));
-        int coin = (int)(((h >> 17) + (unsigned long long)(s / Lp)) & 1ULL);
-        dpos[d] = sec ? bwd_secondary(sc, ka, pixel, s, d, recs[d], coin) : zero3();
+        dpos[d] = sec ? bwd_secondary(sc, ka, pixel, s, d, recs[d]) : zero3();
     }
     bwd_sweep(sc, ka, pixel, px, py, s, recs, 1, nrec, sec ? dpos : nullptr, cam_acc);
     return nrec;

@@ -342,7 +342,7 @@ struct alignas(16) EdgePick {
     V3 sample_p, mwt;
 };
 // `smp` is the edge sampler positioned at this depth's first dimension (4 dimensions are consumed here).
-RB_D bool secondary_edge_pick(const DevScene& sc, const VertexRec& cur, Sampler& smp, int strategy_bit, EdgePick& pk) {
+RB_D bool secondary_edge_pick(const DevScene& sc, const VertexRec& cur, Sampler& smp, EdgePick& pk) {
     double s_edge_sel = smp.next(), s_resample = smp.next(), s_component = smp.next(), s_t = smp.next();
     Real min_rough = cur.min_rough;
     // secondary edges are only sampled until the first rough bounce (src/edge.cpp:1396-1401)
@@ -405,16 +405,19 @@ RB_D bool secondary_edge_pick(const DevScene& sc, const VertexRec& cur, Sampler&
     Real nee_pmf = 1;
     bool diffuse_or_glossy = diffuse_lobe || roughness > Real(0.1);
     if (diffuse_or_glossy) {
-        // The reference flips this coin per sample (edge_sel < 0.5, src/edge.cpp:1461-1468).  We flip it per WARP
-        // (`strategy_bit` is a hash of pixel group, sample batch, depth and seed, identical for the 32 lanes): both
-        // strategies are long, completely different code paths, and a per-lane choice makes every warp execute both.
-        // The coin stays fair and independent of the remaining samples, so the expectation is unchanged.
-        use_nee = strategy_bit != 0;
+        // The strategy coin is the reference's: the upper half of `edge_sel` goes to the hierarchy (rescaled), the lower half
+        // to the gather (src/edge.cpp:1461-1472).  A cheaper-to-run block-wide coin (every warp in one strategy) was tried and
+        // is NOT equivalent: the reference scrambles all Sobol dimensions of a pixel with one value, so edge_sel, resample_sel,
+        // bsdf_component and t of a sample are strongly related (identical for sample 0) and the mean over seeds at a fixed
+        // sample count depends on exactly how the dimensions are consumed (measured on C2 at 8 spp: boundary term of the lamp
+        // off by 22 % with an independent coin, 0.6 standard errors with this one).  It also makes the pick a pure function of
+        // (pixel, sample, depth), independent of bands, stripes and block size.
+        use_nee = s_edge_sel < 0.5;
+        if (!use_nee) edge_sel = (Real)((s_edge_sel - 0.5) * 2);
         if (roughness > Real(0.1)) nee_pmf = Real(0.5);
         else nee_pmf = use_nee ? pd * Real(0.5) : 1 - pd * Real(0.5);
     }
     if (!use_nee) {
-        // (edge_sel is no longer consumed by the strategy coin, so it is uniform on [0, 1) as it stands)
         edge_id = sample_edge_hier(c, edge_sel, (Real)s_resample, edge_weight);
         if (edge_id == -1 || edge_weight <= 0) return false;
         const Edge& e = sc.edges[edge_id];
@@ -568,8 +571,8 @@ RB_D void secondary_edge_shade(const DevScene& sc, const DevDScene& ds, const Re
 
 // pick + shade for one vertex (host-compiled emulator; the kernels run the two steps separately)
 RB_D void secondary_edge_sample(const DevScene& sc, const DevDScene& ds, const RenderParams& rp, const VertexRec& cur, int depth, Sampler smp,
-                                V3 d_color, int strategy_bit, V3& d_position) {
+                                V3 d_color, V3& d_position) {
     EdgePick pk;
-    if (!secondary_edge_pick(sc, cur, smp, strategy_bit, pk)) return;
+    if (!secondary_edge_pick(sc, cur, smp, pk)) return;
     secondary_edge_shade(sc, ds, rp, cur, depth, smp, d_color, pk, d_position);
 }

@@ -25,7 +25,9 @@ def main():
     import parity_utils as pu
     dev = torch.device("cpu")
     for name in names:
-        if name in pu.GBUFFER_CASES:
+        if name in pu.STAT_CASES:
+            pu.assert_stat_matches_golden(name, pu.render_stat_case(rb, dev, name))
+        elif name in pu.GBUFFER_CASES:
             pu.assert_gbuffer_matches_golden(name, pu.render_gbuffer(rb, dev, pu.GBUFFER_CASES[name]).numpy())
         else:
             cfg = pu.CASES[name]

@@ -70,6 +70,11 @@ STAT_CASES = {
     # secondary-edge (shadow) gradient of the blocker: mean over seeds +- standard error
     "c2_shadow_blocker_secondary_stat": dict(scene="shadow_blocker", res=64, spp=64, mb=1, sampler="sobol", edges=3, seeds=list(range(1, 9)),
                                              keys=["shape1.vertices"]),
+    # every vertex of C2 differentiable, FEW samples per pixel, many seeds: the mean over seeds at a fixed low sample count
+    # depends on how the reference consumes its (jointly scrambled, hence related) Sobol dimensions, in particular on its
+    # per-sample strategy coin (src/edge.cpp:1461-1472); compared component by component (`z_rms`)
+    "c2_all_vertices_secondary_stat": dict(scene="shadow_blocker_all", res=32, spp=8, mb=1, sampler="sobol", edges=2, seeds=list(range(1, 65)),
+                                           keys=["shape0.vertices", "shape1.vertices", "shape2.vertices"], z_rms=2.0),
     "glossy_room_secondary_stat": dict(scene="glossy_room", res=32, spp=32, mb=2, sampler="sobol", edges=3, seeds=list(range(1, 7)),
                                        keys=["shape3.vertices"]),
 }
@@ -184,3 +189,32 @@ def assert_gbuffer_matches_golden(name, img):
             else:
                 assert rel_l2(img[..., d:d + n], g[..., d:d + n]) < IMG_TOL, c
             d += n
+
+
+def assert_stat_matches_golden(name, acc):
+    """Mean over seeds of the gradients in `acc` ({key: [array per seed]}) against the reference's mean +- standard error."""
+    cfg = STAT_CASES[name]
+    g = load_golden(name)
+    for k in cfg["keys"]:
+        a = np.stack(acc[k]).astype(np.float64)
+        mean, sem = a.mean(0), a.std(0, ddof=1) / np.sqrt(a.shape[0])
+        ref_mean, ref_sem = g["mean." + k], g["sem." + k]
+        err = np.linalg.norm(mean - ref_mean)
+        noise = np.sqrt(np.linalg.norm(sem) ** 2 + np.linalg.norm(ref_sem) ** 2)
+        assert err < 4 * noise, (k, err, noise)
+        assert err < 0.35 * np.linalg.norm(ref_mean), (k, err, np.linalg.norm(ref_mean))
+        if "z_rms" in cfg:  # per component; the floor keeps exactly-zero components (rounding residue) out of it
+            floor = 1e-3 * np.abs(ref_mean).max()
+            z = (mean - ref_mean) / np.maximum(np.sqrt(sem ** 2 + ref_sem ** 2), floor)
+            assert np.sqrt((z ** 2).mean()) < cfg["z_rms"], (k, float(np.sqrt((z ** 2).mean())), float(np.abs(z).max()))
+            assert np.abs(z).max() < 5.0, (k, float(np.abs(z).max()))
+
+
+def render_stat_case(backend, device, name):
+    cfg = STAT_CASES[name]
+    acc = {k: [] for k in cfg["keys"]}
+    for seed in cfg["seeds"]:
+        _, grads = render_case(backend, device, cfg, seed)
+        for k in cfg["keys"]:
+            acc[k].append(grads[k].numpy())
+    return acc

@@ -33,16 +33,18 @@ def single_triangle(device, resolution=(256, 256), grad=True):
     return api.Scene(cam, [tri, light], [mat_grey], [al])
 
 
-def shadow_blocker(device, resolution=(512, 512), grad=True):
+def shadow_blocker(device, resolution=(512, 512), grad=True, grad_all=False):
+    """C2 geometry (tests/test_shadow_blocker.py).  `grad_all`: floor and lamp vertices differentiable too (the lamp's
+    boundary is where the two boundary-sampling strategies of the reference meet)."""
     cam = api.Camera(position=torch.tensor([0.0, 2.0, -5.0]), look_at=torch.tensor([0.0, 0.0, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]),
                      fov=torch.tensor([45.0]), clip_near=1e-2, resolution=resolution)
     mat_grey = api.Material(diffuse_reflectance=_t([0.5, 0.5, 0.5], device, grad=grad))
     mat_black = api.Material(diffuse_reflectance=_t([0.0, 0.0, 0.0], device))
-    floor = api.Shape(_t([[-2.0, 0.0, -2.0], [-2.0, 0.0, 2.0], [2.0, 0.0, -2.0], [2.0, 0.0, 2.0]], device),
+    floor = api.Shape(_t([[-2.0, 0.0, -2.0], [-2.0, 0.0, 2.0], [2.0, 0.0, -2.0], [2.0, 0.0, 2.0]], device, grad=grad and grad_all),
                       _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 0)
     blocker = api.Shape(_t([[-0.2, 3.5, -0.8], [-0.8, 3.0, 0.3], [0.4, 2.8, -0.8], [0.3, 3.2, 1.0]], device, grad=grad),
                         _t([[0, 1, 2], [1, 3, 2]], device, torch.int32), 0)
-    light = api.Shape(_t([[-0.1, 5, -0.1], [-0.1, 5, 0.1], [0.1, 5, -0.1], [0.1, 5, 0.1]], device),
+    light = api.Shape(_t([[-0.1, 5, -0.1], [-0.1, 5, 0.1], [0.1, 5, -0.1], [0.1, 5, 0.1]], device, grad=grad and grad_all),
                       _t([[0, 2, 1], [1, 2, 3]], device, torch.int32), 1)
     al = api.AreaLight(2, torch.tensor([1000.0, 1000.0, 1000.0], requires_grad=grad))
     return api.Scene(cam, [floor, blocker, light], [mat_grey, mat_black], [al])
@@ -235,6 +237,10 @@ def env_ball_flat_sky(device, **kw):
     return env_ball(device, constant_sky=True, **kw)
 
 
+def shadow_blocker_all(device, **kw):
+    return shadow_blocker(device, grad_all=True, **kw)
+
+
 def env_ball_fisheye(device, **kw):
     return env_ball(device, camera_type=2, cam_grad=True, **kw)
 
@@ -244,5 +250,5 @@ def nmap_room(device, **kw):
     return glossy_room(device, nmap=True, **kw)
 
 
-SCENES = {"env_ball_fisheye": env_ball_fisheye, "single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
+SCENES = {"env_ball_fisheye": env_ball_fisheye, "shadow_blocker_all": shadow_blocker_all, "single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
           "nmap_room": nmap_room, "corner_ball": corner_ball, "hires_room": hires_room, "ortho_room": ortho_room, "distort_room": distort_room, "fisheye_room": fisheye_room, "panorama_room": panorama_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}

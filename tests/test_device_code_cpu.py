@@ -57,3 +57,9 @@ def test_device_headers_meet_every_golden_case(emulator):
 
 def test_device_headers_meet_the_gbuffer_goldens(emulator):
     _check(emulator, list(pu.GBUFFER_CASES))
+
+
+def test_device_headers_meet_the_boundary_term_statistics(emulator):
+    """Secondary-edge (shadow) gradients: mean over seeds against the reference's mean +- standard error, incl. the
+    low-sample-count case that pins the reference's strategy coin."""
+    _check(emulator, list(pu.STAT_CASES))

@@ -49,7 +49,7 @@ def test_gbuffer_golden(rb, dev, name):
 
 def test_band_size_does_not_change_gradients(rb, dev, monkeypatch):
     """The adjoint pass walks the image in bands (records through HBM, per-band compaction and sorts): one band or
-    hundreds of tiny ones must give the same sample-exact gradients (secondary edges off: their strategy coin is per block)."""
+    hundreds of tiny ones must give the same sample-exact gradients."""
     cfg = dict(pu.CASES["glossy_room_sobol_mb2"], edges=1)
     _, g_one = pu.render_case(rb, dev, cfg, 9)
     monkeypatch.setenv("RB_BAND_BYTES", str(1 << 20))
@@ -105,21 +105,7 @@ def test_gbuffer_backward_without_radiance_skips_path_tracing(rb, dev):
 
 @pytest.mark.parametrize("name", list(pu.STAT_CASES))
 def test_secondary_edge_gradients_statistically(rb, dev, name):
-    cfg = pu.STAT_CASES[name]
-    g = pu.load_golden(name)
-    acc = {k: [] for k in cfg["keys"]}
-    for seed in cfg["seeds"]:
-        _, grads = pu.render_case(rb, dev, cfg, seed)
-        for k in cfg["keys"]:
-            acc[k].append(grads[k].numpy())
-    for k in cfg["keys"]:
-        a = np.stack(acc[k])
-        mean, sem = a.mean(0), a.std(0, ddof=1) / np.sqrt(a.shape[0])
-        ref_mean, ref_sem = g["mean." + k], g["sem." + k]
-        err = np.linalg.norm(mean - ref_mean)
-        noise = np.sqrt(np.linalg.norm(sem) ** 2 + np.linalg.norm(ref_sem) ** 2)
-        assert err < 4 * noise, (k, err, noise)
-        assert err < 0.35 * np.linalg.norm(ref_mean), (k, err, np.linalg.norm(ref_mean))
+    pu.assert_stat_matches_golden(name, pu.render_stat_case(rb, dev, name))
 
 
 def test_live_reference_if_present(rb, dev):

@@ -295,9 +295,25 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
         acc.base = cam_f.data();
         acc.stride = 1;
         std::vector<VertexRec> recs(rp.max_bounces + 2);
+#ifdef RB_EMU_REF_STREAMS
+        // rank of every (sample, pixel) in the reference's compacted active list of each depth (pixels in ascending order)
+        const int mbr = std::max(rp.max_bounces, 1);
+        const size_t npx = (size_t)rp.vp_w * rp.vp_h;
+        std::vector<int> ranks((size_t)rp.spp * npx * mbr, 0);
+        for (int s = 0; s < rp.spp; s++) {
+            std::vector<int> counter(mbr, 0);
+            for (size_t pixel = 0; pixel < npx; pixel++) {
+                int nrec = bwd_trace(sc, rp, (int)pixel, (int)(pixel % rp.vp_w), (int)(pixel / rp.vp_w), s, recs.data(), 1);
+                for (int d = 0; d < nrec && d < mbr; d++) ranks[((size_t)s * npx + pixel) * mbr + d] = counter[d]++;
+            }
+        }
+#endif
         for (int y = 0; y < rp.vp_h; y++)
             for (int x = 0; x < rp.vp_w; x++)
                 for (int s = 0; s < rp.spp; s++) {
+#ifdef RB_EMU_REF_STREAMS
+                    rb_emu_rank = &ranks[((size_t)s * npx + (size_t)y * rp.vp_w + x) * mbr];
+#endif
                     backward_sample(sc, ka, y * rp.vp_w + x, x, y, s, recs.data(), acc);
                     for (int k = 0; k < RB_CAM_ACC; k++) { cam_accum[k] += cam_f[k]; cam_f[k] = 0.f; }
                 }
