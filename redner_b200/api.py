@@ -418,7 +418,8 @@ class RenderFunction(torch.autograd.Function):
         d_scene = rb.DScene(d_camera, d_shapes, d_materials, d_lights, d_envmap, dev.type == "cuda", dev.index if dev.index is not None else -1)
         c.options.seed = c.seed[1]
         c.options.num_samples = c.num_samples[1]
-        rb.render(c.scene, c.options, rb.float_ptr(0), fp(grad_img), d_scene, rb.float_ptr(0), rb.float_ptr(0))
+        screen_grad = getattr(c, "screen_gradient", None)  # (only set by visualize_screen_gradient)
+        rb.render(c.scene, c.options, rb.float_ptr(0), fp(grad_img), d_scene, fp(screen_grad), rb.float_ptr(0))
 
         out = [None]  # seed
         out += [None, None, None]  # counts
@@ -444,6 +445,33 @@ class RenderFunction(torch.autograd.Function):
             out.append(None)  # envmap
         out += [None] * 9  # num_samples .. backend
         return tuple(out)
+
+
+def visualize_screen_gradient(grad_img: Optional[torch.Tensor], seed: int, scene: Scene, num_samples, max_bounces: int, channels=None, sampler_type=None,
+                              use_primary_edge_sampling: bool = True, use_secondary_edge_sampling: bool = True, sample_pixel_center: bool = False,
+                              device=None, backend=None) -> torch.Tensor:
+    """RenderFunction.visualize_screen_gradient (pyredner/render_pytorch.py:982-1048): the derivative of the (weighted) image
+    with respect to the screen position of every pixel, [height, width, 2] -- the backward pass with a screen-gradient
+    buffer attached (src/primary_intersection.cpp:104-114, src/edge.cpp:765-773).  `grad_img` None means all ones."""
+    args = RenderFunction.serialize_scene(scene, num_samples, max_bounces, channels=channels, sampler_type=sampler_type,
+                                          use_primary_edge_sampling=use_primary_edge_sampling, use_secondary_edge_sampling=use_secondary_edge_sampling,
+                                          sample_pixel_center=sample_pixel_center, device=device, backend=backend)
+    c = RenderFunction._unpack((seed, seed), args)
+    c.num_samples = (c.num_samples[0], c.num_samples[0])  # (the reference renders this pass with the forward sample count)
+    rb = c.backend
+    nch = rb.compute_num_channels(c.channels, c.scene.max_generic_texture_dimension)
+    h, w = c.viewport[2] - c.viewport[0], c.viewport[3] - c.viewport[1]
+    if grad_img is None:
+        grad_img = torch.ones(h, w, nch, device=c.device)
+    assert tuple(grad_img.shape) == (h, w, nch)
+    c.screen_gradient = torch.zeros(h, w, 2, device=c.device)
+    ctx = _Ctx()
+    ctx.c, ctx.args = c, args
+    RenderFunction.backward(ctx, grad_img.to(c.device))
+    return c.screen_gradient
+
+
+RenderFunction.visualize_screen_gradient = staticmethod(visualize_screen_gradient)  # (where pyredner keeps it)
 
 
 def render_pathtracing(scene: Scene, num_samples=(4, 4), max_bounces: int = 1, seed: int = 0, sampler_type=None, device=None, backend=None,

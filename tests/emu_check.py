@@ -27,6 +27,8 @@ def main():
     for name in names:
         if name in pu.STAT_CASES:
             pu.assert_stat_matches_golden(name, pu.render_stat_case(rb, dev, name))
+        elif name in pu.SCREEN_CASES:
+            pu.assert_screen_gradient_matches_golden(name, pu.render_screen_gradient(rb, dev, pu.SCREEN_CASES[name]).numpy())
         elif name in pu.GBUFFER_CASES:
             pu.assert_gbuffer_matches_golden(name, pu.render_gbuffer(rb, dev, pu.GBUFFER_CASES[name]).numpy())
         else:

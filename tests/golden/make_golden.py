@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 import ref_loader  # noqa: E402
-from parity_utils import CASES, GBUFFER_CASES, STAT_CASES, render_case, render_gbuffer  # noqa: E402
+from parity_utils import CASES, GBUFFER_CASES, SCREEN_CASES, STAT_CASES, render_case, render_gbuffer, render_screen_gradient  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -47,6 +47,12 @@ def main():
         img = render_gbuffer(ref, dev, cfg)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), image=img.numpy())
         print(name, tuple(img.shape), "mean %.6f" % img.mean().item())
+    for name, cfg in SCREEN_CASES.items():
+        if only and name not in only:
+            continue
+        img = render_screen_gradient(ref, dev, cfg)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), image=img.numpy())
+        print(name, tuple(img.shape), "norm %.6f" % img.norm().item())
     for name, cfg in STAT_CASES.items():
         if only and name not in only:
             continue

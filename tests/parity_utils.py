@@ -66,6 +66,13 @@ GBUFFER_CASES = {
     "gbuffer_nmap_room_radiance_last": dict(scene="nmap_room", res=32, spp=4, mb=1, sampler="sobol", seed=6,
                                             channels=["depth", "shading_normal", "radiance"]),
 }
+# d(image) / d(screen position of each pixel) (RenderFunction.visualize_screen_gradient): first-hit adjoint through the camera
+# plus the primary-edge term (src/primary_intersection.cpp:104-114, src/edge.cpp:765-773)
+SCREEN_CASES = {
+    "screen_gradient_c1": dict(scene="single_triangle", res=32, spp=4, mb=1, sampler="sobol", edges=1, seed=5, tol=1e-4),
+    # (textured floor seen by edge rays: the stale-footprint difference of the primary-edge entries above applies)
+    "screen_gradient_fisheye_room": dict(scene="fisheye_room", res=24, spp=2, mb=1, sampler="sobol", edges=1, seed=5, tol=3e-3),
+}
 STAT_CASES = {
     # secondary-edge (shadow) gradient of the blocker: mean over seeds +- standard error
     "c2_shadow_blocker_secondary_stat": dict(scene="shadow_blocker", res=64, spp=64, mb=1, sampler="sobol", edges=3, seeds=list(range(1, 9)),
@@ -218,3 +225,16 @@ def render_stat_case(backend, device, name):
         for k in cfg["keys"]:
             acc[k].append(grads[k].numpy())
     return acc
+
+
+def render_screen_gradient(backend, device, cfg):
+    sc = scenes.SCENES[cfg["scene"]](device, resolution=(cfg["res"], cfg["res"]), grad=False)
+    st = backend.SamplerType.sobol if cfg["sampler"] == "sobol" else backend.SamplerType.independent
+    return api.visualize_screen_gradient(None, cfg["seed"], sc, cfg["spp"], cfg["mb"], sampler_type=st, use_primary_edge_sampling=bool(cfg["edges"] & 1),
+                                         use_secondary_edge_sampling=bool(cfg["edges"] & 2), device=device, backend=backend).detach().cpu()
+
+
+def assert_screen_gradient_matches_golden(name, img):
+    g = load_golden(name)["image"]
+    assert img.shape == g.shape and np.linalg.norm(g) > 0
+    assert rel_l2(img, g) < SCREEN_CASES[name]["tol"], rel_l2(img, g)

@@ -56,7 +56,7 @@ def test_device_headers_meet_every_golden_case(emulator):
 
 
 def test_device_headers_meet_the_gbuffer_goldens(emulator):
-    _check(emulator, list(pu.GBUFFER_CASES))
+    _check(emulator, list(pu.GBUFFER_CASES) + list(pu.SCREEN_CASES))
 
 
 def test_device_headers_meet_the_boundary_term_statistics(emulator):

@@ -46,6 +46,12 @@ def test_gbuffer_goldens_are_reference_outputs(reference_module, name):
     assert np.array_equal(img.numpy(), pu.load_golden(name)["image"])
 
 
+@pytest.mark.parametrize("name", list(pu.SCREEN_CASES))
+def test_screen_gradient_goldens_are_reference_outputs(reference_module, name):
+    img = pu.render_screen_gradient(reference_module, torch.device("cpu"), pu.SCREEN_CASES[name])
+    assert pu.rel_l2(img.numpy(), pu.load_golden(name)["image"]) < 1e-6  # (atomics: not bitwise)
+
+
 def _scene_dict(sc):
     cam = sc.camera
     return dict(camera=dict(position=cam.position.detach().double().numpy(), look_at=cam.look_at.double().numpy(), up=cam.up.double().numpy(),

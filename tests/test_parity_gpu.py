@@ -47,6 +47,13 @@ def test_gbuffer_golden(rb, dev, name):
     pu.assert_gbuffer_matches_golden(name, pu.render_gbuffer(rb, dev, pu.GBUFFER_CASES[name]).numpy())
 
 
+@pytest.mark.parametrize("name", list(pu.SCREEN_CASES))
+def test_screen_gradient_golden(rb, dev, name):
+    """visualize_screen_gradient: the backward pass with a screen-gradient image attached (first-hit adjoint through the camera
+    + primary-edge term), against the reference's output."""
+    pu.assert_screen_gradient_matches_golden(name, pu.render_screen_gradient(rb, dev, pu.SCREEN_CASES[name]).numpy())
+
+
 def test_band_size_does_not_change_gradients(rb, dev, monkeypatch):
     """The adjoint pass walks the image in bands (records through HBM, per-band compaction and sorts): one band or
     hundreds of tiny ones must give the same sample-exact gradients."""
