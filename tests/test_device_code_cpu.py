@@ -31,18 +31,30 @@ def _source_hash():
     return h.hexdigest()[:12]
 
 
-@pytest.fixture(scope="module")
-def emulator():
+def _build(flags=""):
     if shutil.which("g++") is None or not os.path.isdir("/usr/local/cuda/include"):
         pytest.skip("needs g++ and the CUDA headers")
     out_dir = os.path.join(ROOT, "tests", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    so = os.path.join(out_dir, "libredner_b200_emu_%s.so" % _source_hash())
+    tag = hashlib.sha1((_source_hash() + flags).encode()).hexdigest()[:12]
+    so = os.path.join(out_dir, "libredner_b200_emu_%s.so" % tag)
     if not os.path.exists(so):
-        env = dict(os.environ, RB_EMU_OUT=so + ".tmp", RB_EMU_OPT="-O1")
+        env = dict(os.environ, RB_EMU_OUT=so + ".tmp", RB_EMU_OPT="-O1", RB_EMU_FLAGS=flags)
         subprocess.run(["bash", os.path.join(EMU_DIR, "build.sh")], check=True, env=env, timeout=900)
         os.replace(so + ".tmp", so)
     return so
+
+
+@pytest.fixture(scope="module")
+def emulator():
+    return _build()
+
+
+@pytest.fixture(scope="module")
+def emulator_lean():
+    """The same headers with -DRB_LEAN: environment map, general cameras and G-buffer channels compiled out, as in
+    rb_kernels_lean.cu (the instantiation the driver launches for the common configuration)."""
+    return _build("-DRB_LEAN")
 
 
 def _check(so, names):
@@ -63,3 +75,9 @@ def test_device_headers_meet_the_boundary_term_statistics(emulator):
     """Secondary-edge (shadow) gradients: mean over seeds against the reference's mean +- standard error, incl. the
     low-sample-count case that pins the reference's strategy coin."""
     _check(emulator, list(pu.STAT_CASES))
+
+
+def test_lean_instantiation_meets_the_goldens_it_serves(emulator_lean):
+    names = [n for n, c in pu.CASES.items() if "channels" not in c and c["scene"] in ("single_triangle", "shadow_blocker", "glossy_room", "nmap_room")]
+    assert len(names) >= 7
+    _check(emulator_lean, names + ["c2_all_vertices_secondary_stat"])
