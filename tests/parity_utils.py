@@ -82,7 +82,7 @@ STAT_CASES = {
     # per-sample strategy coin (src/edge.cpp:1461-1472); compared component by component (`z_rms`)
     "c2_all_vertices_secondary_stat": dict(scene="shadow_blocker_all", res=32, spp=8, mb=1, sampler="sobol", edges=2, seeds=list(range(1, 65)),
                                            keys=["shape0.vertices", "shape1.vertices", "shape2.vertices"], z_rms=2.0),
-    "glossy_room_secondary_stat": dict(scene="glossy_room", res=32, spp=32, mb=2, sampler="sobol", edges=3, seeds=list(range(1, 7)),
+    "glossy_room_secondary_stat": dict(scene="glossy_room", res=32, spp=32, mb=2, sampler="sobol", edges=3, seeds=list(range(1, 25)),
                                        keys=["shape3.vertices"]),
 }
 
