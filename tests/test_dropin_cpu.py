@@ -81,3 +81,92 @@ def test_envmap_preprocessing_matches_pyredner():
     code = ENV_SCRIPT % {"dropin": os.path.join(ROOT, "redner_b200", "dropin"), "ref": REF, "root": ROOT}
     out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ENVMAP-TABLES-OK" in out.stdout, (out.stdout[-500:], out.stderr[-1500:])
+
+
+E2E_SCRIPT = r'''
+import sys, types, ctypes, os
+native, out = sys.argv[1], sys.argv[2]
+sys.path.insert(0, %(ref)r)
+sys.path.insert(0, %(root)r)
+for name in ("skimage", "skimage.io", "skimage.transform", "imageio"):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules["skimage"].io = sys.modules["skimage.io"]
+sys.modules["skimage"].transform = sys.modules["skimage.transform"]
+if native == "reference":      # the reference's own pybind module
+    d = os.path.join(%(root)r, "oracle", "_ref")
+    for lib in ("libtbbmalloc.so.2", "libtbb.so.2", "libembree3.so.3"):
+        ctypes.CDLL(os.path.join(d, lib), mode=ctypes.RTLD_GLOBAL)
+    sys.path.insert(0, d)
+else:                          # our drop-in module, bound to the host build of the device headers (this process only)
+    from redner_b200 import _lib
+    _lib._lib = _lib._bind(ctypes.CDLL(native))
+    sys.path.insert(0, %(dropin)r)
+import numpy as np, torch, redner, pyredner
+pyredner.set_use_gpu(False)
+pyredner.set_print_timing(False)
+g = torch.Generator().manual_seed(7)
+cam = pyredner.Camera(position=torch.tensor([0.1, 1.2, -4.0], requires_grad=True), look_at=torch.tensor([0.0, 0.5, 0.0], requires_grad=True),
+                      up=torch.tensor([0.0, 1.0, 0.0], requires_grad=True), fov=torch.tensor([45.0]), clip_near=1e-2, resolution=(24, 28))
+tex = (0.2 + 0.6 * torch.rand(8, 8, 3, generator=g)).requires_grad_(True)
+m_floor = pyredner.Material(diffuse_reflectance=pyredner.Texture(tex, uv_scale=torch.tensor([2.0, 2.0])))
+m_tri = pyredner.Material(diffuse_reflectance=torch.tensor([0.4, 0.5, 0.3], requires_grad=True), specular_reflectance=torch.tensor([0.3, 0.3, 0.3], requires_grad=True),
+                          roughness=torch.tensor([0.2], requires_grad=True))
+m_l = pyredner.Material(diffuse_reflectance=torch.tensor([0.0, 0.0, 0.0]))
+floor = pyredner.Shape(vertices=torch.tensor([[-2.0, 0.0, -2.0], [-2.0, 0.0, 2.0], [2.0, 0.0, -2.0], [2.0, 0.0, 2.0]]), indices=torch.tensor([[0, 1, 2], [1, 3, 2]], dtype=torch.int32),
+                       uvs=torch.tensor([[0.0, 0.0], [0.0, 1.0], [1.0, 0.0], [1.0, 1.0]]), normals=None, material_id=0)
+tri_v = torch.tensor([[-0.8, 0.3, 0.2], [0.7, 0.4, -0.1], [0.0, 1.6, 0.3]], requires_grad=True)
+tri = pyredner.Shape(vertices=tri_v, indices=torch.tensor([[0, 1, 2]], dtype=torch.int32), uvs=None, normals=None, material_id=1)
+lamp = pyredner.Shape(vertices=torch.tensor([[-0.5, 2.8, -0.5], [-0.5, 2.8, 0.5], [0.5, 2.8, -0.5], [0.5, 2.8, 0.5]]), indices=torch.tensor([[0, 2, 1], [1, 2, 3]], dtype=torch.int32),
+                      uvs=None, normals=None, material_id=2)
+inten = torch.tensor([20.0, 19.0, 18.0], requires_grad=True)
+scene = pyredner.Scene(cam, [floor, tri, lamp], [m_floor, m_tri, m_l], [pyredner.AreaLight(shape_id=2, intensity=inten)])
+res = {}
+# pass 1: textured floor, two channels, interior derivatives only (every number is sample-exact)
+args = pyredner.RenderFunction.serialize_scene(scene=scene, num_samples=4, max_bounces=2, sampler_type=redner.SamplerType.sobol,
+                                               channels=[redner.channels.radiance, redner.channels.depth],
+                                               use_primary_edge_sampling=False, use_secondary_edge_sampling=False)
+img = pyredner.RenderFunction.apply(3, *args)
+(img * torch.tensor([1.0, 1.0, 1.0, 0.2])).pow(2).sum().backward()
+res.update(image=img.detach().numpy(), position=cam.position.grad.numpy().copy(), look_at=cam.look_at.grad.numpy().copy(), up=cam.up.grad.numpy().copy(),
+           tex=tex.grad.numpy().copy(), kd=m_tri.diffuse_reflectance.texels.grad.numpy().copy(), ks=m_tri.specular_reflectance.texels.grad.numpy().copy(),
+           ro=m_tri.roughness.texels.grad.numpy().copy(), tri=tri_v.grad.numpy().copy(), inten=inten.grad.numpy().copy())
+# pass 2: primary edge sampling (silhouette derivatives) on a one-colour floor -- what an edge ray sees must not depend on the
+# filter footprint for the comparison to be sample-exact (DESIGN.md section 4)
+for t in (cam.position, cam.look_at, cam.up, tri_v):
+    t.grad = None
+scene.materials[0] = pyredner.Material(diffuse_reflectance=torch.tensor([0.5, 0.45, 0.4]))
+args = pyredner.RenderFunction.serialize_scene(scene=scene, num_samples=4, max_bounces=1, sampler_type=redner.SamplerType.sobol,
+                                               use_primary_edge_sampling=True, use_secondary_edge_sampling=False)
+img2 = pyredner.RenderFunction.apply(5, *args)
+img2.pow(2).sum().backward()
+res.update(edge_image=img2.detach().numpy(), edge_position=cam.position.grad.numpy(), edge_look_at=cam.look_at.grad.numpy(), edge_up=cam.up.grad.numpy(),
+           edge_tri=tri_v.grad.numpy())
+np.savez(out, **res)
+print("DONE")
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pyredner")), reason="reference checkout not present")
+def test_unmodified_pyredner_gives_the_same_numbers_on_either_native_module(tmp_path):
+    """The drop-in claim, numerically, without a GPU: the UNMODIFIED pyredner (its own serialize / unpack / forward / backward)
+    renders and differentiates one scene twice -- on the reference's pybind module and on redner_b200/dropin/redner.py bound to
+    the host build of the device headers (tools/cpu_emu, test infrastructure) -- and every number must agree."""
+    import numpy as np
+    import test_device_code_cpu as tdc
+    emu = tdc._build()
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref")):
+        pytest.skip("oracle/_ref not built")
+    code = E2E_SCRIPT % {"dropin": os.path.join(ROOT, "redner_b200", "dropin"), "ref": REF, "root": ROOT}
+    outs = {}
+    for native in ("reference", emu):
+        path = str(tmp_path / ("ref.npz" if native == "reference" else "ours.npz"))
+        r = subprocess.run([sys.executable, "-W", "ignore", "-c", code, native, path], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "DONE" in r.stdout, r.stderr[-3000:]
+        outs[native] = dict(np.load(path))
+    a, b = outs["reference"], outs[emu]
+    rel = lambda x, y: float(np.linalg.norm(x.astype(np.float64) - y) / max(np.linalg.norm(y), 1e-30))  # noqa: E731
+    for k in a:
+        if np.linalg.norm(a[k]) < 1e-4:  # (e.g. the roughness of a surface no specular path reaches)
+            continue
+        tol = 1e-5 if k.endswith("image") else (2e-3 if k.startswith("edge_") else 2e-4)  # edge rays graze silhouettes: a hit may flip
+        assert rel(b[k], a[k]) < tol, (k, rel(b[k], a[k]))
