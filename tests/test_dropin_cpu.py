@@ -141,6 +141,22 @@ img2 = pyredner.RenderFunction.apply(5, *args)
 img2.pow(2).sum().backward()
 res.update(edge_image=img2.detach().numpy(), edge_position=cam.position.grad.numpy(), edge_look_at=cam.look_at.grad.numpy(), edge_up=cam.up.grad.numpy(),
            edge_tri=tri_v.grad.numpy())
+# pass 3: the callers either side of the path (SURVEY.md 8f ranks 2-3), untouched: deferred shading of a G-buffer and a
+# BATCH of two scenes through pyredner.render_g_buffer (pyredner/render_utils.py:104-313, :431-503)
+for t in (cam.position, cam.look_at, cam.up, tri_v):
+    t.grad = None
+dl = [pyredner.PointLight(position=torch.tensor([0.5, 2.5, -1.0]), intensity=torch.tensor([8.0, 8.0, 8.0])),
+      pyredner.AmbientLight(intensity=torch.tensor([0.1, 0.1, 0.1]))]
+img3 = pyredner.render_deferred(scene, lights=dl, aa_samples=2, seed=11, device=torch.device("cpu"))
+img3.pow(2).sum().backward()
+res.update(deferred_image=img3.detach().numpy(), deferred_position=cam.position.grad.numpy().copy(), deferred_tri=tri_v.grad.numpy().copy())
+cam2 = pyredner.Camera(position=torch.tensor([-0.6, 1.0, -3.5]), look_at=torch.tensor([0.0, 0.5, 0.0]), up=torch.tensor([0.0, 1.0, 0.0]), fov=torch.tensor([50.0]),
+                       clip_near=1e-2, resolution=(24, 28))
+scene2 = pyredner.Scene(cam2, scene.shapes, scene.materials, scene.area_lights)
+with torch.no_grad():
+    gb = pyredner.render_g_buffer([scene, scene2], channels=[pyredner.channels.position, pyredner.channels.shading_normal, pyredner.channels.diffuse_reflectance],
+                                  num_samples=(2, 2), seed=[13, 14], device=torch.device("cpu"))
+res.update(batch_gbuffer_image=gb.numpy())
 np.savez(out, **res)
 print("DONE")
 '''
