@@ -81,3 +81,13 @@ def test_lean_instantiation_meets_the_goldens_it_serves(emulator_lean):
     names = [n for n, c in pu.CASES.items() if "channels" not in c and c["scene"] in ("single_triangle", "shadow_blocker", "glossy_room", "nmap_room")]
     assert len(names) >= 7
     _check(emulator_lean, names + ["c2_all_vertices_secondary_stat"])
+
+
+def test_random_scene_sweep_against_the_live_reference(emulator):
+    """tools/fuzz_emu.py on a fixed range of seeds: random cameras / meshes / materials / lamps / options rendered and
+    differentiated by the compiled reference and by the host build of the device headers; nothing may be flagged."""
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref")):
+        pytest.skip("oracle/_ref not built")
+    r = subprocess.run([sys.executable, "-W", "ignore", os.path.join(ROOT, "tools", "fuzz_emu.py"), emulator, "0", "80"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert r.stdout.strip().splitlines()[-1] == "flagged 0 of 80", "\n".join(l for l in r.stdout.splitlines() if "<<<<" in l or "ERROR" in l)[-3000:]
