@@ -237,7 +237,7 @@ def main():
                 continue
             a, b = gc[k].numpy().astype(np.float64), gr[k].numpy().astype(np.float64)
             # relative to this gradient, but never below the rounding residue of the case's largest gradient
-            e = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-3 * scale, 1e-12))
+            e = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-3 * scale, 1e-9))
             if e > worst:
                 worst, wk = e, k
         tol = 3e-2 if cfg["edges"] else 1e-3
