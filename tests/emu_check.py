@@ -32,7 +32,7 @@ def main():
         elif name in pu.GBUFFER_CASES:
             pu.assert_gbuffer_matches_golden(name, pu.render_gbuffer(rb, dev, pu.GBUFFER_CASES[name]).numpy())
         else:
-            cfg = pu.CASES[name]
+            cfg = pu.CASES[name] if name in pu.CASES else pu.REFSTREAM_CASES[name]
             img, grads = pu.render_case(rb, dev, cfg, cfg["seed"])
             pu.assert_matches_golden(name, img.numpy(), grads)
         print("ok", name, flush=True)

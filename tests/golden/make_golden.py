@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 import ref_loader  # noqa: E402
-from parity_utils import CASES, GBUFFER_CASES, SCREEN_CASES, STAT_CASES, render_case, render_gbuffer, render_screen_gradient  # noqa: E402
+from parity_utils import CASES, GBUFFER_CASES, REFSTREAM_CASES, SCREEN_CASES, STAT_CASES, render_case, render_gbuffer, render_screen_gradient  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -32,7 +32,7 @@ def main():
     ref = ref_loader.load()
     dev = torch.device("cpu")
     only = set(sys.argv[1:])  # optional: regenerate only the named cases
-    for name, cfg in CASES.items():
+    for name, cfg in list(CASES.items()) + list(REFSTREAM_CASES.items()):
         if only and name not in only:
             continue
         img, grads = render_case(ref, dev, cfg, cfg["seed"])

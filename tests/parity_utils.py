@@ -73,6 +73,14 @@ SCREEN_CASES = {
     # (textured floor seen by edge rays: the stale-footprint difference of the primary-edge entries above applies)
     "screen_gradient_fisheye_room": dict(scene="fisheye_room", res=24, spp=2, mb=1, sampler="sobol", edges=1, seed=5, tol=3e-3),
 }
+# Secondary-edge gradients SAMPLE BY SAMPLE: only the host build of the device headers with -DRB_EMU_REF_STREAMS can index the
+# boundary-sample streams by the rank of the pixel in the reference's compacted wavefront (src/pathtracer.cpp:504-505); with
+# that, every gradient of these cases equals the reference's (measured 1e-7 .. 4e-6).  Not run on the GPU.
+REFSTREAM_CASES = {
+    "c1_secondary_exact": dict(scene="single_triangle", res=32, spp=4, mb=2, sampler="sobol", edges=2, seed=2),
+    "c2_all_vertices_secondary_exact": dict(scene="shadow_blocker_all", res=32, spp=8, mb=2, sampler="sobol", edges=2, seed=1),
+    "c1_both_edge_samplers_exact": dict(scene="single_triangle", res=32, spp=4, mb=1, sampler="sobol", edges=3, seed=2),
+}
 STAT_CASES = {
     # secondary-edge (shadow) gradient of the blocker: mean over seeds +- standard error
     "c2_shadow_blocker_secondary_stat": dict(scene="shadow_blocker", res=64, spp=64, mb=1, sampler="sobol", edges=3, seeds=list(range(1, 9)),
@@ -162,7 +170,7 @@ CHANNEL_WIDTH = {"radiance": 3, "alpha": 1, "depth": 1, "position": 3, "geometry
 
 def assert_matches_golden(name, img, grads):
     """Image and every gradient of golden case `name` (numpy image, dict of torch gradients) within the suite's tolerances."""
-    cfg = CASES[name]
+    cfg = CASES[name] if name in CASES else REFSTREAM_CASES[name]
     g = load_golden(name)
     assert rel_l2(img, g["image"]) < IMG_TOL
     exact_vertices = not (cfg["sampler"] == "independent" and cfg["edges"])  # PCG edge streams depend on global compaction

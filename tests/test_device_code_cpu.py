@@ -91,3 +91,9 @@ def test_random_scene_sweep_against_the_live_reference(emulator):
     r = subprocess.run([sys.executable, "-W", "ignore", os.path.join(ROOT, "tools", "fuzz_emu.py"), emulator, "0", "80"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     assert r.stdout.strip().splitlines()[-1] == "flagged 0 of 80", "\n".join(l for l in r.stdout.splitlines() if "<<<<" in l or "ERROR" in l)[-3000:]
+
+
+def test_secondary_edges_sample_by_sample_with_the_reference_streams():
+    """a17 without statistics: with the boundary-sample streams indexed like the reference's compacted wavefront
+    (-DRB_EMU_REF_STREAMS, possible only in a sequential host build) every secondary-edge gradient equals the reference's."""
+    _check(_build("-DRB_EMU_REF_STREAMS"), list(pu.REFSTREAM_CASES))
