@@ -252,8 +252,6 @@ RB_D int sample_edge_gather(const EdgeCtx& c, const Ray& nee, const Isect& lis, 
     const DevScene& sc = *c.sc;
     int stack[RB_EDGE_STACK_L];
     int sp = 0;
-    int n_cs_items = 0; // entries below this index on the stack belong to ... (we tag 6D nodes with the sign bit instead)
-    (void)n_cs_items;
     int selected = -1;
     Real edge_weight = 0, wsum = 0;
     Real expand = sc.edge_bounds_expand;
