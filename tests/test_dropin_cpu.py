@@ -157,6 +157,25 @@ with torch.no_grad():
     gb = pyredner.render_g_buffer([scene, scene2], channels=[pyredner.channels.position, pyredner.channels.shading_normal, pyredner.channels.diffuse_reflectance],
                                   num_samples=(2, 2), seed=[13, 14], device=torch.device("cpu"))
 res.update(batch_gbuffer_image=gb.numpy())
+# pass 4: a short inverse-rendering loop in the style of tests/test_single_triangle.py: move the triangle towards a target
+# image with Adam, primary-edge (silhouette) gradients driving it; the loss curves must coincide
+with torch.no_grad():
+    target_v = tri_v + torch.tensor([[0.15, -0.1, 0.0], [-0.1, 0.1, 0.05], [0.05, -0.15, 0.0]])
+scene.shapes[1].vertices = target_v
+args = pyredner.RenderFunction.serialize_scene(scene=scene, num_samples=4, max_bounces=1, sampler_type=redner.SamplerType.sobol, use_secondary_edge_sampling=False)
+target = pyredner.RenderFunction.apply(1, *args).detach()
+v = tri_v.detach().clone().requires_grad_(True)
+scene.shapes[1].vertices = v
+opt = torch.optim.Adam([v], lr=2e-2)
+losses = []
+for it in range(8):
+    opt.zero_grad()
+    args = pyredner.RenderFunction.serialize_scene(scene=scene, num_samples=4, max_bounces=1, sampler_type=redner.SamplerType.sobol, use_secondary_edge_sampling=False)
+    loss = (pyredner.RenderFunction.apply(it + 2, *args) - target).pow(2).sum()
+    loss.backward()
+    opt.step()
+    losses.append(float(loss))
+res.update(opt_losses=np.array(losses), opt_vertices=v.detach().numpy())
 np.savez(out, **res)
 print("DONE")
 '''
@@ -184,5 +203,5 @@ def test_unmodified_pyredner_gives_the_same_numbers_on_either_native_module(tmp_
     for k in a:
         if np.linalg.norm(a[k]) < 1e-4:  # (e.g. the roughness of a surface no specular path reaches)
             continue
-        tol = 1e-5 if k.endswith("image") else (2e-3 if k.startswith("edge_") else 2e-4)  # edge rays graze silhouettes: a hit may flip
+        tol = 1e-5 if k.endswith("image") else (2e-3 if k.startswith(("edge_", "opt_")) else 2e-4)  # edge rays graze silhouettes: a hit may flip
         assert rel(b[k], a[k]) < tol, (k, rel(b[k], a[k]))
