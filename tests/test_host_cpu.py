@@ -111,3 +111,49 @@ def test_gloo_world_size_2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def _tile_worker(rank, world, port, emu_so, out_path):
+    """One rank of a REAL sharded render on CPU: the device headers' host build (tools/cpu_emu, test infrastructure) behind the
+    C ABI, stripes through rb_scene_set_partition, framebuffer and gradients through the packed gloo all-reduce."""
+    import ctypes
+    import numpy as np
+    from redner_b200 import _lib
+    _lib._lib = _lib._bind(ctypes.CDLL(emu_so))  # this process only
+    from redner_b200 import redner as rb
+    import parity_utils as pu
+    import scenes
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dev = torch.device("cpu")
+        sc = scenes.glossy_room(dev, resolution=(26, 22))
+        img = rdist.render_tiles(sc, 4, 2, seed=5, rows_per_stripe=4, sampler_type=rb.SamplerType.sobol, device=dev, backend=rb,
+                                 use_primary_edge_sampling=True, use_secondary_edge_sampling=False)
+        img.pow(2).sum().backward()
+        if rank == 0:
+            g = pu.collect_grads(sc)
+            np.savez(out_path, image=img.detach().numpy(), **{k: v.numpy() for k, v in g.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_renders_the_same_image_and_gradients_as_one_rank(tmp_path):
+    """N > 1 with real rendering, on CPU: two gloo ranks render disjoint stripes of one image (and disjoint shares of the
+    primary-edge samples); the all-reduced image must equal the single-rank image bit for bit and every all-reduced gradient
+    the single-rank gradient up to summation order."""
+    import numpy as np
+    import test_device_code_cpu as tdc
+    emu = tdc._build()
+    outs = {}
+    for world in (1, 2):
+        path = str(tmp_path / ("w%d.npz" % world))
+        mp.spawn(_tile_worker, args=(world, _free_port(), emu, path), nprocs=world, join=True)
+        outs[world] = dict(np.load(path))
+    a, b = outs[1], outs[2]
+    assert np.array_equal(a["image"], b["image"])
+    assert set(a) == set(b) and len(a) > 5
+    for k in a:
+        n = np.linalg.norm(a[k])
+        if k != "image" and n > 0:
+            assert np.linalg.norm(a[k] - b[k]) / n < 1e-5, k

@@ -230,7 +230,8 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
         if (opt->channels[i] == RB_CH_RADIANCE) rp.rad_off = off;
         off += rb_channel_width(opt->channels[i], scene->max_generic);
     }
-    rp.part = 0; rp.num_parts = 1; rp.rows_per_stripe = 16;
+    rp.part = scene->part; rp.num_parts = scene->num_parts; rp.rows_per_stripe = scene->rps; // round-robin stripes of rows, as in rb_kernels_body.cuh
+    auto owned = [&](int y) { return (y / rp.rows_per_stripe) % rp.num_parts == rp.part; };
     rp.vp_w = scene->cam.viewport_end[0] - scene->cam.viewport_beg[0];
     rp.vp_h = scene->cam.viewport_end[1] - scene->cam.viewport_beg[1];
     ka.lanes_per_pixel = 1;
@@ -246,6 +247,7 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
     if (image && !only_radiance) {
         for (int y = 0; y < rp.vp_h; y++)
             for (int x = 0; x < rp.vp_w; x++) {
+                if (!owned(y)) continue;
                 int pixel = y * rp.vp_w + x;
                 float acc[RB_MAX_ND] = {0};
                 int ids[3] = {-1, -1, -1}, last = -1;
@@ -271,6 +273,7 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
     } else if (image) {
         for (int y = 0; y < rp.vp_h; y++)
             for (int x = 0; x < rp.vp_w; x++) {
+                if (!owned(y)) continue;
                 int pixel = y * rp.vp_w + x;
                 V3 acc = zero3();
                 for (int s = 0; s < rp.spp; s++) acc += forward_sample(sc, rp, pixel, x, y, s);
@@ -311,6 +314,7 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
         for (int y = 0; y < rp.vp_h; y++)
             for (int x = 0; x < rp.vp_w; x++)
                 for (int s = 0; s < rp.spp; s++) {
+                    if (!owned(y)) continue;
 #ifdef RB_EMU_REF_STREAMS
                     rb_emu_rank = &ranks[((size_t)s * npx + (size_t)y * rp.vp_w + x) * mbr];
 #endif
@@ -321,6 +325,7 @@ extern "C" int rb_render(const rb_scene* scene, const rb_options* opt, float* im
             long long n_px = (long long)rp.vp_w * rp.vp_h;
             for (long long i = 0; i < n_px; i++)
                 for (int s = 0; s < rp.spp; s++) {
+                    if (i % rp.num_parts != rp.part) continue; // primary-edge samples are sharded by sample index
                     primary_edge_sample(sc, ka, i, s, primary_edge_dim_base(sc, rp), acc);
                     for (int k = 0; k < RB_CAM_ACC; k++) { cam_accum[k] += cam_f[k]; cam_f[k] = 0.f; }
                 }
