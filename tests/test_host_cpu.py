@@ -129,8 +129,8 @@ def _tile_worker(rank, world, port, emu_so, out_path):
         dev = torch.device("cpu")
         sc = scenes.glossy_room(dev, resolution=(26, 22))
         img = rdist.render_tiles(sc, 4, 2, seed=5, rows_per_stripe=4, sampler_type=rb.SamplerType.sobol, device=dev, backend=rb,
-                                 use_primary_edge_sampling=True, use_secondary_edge_sampling=False)
-        img.pow(2).sum().backward()
+                                 use_primary_edge_sampling=True, use_secondary_edge_sampling=True)  # (the boundary-term pick is a pure function
+        img.pow(2).sum().backward()                                                                    # of pixel, sample and depth: shardable)
         if rank == 0:
             g = pu.collect_grads(sc)
             np.savez(out_path, image=img.detach().numpy(), **{k: v.numpy() for k, v in g.items()})
