@@ -63,6 +63,24 @@ typedef float Real;
 #define RB_INV_PI Real(0.31830988618379067154)
 
 RB_HD Real rb_sq(Real x) { return x * x; }
+// a * b + c with TWO roundings, never contracted into an FMA.  Used where the reference's un-fused double arithmetic produces
+// exact values that decisions hang on: a hit point `org + t * dir` on an axis-aligned plane comes out EXACTLY on the plane for
+// ~85 % of the rays when product and sum are rounded separately (t is the rounded root of that very equation), and a few ulps
+// above or BELOW it with an FMA -- and `inside(box, p)` of the edge hierarchy (src/edge.cpp:1181, src/aabb.h:131-135) flips with it.
+// Measured on B200 (C2, 32x32x8, 64 seeds): boundary terms of the lamp 9.7 sigma off the reference with the contracted form,
+// 1.1 sigma without (profiles/r02_secondary_parity_bisect.txt).
+RB_HD Real rb_mul_add_unfused(Real a, Real b, Real c) {
+#ifdef __CUDA_ARCH__
+#ifdef RB_REAL_DOUBLE
+    return __dadd_rn(__dmul_rn(a, b), c);
+#else
+    return __fadd_rn(__fmul_rn(a, b), c);
+#endif
+#else
+    volatile Real p = a * b; // (host build: keep the compiler from contracting under -mfma / -ffp-contract=fast)
+    return p + c;
+#endif
+}
 RB_HD Real rb_max(Real a, Real b) { return a > b ? a : b; }
 RB_HD Real rb_min(Real a, Real b) { return a < b ? a : b; }
 RB_HD int rb_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

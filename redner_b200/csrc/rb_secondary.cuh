@@ -5,9 +5,10 @@
 //   get_ltc_matrix                            src/edge.cpp:803-814
 //   secondary_edge_weights_updater            src/edge.cpp:1856-1972 (intersect_jacobian :1829-1853)
 //   secondary_edge_derivatives_accumulator    src/edge.cpp:2001-2043
-// The estimator is the reference's; the hierarchy it walks is our own flat, balanced tree (EdgeNode, built in
-// rb_scene_host.hpp) instead of the treelet-optimised pointer LBVH of src/edge_tree.cpp, so individual samples
-// differ from the reference's while the expectation is the same (edge-sampling parity is statistical).
+// The estimator is the reference's and so is the hierarchy it walks (a restatement of src/edge_tree.cpp incl. the treelet
+// pass, flattened into EdgeNode records); what differs from the reference is only which Sobol point a vertex gets (the
+// reference indexes that stream by the rank of the pixel in its compacted wavefront), hence statistical parity on the GPU
+// and sample-exact parity in the host build with -DRB_EMU_REF_STREAMS.
 // Every path keeps its traversal state in a <= 24-entry stack: each stack item carries at least one of the 16
 // stochastic descents, so the hierarchical sampler never holds more than 16 items; the gather variant holds at
 // most two per level of the balanced tree.
@@ -482,10 +483,22 @@ RB_D void secondary_edge_shade(const DevScene& sc, const DevDScene& ds, const Re
     const V3 sample_p = pk.sample_p, mwt = pk.mwt;
     const Edge edge = sc.edges[edge_id];
     V3 v0 = edge_v0(sc.shapes, edge), v1 = edge_v1(sc.shapes, edge);
-    V3 hpn = normalize(cross(v0 - sp.position, v1 - sp.position));
-    Real plen = length(sample_p);
-    Real offset = Real(1e-5) / plen;
-    V3 sdir = normalize(sample_p);
+    // The two edge rays differ by 1e-5 / |sample_p| in direction -- ten to thirty fp32 ulps.  The reference builds them in double and
+    // rounds to float once for Embree (src/edge.cpp:1670-1678, src/scene.cpp:559-566); so do we (in fp32, with 2-ulp division and
+    // square root, the perturbation drowns in the rounding of the normalisations and the +nt / -nt sides stop being symmetric).
+    D3 hp_d, sd_d;
+    double plen_d;
+    {
+        D3 a = d3((double)v0.x - (double)sp.position.x, (double)v0.y - (double)sp.position.y, (double)v0.z - (double)sp.position.z);
+        D3 b = d3((double)v1.x - (double)sp.position.x, (double)v1.y - (double)sp.position.y, (double)v1.z - (double)sp.position.z);
+        hp_d = d3_normalize(d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x));
+        plen_d = sqrt((double)sample_p.x * (double)sample_p.x + (double)sample_p.y * (double)sample_p.y + (double)sample_p.z * (double)sample_p.z);
+        sd_d = d3((double)sample_p.x / plen_d, (double)sample_p.y / plen_d, (double)sample_p.z / plen_d);
+    }
+    const double offset_d = (double)1e-5f / plen_d;
+    V3 hpn = mk3((Real)hp_d.x, (Real)hp_d.y, (Real)hp_d.z);
+    Real plen = (Real)plen_d;
+    V3 sdir = mk3((Real)sd_d.x, (Real)sd_d.y, (Real)sd_d.z);
     V3 f = bsdf_eval(mat, sp, wi, sdir, min_rough);
     if (sum(f) < Real(1e-6)) return;
     // ray differential of the two edge rays (src/edge.cpp:1703-1733)
@@ -512,7 +525,11 @@ RB_D void secondary_edge_shade(const DevScene& sc, const DevDScene& ds, const Re
     int light_id[2] = {-1, -1};
     for (int k = 0; k < 2; k++) {
         eray[k].org = sp.position;
-        eray[k].dir = normalize(k == 0 ? sdir + offset * hpn : sdir - offset * hpn);
+        {
+            double sg = k == 0 ? offset_d : -offset_d;
+            D3 dk = d3_normalize(d3(sd_d.x + sg * hp_d.x, sd_d.y + sg * hp_d.y, sd_d.z + sg * hp_d.z));
+            eray[k].dir = mk3((Real)dk.x, (Real)dk.y, (Real)dk.z);
+        }
         eray[k].tmin = Real(1e-3) * plen;
         eray[k].tmax = INFINITY;
         eis[k] = no_isect();

@@ -189,7 +189,8 @@ RB_HD SurfacePoint make_surface_point(const rb_shape& s, int tri, const Ray& ray
     Real u = h.u, v = h.v, w = 1 - (u + v), t = h.t;
     SurfacePoint p;
     p.uv = w * a.uv0 + u * a.uv1 + v * a.uv2;
-    p.position = ray.org + ray.dir * t;
+    // hit point: product and sum rounded separately like the reference's (src/shape.h:295), see rb_mul_add_unfused
+    p.position = mk3(rb_mul_add_unfused(ray.dir.x, t, ray.org.x), rb_mul_add_unfused(ray.dir.y, t, ray.org.y), rb_mul_add_unfused(ray.dir.z, t, ray.org.z));
     V3 gn = normalize(cross(v1 - v0, v2 - v0));
     V2 uv02 = a.uv0 - a.uv2, uv12 = a.uv1 - a.uv2;
     Real det = uv02.x * uv12.y - uv02.y * uv12.x;

@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 import ref_loader  # noqa: E402
-from parity_utils import CASES, GBUFFER_CASES, REFSTREAM_CASES, SCREEN_CASES, STAT_CASES, render_case, render_gbuffer, render_screen_gradient  # noqa: E402
+from parity_utils import CASES, GBUFFER_CASES, REFSTREAM_CASES, SCREEN_CASES, STAT_CASES, render_case, render_gbuffer, render_screen_gradient, render_stat_case  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -56,16 +56,14 @@ def main():
     for name, cfg in STAT_CASES.items():
         if only and name not in only:
             continue
-        acc = {}
-        for seed in cfg["seeds"]:
-            _, grads = render_case(ref, dev, cfg, seed)
-            for k in cfg["keys"]:
-                acc.setdefault(k, []).append(grads[k].numpy())
+        acc = render_stat_case(ref, dev, name)
         arrs = {}
         for k, lst in acc.items():
             a = np.stack(lst)
             arrs["mean." + k] = a.mean(0)
             arrs["sem." + k] = a.std(0, ddof=1) / np.sqrt(len(lst))
+            if cfg.get("test") == "ranks":  # per-seed values for the two-sample rank test (heavy-tailed estimators)
+                arrs["samples." + k] = a
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
         print(name, {k: float(np.linalg.norm(v)) for k, v in arrs.items()})
 

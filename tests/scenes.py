@@ -7,7 +7,9 @@ plus small procedural scenes (`glossy_room`, `sphere_box`) that exercise the spe
 textures and multi-bounce paths without needing mesh files.
 """
 import math
+import os
 
+import numpy as np
 import torch
 
 from redner_b200 import api
@@ -250,5 +252,100 @@ def nmap_room(device, **kw):
     return glossy_room(device, nmap=True, **kw)
 
 
-SCENES = {"env_ball_fisheye": env_ball_fisheye, "shadow_blocker_all": shadow_blocker_all, "single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
+# ---------------------------------------------------------------------------------------------------- reference meshes
+# BASELINE configs C3 - C5 use the reference's own test scenes.  /root/reference is not on the GPU box, so their arrays
+# were exported once with the reference's unmodified loaders (tests/golden/export_ref_scenes.py) into .npz fixtures.
+_FIXTURE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_fixture_cache = {}
+
+
+def _fixture(name):
+    if name not in _fixture_cache:
+        _fixture_cache[name] = dict(np.load(os.path.join(_FIXTURE_DIR, name + ".npz")))
+    return _fixture_cache[name]
+
+
+def _mitsuba_fixture_scene(name, device, resolution, grad_shapes=(), grad_materials=(), cam_translation=None, cam_grad=False, materials_override=None):
+    f = _fixture(name)
+    res = tuple(int(x) for x in f["cam.resolution"]) if resolution is None else tuple(resolution)
+    pos, look = torch.from_numpy(f["cam.position"]).clone(), torch.from_numpy(f["cam.look_at"]).clone()
+    if cam_translation is not None:
+        pos, look = pos + cam_translation, look + cam_translation
+    up = torch.from_numpy(f["cam.up"]).clone()
+    if cam_grad:
+        pos.requires_grad_(True), look.requires_grad_(True), up.requires_grad_(True)
+    cam = api.Camera(position=pos, look_at=look, up=up, fov=torch.from_numpy(f["cam.fov"]).clone(), clip_near=float(f["cam.clip_near"]), resolution=res)
+    shapes = []
+    for i in range(int(f["num_shapes"])):
+        p = "shape%d." % i
+        opt = {k: torch.from_numpy(f[p + k]).to(device) for k in ("uvs", "normals", "uv_indices", "normal_indices") if p + k in f}
+        v = torch.from_numpy(f[p + "vertices"]).to(device)
+        if i in grad_shapes or (i - int(f["num_shapes"])) in grad_shapes:
+            v.requires_grad_(True)
+        shapes.append(api.Shape(v, torch.from_numpy(f[p + "indices"]).to(device), int(f[p + "material_id"]), **opt))
+    mats = []
+    for i in range(int(f["num_materials"])):
+        p = "mat%d." % i
+        g = i in grad_materials or (i - int(f["num_materials"])) in grad_materials
+        tex = {}
+        for k in ("diffuse", "specular", "roughness"):
+            t = torch.from_numpy(f[p + k + ".texels"]).to(device)
+            if materials_override and (i, k) in materials_override:
+                t = torch.tensor(materials_override[(i, k)], dtype=torch.float32, device=device)
+            if g:
+                t.requires_grad_(True)
+            tex[k] = api.Texture(t, torch.from_numpy(f[p + k + ".uv_scale"]).to(device))
+        mats.append(api.Material(diffuse_reflectance=tex["diffuse"], specular_reflectance=tex["specular"], roughness=tex["roughness"],
+                                 two_sided=bool(f[p + "two_sided"])))
+    lights = [api.AreaLight(int(f["light%d.shape_id" % i]), torch.from_numpy(f["light%d.intensity" % i]).clone(), two_sided=bool(f["light%d.two_sided" % i]))
+              for i in range(int(f["num_lights"]))]
+    return api.Scene(cam, shapes, mats, lights)
+
+
+def teapot(device, resolution=(512, 512), grad=True):
+    """C3, tests/test_teapot_reflectance.py:12-60 (tests/scenes/teapot.xml, 15 712 triangles, 3 lamps, textured floor): the
+    optimisation's initial guess -- teapot material diffuse 0.3 / specular 0.5 / roughness 0.2 and the camera translated by
+    (-0.2, 0.2, -0.2), all differentiable (SVBRDF + camera-pose gradients)."""
+    n = int(_fixture("scene_teapot")["num_materials"])
+    over = {(n - 1, "diffuse"): [0.3, 0.3, 0.3], (n - 1, "specular"): [0.5, 0.5, 0.5], (n - 1, "roughness"): [0.2]}
+    return _mitsuba_fixture_scene("scene_teapot", device, resolution, grad_materials=(-1,) if grad else (), cam_translation=torch.tensor([-0.2, 0.2, -0.2]),
+                                  cam_grad=grad, materials_override=over)
+
+
+def teapot_geometry(device, resolution=(512, 512), grad=True):
+    """C3's scene with the teapot's vertices (lid = shape 4, body = shape 5) differentiable: boundary terms on a 15 k-triangle mesh."""
+    return _mitsuba_fixture_scene("scene_teapot", device, resolution, grad_shapes=(4, 5) if grad else (), cam_translation=torch.tensor([-0.2, 0.2, -0.2]))
+
+
+def bunny_box(device, resolution=(1024, 1024), grad=True, cam_translation=None):
+    """C4, tests/test_bunny_box.py:8-36 (tests/scenes/bunny_box.xml, 14 416 triangles, Cornell-style closed box, deep
+    paths): the bunny's vertices are differentiable (the test's translation / rotation parameters are linear functions of them)."""
+    return _mitsuba_fixture_scene("scene_bunny_box", device, resolution, grad_shapes=(-1,) if grad else (), cam_translation=cam_translation)
+
+
+def bunny_box_shifted(device, **kw):
+    """C4's meshes seen from a camera moved off the box's axis by (0.013, 0.007, 0).  The file's camera sits exactly on the
+    axis of the box, so the floor / wall corners project onto exact pixel diagonals, and the (0, 0), (.5, .5), (.25, .75) ...
+    points of a Sobol pattern put primary rays EXACTLY on an edge shared by two shapes: which of the two a ray then hits is decided
+    by the last bit of two hit distances (in Embree as well as here) and the rest of the path follows.  Sample-exact
+    comparisons with the Sobol sampler use this camera; with the independent sampler the file's camera is used."""
+    return bunny_box(device, cam_translation=torch.tensor([0.013, 0.007, 0.0]), **kw)
+
+
+def teapot_pose(device, k, num_poses=64, resolution=(512, 512), grad=True):
+    """C5 (BASELINE.json configs[4]): pose k of `num_poses` cameras on a circle around the teapot of C3, at the distance
+    and height of the file's camera, looking at the teapot's centre; the pose is differentiable."""
+    sc = teapot(device, resolution=resolution, grad=grad)
+    f = _fixture("scene_teapot")
+    centre = torch.tensor([0.3, 2.6, 0.0])  # centre of the teapot's bounding box (shapes 4 and 5)
+    p0 = torch.from_numpy(f["cam.position"])
+    r = float(torch.linalg.norm((p0 - centre)[[0, 2]]))
+    a = 2.0 * math.pi * k / num_poses
+    pos = torch.tensor([float(centre[0]) + r * math.sin(a), float(p0[1]), float(centre[2]) + r * math.cos(a)])
+    sc.camera = api.Camera(position=pos.requires_grad_(grad), look_at=centre.clone().requires_grad_(grad), up=torch.tensor([0.0, 1.0, 0.0], requires_grad=grad),
+                           fov=torch.from_numpy(f["cam.fov"]).clone(), clip_near=float(f["cam.clip_near"]), resolution=tuple(resolution))
+    return sc
+
+
+SCENES = {"teapot": teapot, "bunny_box": bunny_box, "bunny_box_shifted": bunny_box_shifted, "teapot_geometry": teapot_geometry, "env_ball_fisheye": env_ball_fisheye, "shadow_blocker_all": shadow_blocker_all, "single_triangle": single_triangle, "shadow_blocker": shadow_blocker, "glossy_room": glossy_room, "random_soup": random_soup,
           "nmap_room": nmap_room, "corner_ball": corner_ball, "hires_room": hires_room, "ortho_room": ortho_room, "distort_room": distort_room, "fisheye_room": fisheye_room, "panorama_room": panorama_room, "env_ball": env_ball, "env_ball_flat_sky": env_ball_flat_sky}

@@ -64,7 +64,7 @@ def _scene_dict(sc):
 @pytest.mark.parametrize("name", ["c1_single_triangle_sobol", "c1_single_triangle_pcg", "c2_shadow_blocker_sobol"])
 def test_restatement_matches_golden(name):
     cfg = pu.CASES[name]
-    sc = scenes.SCENES[cfg["scene"]](torch.device("cpu"), resolution=(cfg["res"], cfg["res"]))
+    sc = scenes.SCENES[cfg["scene"]](torch.device("cpu"), resolution=pu._res(cfg))
     img = restate.render_forward(_scene_dict(sc), cfg["spp"], cfg["seed"], cfg["sampler"])
     g = pu.load_golden(name)["image"]
     assert pu.rel_l2(img, g) < 1e-6  # measured 4e-8 .. 6e-8 (the golden is fp32)
