@@ -30,6 +30,12 @@ load_serialized material parallel path_contribution pathtracer pcg_sampler prima
 primary_intersection rebuild_topology redner scene shape sobol_sampler"
 CXXFLAGS="-std=c++14 -O3 -fPIC -fvisibility=hidden -w -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP \
 -I$REF/thrust -I$REF/redner-dependencies/embree/include -I$REF -I$PYINC -I$PBINC"
+# The reference's Python package, unmodified, next to its native module (git-ignored like everything under oracle/_ref): the
+# GPU box has no /root/reference, and the drop-in test there runs THIS pyredner on redner_b200/dropin/redner.py.
+mkdir -p "$OUT"
+rm -rf "$OUT/pyredner"
+cp -r "$REF/pyredner" "$OUT/pyredner"
+find "$OUT/pyredner" -name __pycache__ -prune -exec rm -rf {} + 2>/dev/null || true
 if [ -f "$TARGET" ] && [ -z "${FORCE:-}" ]; then
     echo "[oracle] $TARGET already built"
     exit 0

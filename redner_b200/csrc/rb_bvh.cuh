@@ -14,7 +14,6 @@
 #pragma once
 #include "rb_types.cuh"
 
-#define RB_BVH_STACK 64
 
 RB_D float rb_msub(float a, float b, float c) { return fmaf(a, b, -c); }
 struct F3 {
@@ -52,16 +51,16 @@ RB_D bool tri_test(F3 O, F3 D, float tnear, float tfar, const BVHTri& tri, float
 }
 
 struct BoxRay {
-    float ox, oy, oz;    // org * inv_dir (negated use)
+    float nx, ny, nz;    // -org / dir
     float ix, iy, iz;    // 1 / dir
 };
 RB_D float safe_rcp(float d) { return 1.0f / (fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); }
 
-// slab test for one child box; returns entry distance or +inf when missed
+// slab test for one child box; returns entry distance or +inf when missed.  One FMA per plane: (b - o) / d == b * (1/d) - o * (1/d).
 RB_D float box_test(const BoxRay& r, float lox, float hix, float loy, float hiy, float loz, float hiz, float tnear, float tfar) {
-    float tx0 = (lox - r.ox) * r.ix, tx1 = (hix - r.ox) * r.ix;
-    float ty0 = (loy - r.oy) * r.iy, ty1 = (hiy - r.oy) * r.iy;
-    float tz0 = (loz - r.oz) * r.iz, tz1 = (hiz - r.oz) * r.iz;
+    float tx0 = fmaf(lox, r.ix, r.nx), tx1 = fmaf(hix, r.ix, r.nx);
+    float ty0 = fmaf(loy, r.iy, r.ny), ty1 = fmaf(hiy, r.iy, r.ny);
+    float tz0 = fmaf(loz, r.iz, r.nz), tz1 = fmaf(hiz, r.iz, r.nz);
     float t0 = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tnear));
     float t1 = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tfar));
     // boxes are padded at build time; the extra relative slack covers the rounding of the slab products
@@ -81,6 +80,12 @@ struct BvhHit { // returned in registers
 #else
 #define RB_BVH_FN RB_D
 #endif
+// Two traversal loops were measured on B200 (profiles/r02_bvh_loop_ab.txt; teapot 512x512x32 / bunny box 512x512x16, k_forward ms):
+//   one loop, "inner node or leaf" per iteration (this one)                14.4 / 20.9
+//   "while-while" (Aila & Laine 2009: descend to a leaf, then test)        15.9 / 23.8   -- kept below under RB_BVH_WHILE_WHILE
+// With ONE triangle per leaf a leaf test costs about as much as an inner step, so batching the leaf tests buys nothing and the
+// second loop's extra control flow loses ~10 %.
+#ifndef RB_BVH_WHILE_WHILE
 template <bool ANY_HIT>
 RB_BVH_FN BvhHit bvh_trace_impl(const float4* __restrict__ nodes4, const float4* __restrict__ tris4, int root, int num_tris, float ox, float oy,
                              float oz, float dx, float dy, float dz, float tnear, float tfar) {
@@ -97,7 +102,7 @@ RB_BVH_FN BvhHit bvh_trace_impl(const float4* __restrict__ nodes4, const float4*
     if (!(tfar >= tnear)) return res;
     BoxRay br;
     br.ix = safe_rcp(D.x); br.iy = safe_rcp(D.y); br.iz = safe_rcp(D.z);
-    br.ox = O.x; br.oy = O.y; br.oz = O.z;
+    br.nx = -O.x * br.ix; br.ny = -O.y * br.iy; br.nz = -O.z * br.iz;
     int stack[RB_BVH_STACK];
     int sp = 0;
     int node = root;
@@ -145,6 +150,73 @@ RB_BVH_FN BvhHit bvh_trace_impl(const float4* __restrict__ nodes4, const float4*
     res.t = tfar;
     return res;
 }
+#else
+#define RB_BVH_DONE 0x7fffffff
+// "while-while" traversal (Aila & Laine 2009): every lane descends through inner nodes until it holds a leaf (or is done), then
+// the lanes of the warp test their triangles together.  With one loop that handles "inner node or leaf" per iteration the lanes
+// of a warp sat in different halves of the body most of the time: 8 of 32 lanes active in this function on the teapot
+// (profiles/r02_teapot_*), against 28 on the 6-triangle scene of C2.
+template <bool ANY_HIT>
+RB_BVH_FN BvhHit bvh_trace_impl(const float4* __restrict__ nodes4, const float4* __restrict__ tris4, int root, int num_tris, float ox, float oy,
+                             float oz, float dx, float dy, float dz, float tnear, float tfar) {
+    BvhHit res;
+    res.shape_id = -1;
+    res.tri_id = -1;
+    res.t = tfar;
+    res.hit = 0;
+    F3 O = f3(ox, oy, oz);
+    F3 D = f3(dx, dy, dz);
+    if (num_tris <= 0) return res;
+    // zero / degenerate directions never hit (src/scene.cpp:577-578)
+    if (D.x * D.x + D.y * D.y + D.z * D.z <= 1e-3f) return res;
+    if (!(tfar >= tnear)) return res;
+    BoxRay br;
+    br.ix = safe_rcp(D.x); br.iy = safe_rcp(D.y); br.iz = safe_rcp(D.z);
+    br.nx = -O.x * br.ix; br.ny = -O.y * br.iy; br.nz = -O.z * br.iz;
+    int stack[RB_BVH_STACK];
+    int sp = 0;
+    int node = root;
+    while (node != RB_BVH_DONE) {
+        while (node >= 0 && node != RB_BVH_DONE) {
+            float4 bx = __ldg(nodes4 + 4 * (size_t)node + 0);
+            float4 by = __ldg(nodes4 + 4 * (size_t)node + 1);
+            float4 bz = __ldg(nodes4 + 4 * (size_t)node + 2);
+            float4 ch = __ldg(nodes4 + 4 * (size_t)node + 3);
+            int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
+            float tl = box_test(br, bx.x, bx.y, by.x, by.y, bz.x, bz.y, tnear, tfar);
+            float tr = box_test(br, bx.z, bx.w, by.z, by.w, bz.z, bz.w, tnear, tfar);
+            bool hl = tl < INFINITY, hr = tr < INFINITY;
+            if (hl && hr) {
+                bool swap = tr < tl;
+                node = swap ? right : left;
+                stack[sp++] = swap ? left : right; // (depth < RB_BVH_STACK is guaranteed by rb_build_bvh)
+            } else if (hl | hr) {
+                node = hl ? left : right;
+            } else {
+                node = sp > 0 ? stack[--sp] : RB_BVH_DONE;
+            }
+        }
+        if (node != RB_BVH_DONE) {
+            int slot = ~node;
+            BVHTri tri;
+            tri.v0 = __ldg(tris4 + 3 * (size_t)slot + 0);
+            tri.v1 = __ldg(tris4 + 3 * (size_t)slot + 1);
+            tri.v2 = __ldg(tris4 + 3 * (size_t)slot + 2);
+            float t;
+            if (tri_test(O, D, tnear, tfar, tri, t)) {
+                res.hit = 1;
+                tfar = t;
+                res.shape_id = __float_as_int(tri.v0.w);
+                res.tri_id = __float_as_int(tri.v1.w);
+                if (ANY_HIT) break;
+            }
+            node = sp > 0 ? stack[--sp] : RB_BVH_DONE;
+        }
+    }
+    res.t = tfar;
+    return res;
+}
+#endif
 template <bool ANY_HIT>
 RB_D bool bvh_trace(const DevScene& sc, const Ray& ray, int& shape_id, int& tri_id, float& t_hit) {
     BvhHit h = bvh_trace_impl<ANY_HIT>(reinterpret_cast<const float4*>(sc.bvh_nodes), reinterpret_cast<const float4*>(sc.bvh_tris), sc.bvh_root,

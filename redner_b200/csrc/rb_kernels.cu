@@ -4,9 +4,9 @@
 // bounce per sample, with every per-path field (5.5 - 9.4 KB/pixel in double) streamed through managed memory between
 // stage functors.  Here a path lives in registers inside a kernel and only a 128-byte record per path vertex crosses kernels:
 //   forward    k_forward / k_forward_channels   camera sample -> primary hit -> emission -> bounce loop -> pixel
-//   backward   per band of samples:  k_bwd_trace (primal replay, records) -> scan + k_bwd_compact (path / vertex lists)
-//              -> k_bwd_sec_pick -> radix sort by edge -> k_bwd_sec_shade (boundary terms) -> k_bwd_sweep (reverse sweep,
-//              first-hit and camera adjoints);  then k_prim_keys -> radix sort -> k_primary_edge;  k_finish_camera
+//   backward   per band of samples:  k_bwd_trace (primal replay, records, work lists by warp ballot) -> k_bwd_sec_pick ->
+//              counting sort by edge (k_sec_offsets, k_sec_scatter) -> k_bwd_sec_shade (boundary terms) -> k_bwd_sweep (reverse
+//              sweep, first-hit and camera adjoints);  then k_prim_keys -> radix sort -> k_primary_edge;  k_finish_camera
 // Every kernel is small enough for the GPC instruction cache and walks the stages of a sample block-synchronously
 // (RB_PHASE_SYNC): a fused megakernel of the same code ran instruction-fetch bound at 6 % issue utilisation.
 // Forward: a warp owns 32/L pixels with L lanes per pixel (L = min(32, 2^floor(log2 spp))); lanes of a pixel are its
@@ -17,7 +17,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -38,13 +39,12 @@
 // serialises concurrent backward passes on one device; rb_release_scratch() frees everything.
 #include <mutex>
 struct DeviceScratch {
+    std::mutex mutex; // one backward pass per DEVICE at a time; passes on different devices of one process run concurrently
     char* ptr = nullptr;
     size_t bytes = 0;
 };
-static std::mutex g_scratch_mutex;
 static DeviceScratch g_scratch[64];
-static char* scratch_ensure(int device, size_t bytes) {
-    DeviceScratch& sc = g_scratch[device & 63];
+static char* scratch_ensure(DeviceScratch& sc, size_t bytes) { // (caller holds sc.mutex and has made the device current)
     if (sc.bytes >= bytes) return sc.ptr;
     if (sc.ptr) {
         cudaDeviceSynchronize();
@@ -60,36 +60,34 @@ static char* scratch_ensure(int device, size_t bytes) {
     return sc.ptr;
 }
 extern "C" void rb_release_scratch(void) {
-    std::lock_guard<std::mutex> lock(g_scratch_mutex);
     int prev = 0;
     cudaGetDevice(&prev);
-    for (int d = 0; d < 64; d++)
+    for (int d = 0; d < 64; d++) {
+        std::lock_guard<std::mutex> lock(g_scratch[d].mutex);
         if (g_scratch[d].ptr) {
             cudaSetDevice(d);
             cudaDeviceSynchronize();
             cudaFree(g_scratch[d].ptr);
-            g_scratch[d] = DeviceScratch();
+            g_scratch[d].ptr = nullptr;
+            g_scratch[d].bytes = 0;
         }
+    }
     cudaSetDevice(prev);
 }
-// Destroys the timing events and restores the caller's current device on EVERY exit path of rb_render (RB_CUDA_OK returns).
+// Restores the caller's current device on EVERY exit path of rb_render (RB_CUDA_OK returns).
 struct RenderGuard {
     int prev_device = -1;
-    cudaEvent_t ev[5] = {};
-    int num_ev = 0;
-    std::vector<cudaEvent_t> band_events; // 4 per backward band: start, after trace, after compaction+secondary, after sweep
     ~RenderGuard() {
-        for (cudaEvent_t e : band_events) cudaEventDestroy(e);
-        for (int i = 0; i < num_ev; i++) cudaEventDestroy(ev[i]);
         if (prev_device >= 0) cudaSetDevice(prev_device);
     }
 };
-static int pick_grid(const void* kernel, int device, int* blocks_per_sm_out) {
+// Persistent grid of a kernel: SMs x resident blocks per SM for its block size and dynamic shared memory.
+static int pick_grid(const void* kernel, int device, int block = RB_BLOCK, size_t smem = 0) {
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RB_BLOCK, 0);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
     if (per_sm < 1) per_sm = 1;
-    if (blocks_per_sm_out) *blocks_per_sm_out = per_sm;
     return sms * per_sm;
 }
 
@@ -180,27 +178,31 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
     guard.prev_device = prev;
     cudaStream_t stream = (cudaStream_t)stream_;
     // per-kernel CUDA events on the render stream: [0] start, [1] after k_forward, [2] after the backward bands,
-    // [3] after k_primary_edge, [4] after k_finish_camera
-    cudaEvent_t* ev = guard.ev;
-    for (int i = 0; i < 5; i++) {
-        RB_CUDA_OK(cudaEventCreate(&ev[i]));
-        guard.num_ev = i + 1;
+    // [3] after k_primary_edge, [4] after k_finish_camera; then 4 per backward band.  The events belong to the scene and are
+    // reused by every call (creating ~40 events per call cost more than the kernels of a small render).
+    EventPool& events = scene->events;
+    if (!events.ensure(5)) {
+        rb_set_error("rb_render: cudaEventCreate failed");
+        return 1;
     }
+std::vector<cudaEvent_t>& ev = events.ev;
     int launches = 0;
-    double host_stats[2] = {0, 0};
-    std::unique_lock<std::mutex> scratch_lock(g_scratch_mutex, std::defer_lock); // (released before the guard runs)
-    std::vector<cudaEvent_t>& band_events = guard.band_events;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, scene->device);
+    std::vector<BandCounters> host_counters;
+    long long num_bands_done = 0;
+    std::unique_lock<std::mutex> scratch_lock; // per-device scratch, held for the backward pass (released before the guard runs)
     RB_CUDA_OK(cudaEventRecord(ev[0], stream));
     if (image != nullptr) {
         if (only_radiance) {
             if (lean) {
                 la::forward(&scene->dev, &ka, la::grid(la::K_FORWARD, scene->device), stream);
             } else {
-                int grid = pick_grid((const void*)k_forward, scene->device, nullptr);
-                k_forward<<<grid, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+                int grid = pick_grid((const void*)k_forward, scene->device, RB_BLOCK_FWD);
+                k_forward<<<grid, RB_BLOCK_FWD, 0, stream>>>(scene->dev, ka);
             }
         } else {
-            int grid = pick_grid((const void*)k_forward_channels, scene->device, nullptr);
+            int grid = pick_grid((const void*)k_forward_channels, scene->device);
             k_forward_channels<<<grid, RB_BLOCK, 0, stream>>>(scene->dev, ka);
         }
         launches++;
@@ -216,12 +218,16 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             rb_set_error("rb_render: d_scene does not match the scene (shape / material / light counts)");
             return 1;
         }
-        // ---- scratch layout: gradient descriptors | camera accumulators | band (records, boundary terms, lists, scan)
+        // ---- scratch layout: gradient descriptors | camera accumulators | band (records, boundary terms, work lists)
         const bool secondary = scene->dev.use_secondary_edge && scene->dev.num_edges > 0 && scene->dev.num_lights > 0 && rp.rad_dim >= 0;
         const long long total_samples = (long long)ka.owned_rows * rp.vp_w * rp.spp;
         ka.rec_per_sample = rp.max_bounces + 1;
-        const size_t per_sample = (size_t)ka.rec_per_sample * (sizeof(VertexRec) + (secondary ? sizeof(V3) + sizeof(EdgePick) + 16 + 8 : 0) + sizeof(int)) + 2 * sizeof(int) +
-                                  sizeof(unsigned long long);
+        if (secondary && rp.max_bounces > 64) {
+            rb_set_error("rb_render: secondary edge sampling supports at most 64 bounces");
+            return 1;
+        }
+        const size_t per_sample = (size_t)ka.rec_per_sample * (sizeof(VertexRec) + (secondary ? sizeof(V3) + sizeof(EdgePick) + 16 : 0)) + 2 * sizeof(int) +
+                                  sizeof(ListCount) + (secondary ? sizeof(ulonglong2) : 0);
         size_t band_bytes = RB_BAND_BYTES;
         if (const char* env = getenv("RB_BAND_BYTES")) { // test hook: force many small bands
             long long v = atoll(env);
@@ -230,28 +236,31 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         long long band = (long long)std::max<size_t>(band_bytes / per_sample, 1024);
         band = std::min<long long>(band, (1LL << 30) / ka.rec_per_sample);
         band = std::min<long long>(band, std::max<long long>(total_samples, 1));
-        size_t scan_bytes = 0;
-        cub::TransformInputIterator<unsigned long long, CountOp, const int*> probe((const int*)nullptr, CountOp());
-        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, probe, (unsigned long long*)nullptr, (int)band, stream);
+        const long long num_bands = (total_samples + band - 1) / band;
+        if (!events.ensure((size_t)(5 + 4 * num_bands))) {
+            rb_set_error("rb_render: cudaEventCreate failed");
+            return 1;
+        }
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
         size_t nb_shapes = std::max(1, d_scene->num_shapes) * sizeof(rb_dshape), nb_mats = std::max(1, d_scene->num_materials) * sizeof(rb_material),
                nb_lights = std::max(1, d_scene->num_lights) * sizeof(float*);
         size_t o_shapes = 0, o_mats = o_shapes + al(nb_shapes), o_lights = o_mats + al(nb_mats), o_cam = o_lights + al(nb_lights);
-        size_t o_rec = o_cam + al((RB_CAM_ACC + 2) * sizeof(double)), o_dpos = o_rec + al((size_t)band * ka.rec_per_sample * sizeof(VertexRec));
+        size_t o_cnt = o_cam + al(RB_CAM_ACC * sizeof(double));
+        const size_t n_edges = (size_t)std::max(scene->dev.num_edges, 1);
+        size_t o_hist = o_cnt + al((size_t)num_bands * sizeof(BandCounters)), o_eoffs = o_hist + al(secondary ? n_edges * 4 : 0);
+        size_t o_ecur = o_eoffs + al(secondary ? n_edges * 4 : 0);
+        size_t o_rec = o_ecur + al(secondary ? n_edges * 4 : 0), o_dpos = o_rec + al((size_t)band * ka.rec_per_sample * sizeof(VertexRec));
         size_t o_nrec = o_dpos + al(secondary ? (size_t)band * ka.rec_per_sample * sizeof(V3) : 0);
-        size_t o_offs = o_nrec + al((size_t)band * sizeof(int)), o_paths = o_offs + al((size_t)band * sizeof(unsigned long long));
-        size_t o_verts = o_paths + al((size_t)band * sizeof(int)), o_tot = o_verts + al((size_t)band * ka.rec_per_sample * sizeof(int));
-        size_t o_scan = o_tot + 256;
-        // boundary terms: edge picks, (edge, vertex) sort buffers, radix-sort temporaries
-        const size_t max_verts = (size_t)band * ka.rec_per_sample;
-        size_t sec_sort_bytes = 0;
-        if (secondary)
-            cub::DeviceRadixSort::SortPairs(nullptr, sec_sort_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const unsigned*)nullptr, (unsigned*)nullptr, (int)max_verts, 0, 32,
-                                            stream);
-        size_t o_picks = o_scan + al(scan_bytes), o_sk0 = o_picks + al(secondary ? max_verts * sizeof(EdgePick) : 0);
-        size_t o_sv0 = o_sk0 + al(secondary ? max_verts * 4 : 0), o_sk1 = o_sv0 + al(secondary ? max_verts * 4 : 0), o_sv1 = o_sk1 + al(secondary ? max_verts * 4 : 0);
-        size_t o_ssort = o_sv1 + al(secondary ? max_verts * 4 : 0);
-        size_t scratch_bytes = o_ssort + al(sec_sort_bytes);
+        size_t o_vmask = o_nrec + al((size_t)band * sizeof(int)), o_offs = o_vmask + al(secondary ? (size_t)band * sizeof(ulonglong2) : 0);
+        auto count_it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), ListCountOf{nullptr, nullptr});
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveScan(nullptr, scan_bytes, count_it, (ListCount*)nullptr, ListCountSum(), ListCount{0, 0, 0, 0}, (int)band, stream);
+        size_t o_scan = o_offs + al((size_t)band * sizeof(ListCount)), o_paths = o_scan + al(scan_bytes);
+        // boundary terms: vertex list, edge picks, (edge, vertex) per slot, slots in edge order
+        const size_t vert_cap = (size_t)band * ka.rec_per_sample, slots = vert_cap + 32;
+        size_t o_verts = o_paths + al((size_t)band * sizeof(int)), o_picks = o_verts + al(secondary ? vert_cap * sizeof(int) : 0);
+        size_t o_sk = o_picks + al(secondary ? slots * sizeof(EdgePick) : 0), o_sv = o_sk + al(secondary ? slots * 4 : 0), o_so = o_sv + al(secondary ? slots * 4 : 0);
+        size_t scratch_bytes = o_so + al(secondary ? slots * 4 : 0);
         // primary-edge pass (reuses the band area): keys/values double buffers + radix-sort temporaries
         const bool primary = scene->dev.use_primary_edge && scene->dev.num_edges > 0 && scene->dev.prim_edge_cdf != nullptr;
         const long long n_px_all = (long long)rp.vp_w * rp.vp_h;
@@ -262,8 +271,9 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         size_t o_k0 = o_rec, o_k1 = o_k0 + al((size_t)band_e * 4), o_v0 = o_k1 + al((size_t)band_e * 4), o_v1 = o_v0 + al((size_t)band_e * 4);
         size_t o_sort = o_v1 + al((size_t)band_e * 4);
         if (primary) scratch_bytes = std::max(scratch_bytes, o_sort + al(sort_bytes));
-        scratch_lock.lock();
-        char* scratch = scratch_ensure(scene->device, scratch_bytes);
+        DeviceScratch& dscratch = g_scratch[scene->device & 63];
+        scratch_lock = std::unique_lock<std::mutex>(dscratch.mutex);
+        char* scratch = scratch_ensure(dscratch, scratch_bytes);
         if (!scratch) {
             rb_set_error("rb_render: out of device memory for the backward scratch");
             return 1;
@@ -277,7 +287,8 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             RB_CUDA_OK(cudaMemcpyAsync(d_mats, d_scene->materials, d_scene->num_materials * sizeof(rb_material), cudaMemcpyHostToDevice, stream));
         if (d_scene->num_lights)
             RB_CUDA_OK(cudaMemcpyAsync(d_lights, d_scene->light_intensity, d_scene->num_lights * sizeof(float*), cudaMemcpyHostToDevice, stream));
-        RB_CUDA_OK(cudaMemsetAsync(cam_accum, 0, (RB_CAM_ACC + 2) * sizeof(double), stream));
+        // camera accumulators, per-band counters and the edge histogram are contiguous: one memset
+        RB_CUDA_OK(cudaMemsetAsync(cam_accum, 0, o_eoffs - o_cam, stream));
         ka.ds.shapes = d_shapes;
         ka.ds.materials = d_mats;
         ka.ds.light_intensity = d_lights;
@@ -292,19 +303,24 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             return 1;
         }
 
-        // ---- interior + first-hit adjoints, band by band: trace -> scan/compact -> boundary terms -> sweep
+        // ---- interior + first-hit adjoints, band by band: trace (+ work lists) -> boundary terms (pick, counting sort by edge, shade)
+        //      -> sweep.  Every list size stays on the device: fixed persistent grids, no host synchronisation inside the pass.
+        BandCounters* counters = (BandCounters*)(scratch + o_cnt);
         ka.records = (VertexRec*)(scratch + o_rec);
         ka.dpos = secondary ? (V3*)(scratch + o_dpos) : nullptr;
         ka.nrec = (int*)(scratch + o_nrec);
-        ka.offs = (unsigned long long*)(scratch + o_offs);
+        ka.vmask = (ulonglong2*)(scratch + o_vmask);
+        ListCount* list_offs = (ListCount*)(scratch + o_offs);
         ka.path_list = (int*)(scratch + o_paths);
         ka.vert_list = (int*)(scratch + o_verts);
-        ka.totals = (unsigned long long*)(scratch + o_tot);
+        ka.vert_cap = (int)vert_cap;
         ka.picks = (EdgePick*)(scratch + o_picks);
-        ka.sec_keys = (unsigned*)(scratch + o_sk0);
-        ka.sec_vals = (unsigned*)(scratch + o_sv0);
-        ka.sec_keys_sorted = (unsigned*)(scratch + o_sk1);
-        ka.sec_vals_sorted = (unsigned*)(scratch + o_sv1);
+        ka.sec_keys = (unsigned*)(scratch + o_sk);
+        ka.sec_vals = (unsigned*)(scratch + o_sv);
+        ka.sec_order = (unsigned*)(scratch + o_so);
+        ka.edge_hist = (unsigned*)(scratch + o_hist);
+        ka.edge_offs = (unsigned*)(scratch + o_eoffs);
+        ka.edge_cursor = (unsigned*)(scratch + o_ecur);
         int grid_t, grid_p, grid_s, grid_w;
         if (lean) {
             grid_t = la::grid(la::K_BWD_TRACE, scene->device);
@@ -312,55 +328,50 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
             grid_s = la::grid(la::K_BWD_SEC_SHADE, scene->device);
             grid_w = la::grid(la::K_BWD_SWEEP, scene->device);
         } else {
-            grid_t = pick_grid((const void*)k_bwd_trace, scene->device, nullptr);
-            grid_p = pick_grid((const void*)k_bwd_sec_pick, scene->device, nullptr);
-            grid_s = pick_grid((const void*)k_bwd_sec_shade, scene->device, nullptr);
-            grid_w = pick_grid((const void*)k_bwd_sweep, scene->device, nullptr);
+            grid_t = pick_grid((const void*)k_bwd_trace, scene->device, RB_BLOCK_TRACE);
+            grid_p = pick_grid((const void*)k_bwd_sec_pick, scene->device, RB_BLOCK_SEC);
+            grid_s = pick_grid((const void*)k_bwd_sec_shade, scene->device, RB_BLOCK_SEC);
+            grid_w = pick_grid((const void*)k_bwd_sweep, scene->device, RB_BLOCK_SWEEP, RB_SMEM_CAM(RB_BLOCK_SWEEP));
         }
-        int edge_bits = 1; // key range of the boundary-term sort: [0, num_edges]
-        while ((1LL << edge_bits) <= (long long)scene->dev.num_edges && edge_bits < 32) edge_bits++;
-        for (long long i0 = 0; i0 < total_samples; i0 += band) {
+        long long band_idx = 0;
+        for (long long i0 = 0; i0 < total_samples; i0 += band, band_idx++) {
             ka.band_i0 = i0;
             ka.band_n = (int)std::min<long long>(band, total_samples - i0);
-            cudaEvent_t e4[4];
-            for (int i = 0; i < 4; i++) {
-                RB_CUDA_OK(cudaEventCreate(&e4[i]));
-                band_events.push_back(e4[i]);
-            }
+            ka.counters = counters + band_idx;
+            cudaEvent_t* e4 = &events.ev[(size_t)(5 + 4 * band_idx)];
             RB_CUDA_OK(cudaEventRecord(e4[0], stream));
             if (lean) la::bwd_trace(&scene->dev, &ka, grid_t, stream);
-            else k_bwd_trace<<<grid_t, RB_BLOCK, 0, stream>>>(scene->dev, ka);
+            else k_bwd_trace<<<grid_t, RB_BLOCK_TRACE, 0, stream>>>(scene->dev, ka);
             RB_CUDA_OK(cudaEventRecord(e4[1], stream));
-            cub::TransformInputIterator<unsigned long long, CountOp, const int*> counts(ka.nrec, CountOp());
-            cub::DeviceScan::ExclusiveSum(scratch + o_scan, scan_bytes, counts, ka.offs, ka.band_n, stream);
-            k_bwd_compact<<<std::min((ka.band_n + 255) / 256, 148 * 8), 256, 0, stream>>>(ka);
-            // the list sizes come back to the host once per band (the only sync inside the pass): exact grids and sort sizes
-            unsigned long long totals_h = 0;
-            RB_CUDA_OK(cudaMemcpyAsync(&totals_h, ka.totals, sizeof(totals_h), cudaMemcpyDeviceToHost, stream));
-            RB_CUDA_OK(cudaStreamSynchronize(stream));
-            ka.n_paths = (int)(totals_h >> 32);
-            ka.n_verts = (int)(totals_h & 0xffffffffULL);
+            {
+                auto counts = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), ListCountOf{ka.nrec, secondary ? ka.vmask : nullptr});
+                RB_CUDA_OK(cub::DeviceScan::ExclusiveScan(scratch + o_scan, scan_bytes, counts, list_offs, ListCountSum(), ListCount{0, 0, 0, 0}, ka.band_n, stream));
+                k_bwd_compact<<<std::min((ka.band_n + 255) / 256, sms * 8), 256, 0, stream>>>(ka, list_offs);
+            }
             launches += 4;
-            if (secondary && ka.n_verts > 0) {
+            if (secondary) {
                 if (lean) la::bwd_sec_pick(&scene->dev, &ka, grid_p, stream);
-                else k_bwd_sec_pick<<<grid_p, RB_BLOCK, 0, stream>>>(scene->dev, ka);
-                cub::DeviceRadixSort::SortPairs(scratch + o_ssort, sec_sort_bytes, ka.sec_keys, ka.sec_keys_sorted, ka.sec_vals, ka.sec_vals_sorted, ka.n_verts, 0, edge_bits,
-                                                stream);
+                else k_bwd_sec_pick<<<grid_p, RB_BLOCK_SEC, 0, stream>>>(scene->dev, ka);
+                k_sec_offsets<<<1, 1024, 0, stream>>>(ka, scene->dev.num_edges);
+                k_sec_scatter<<<sms * 8, 256, 0, stream>>>(ka);
                 if (lean) la::bwd_sec_shade(&scene->dev, &ka, grid_s, stream);
-                else k_bwd_sec_shade<<<grid_s, RB_BLOCK, 0, stream>>>(scene->dev, ka);
-                launches += 2 + 4;
+                else k_bwd_sec_shade<<<grid_s, RB_BLOCK_SEC, 0, stream>>>(scene->dev, ka);
+                launches += 4;
             }
             RB_CUDA_OK(cudaEventRecord(e4[2], stream));
-            if (ka.n_paths > 0) {
-                if (lean) la::bwd_sweep(&scene->dev, &ka, grid_w, stream);
-                else k_bwd_sweep<<<grid_w, RB_BLOCK, 0, stream>>>(scene->dev, ka);
-                launches++;
-            }
+            if (lean) la::bwd_sweep(&scene->dev, &ka, grid_w, stream);
+            else k_bwd_sweep<<<grid_w, RB_BLOCK_SWEEP, RB_SMEM_CAM(RB_BLOCK_SWEEP), stream>>>(scene->dev, ka);
+            launches++;
             RB_CUDA_OK(cudaEventRecord(e4[3], stream));
+        }
+        num_bands_done = band_idx;
+        if (num_bands_done > 0) {
+            host_counters.resize((size_t)num_bands_done);
+            RB_CUDA_OK(cudaMemcpyAsync(host_counters.data(), counters, (size_t)num_bands_done * sizeof(BandCounters), cudaMemcpyDeviceToHost, stream));
         }
         RB_CUDA_OK(cudaEventRecord(ev[2], stream));
         if (scene->dev.use_primary_edge && scene->dev.num_edges > 0 && scene->dev.prim_edge_cdf != nullptr) {
-            int grid_e = lean ? la::grid(la::K_PRIMARY_EDGE, scene->device) : pick_grid((const void*)k_primary_edge, scene->device, nullptr);
+            int grid_e = lean ? la::grid(la::K_PRIMARY_EDGE, scene->device) : pick_grid((const void*)k_primary_edge, scene->device, RB_BLOCK_PRIM, RB_SMEM_CAM(RB_BLOCK_PRIM));
             int dim_base = primary_edge_dim_base(scene->dev, rp);
             unsigned *k0 = (unsigned*)(scratch + o_k0), *k1 = (unsigned*)(scratch + o_k1), *v0 = (unsigned*)(scratch + o_v0), *v1 = (unsigned*)(scratch + o_v1);
             int ebits = 1;
@@ -374,7 +385,7 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
                 int lo = std::max(0, 31 - ebits - 8);
                 cub::DeviceRadixSort::SortPairs(scratch + o_sort, sort_bytes, k0, k1, v0, v1, n, lo, 32, stream);
                 if (lean) la::primary_edge(&scene->dev, &ka, dim_base, t0, n, k1, v1, grid_e, stream);
-                else k_primary_edge<<<grid_e, RB_BLOCK, 0, stream>>>(scene->dev, ka, dim_base, t0, n, k1, v1);
+                else k_primary_edge<<<grid_e, RB_BLOCK_PRIM, RB_SMEM_CAM(RB_BLOCK_PRIM), stream>>>(scene->dev, ka, dim_base, t0, n, k1, v1);
                 launches += 2 + 4;
             }
         }
@@ -382,7 +393,6 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         k_finish_camera<<<1, 32, 0, stream>>>(scene->dev.cam, cam_accum, d_scene->camera);
         launches++;
         RB_CUDA_OK(cudaEventRecord(ev[4], stream));
-        RB_CUDA_OK(cudaMemcpyAsync(host_stats, cam_accum + RB_CAM_ACC, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
     cudaError_t err = cudaStreamSynchronize(stream);
     if (err == cudaSuccess) err = cudaGetLastError();
@@ -395,13 +405,17 @@ extern "C" int rb_render(const rb_scene* scene_, const rb_options* opt, float* i
         if (err == cudaSuccess) cudaEventElapsedTime(&scene->last_stage_ms[i], ev[i], ev[i + 1]);
     }
     for (int i = 0; i < 3; i++) scene->last_bwd_ms[i] = 0.f;
+    double host_stats[2] = {0, 0};
     if (err == cudaSuccess)
-        for (size_t b = 0; b + 3 < band_events.size(); b += 4)
+        for (long long b = 0; b < num_bands_done; b++) {
             for (int i = 0; i < 3; i++) {
                 float t = 0.f;
-                cudaEventElapsedTime(&t, band_events[b + i], band_events[b + i + 1]);
+                cudaEventElapsedTime(&t, events.ev[5 + 4 * b + i], events.ev[5 + 4 * b + i + 1]);
                 scene->last_bwd_ms[i] += t;
             }
+            host_stats[0] += (double)host_counters[(size_t)b].total_vertices;
+            host_stats[1] += (double)host_counters[(size_t)b].total_hits;
+        }
     scene->last_path_vertices = host_stats[0];
     scene->last_primary_hits = host_stats[1];
     if (err != cudaSuccess) {

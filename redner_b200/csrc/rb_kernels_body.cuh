@@ -1,6 +1,36 @@
 // Kernels of rb_render, included by rb_kernels.cu (general instantiation, global namespace) and by rb_kernels_lean.cu
 // (feature-free instantiation, namespace rb_lean, RB_LEAN defined).  No include guard on purpose.
 #define RB_BLOCK 128
+// Threads per block of each kernel family.  The per-sample stages are walked block-synchronously (RB_PHASE_SYNC), so the block
+// size is also the number of threads that share one pass over the instruction stream; see DESIGN.md section 6 for the measurements.
+// Measured on B200 (profiles/r02_block_size_ab.txt; C2 / teapot 512x512x32 / bunny box 512x512x16, ms):
+//   k_forward     128 x 4: 3.55 / 16.8 / 22.1    256 x 2: 3.20 / 14.8 / 21.6    512 x 1: 3.30 / 14.2 / 21.1
+//   k_bwd_sweep   128 x 4: 5.06 / 31.9 / 18.5    256 x 2: 3.71 / 20.6 / 16.4    512 x 1: 3.84 / 14.4 / 16.9   (I-cache bound: 281 KB of SASS)
+//   k_bwd_trace, k_bwd_sec_*, k_primary_edge: within 3 % of each other, 128 or 256 best
+//   without the phase barriers (RB_NO_LOCKSTEP): k_bwd_sweep 12.1 / 234 / 146
+#ifndef RB_BLOCK_FWD
+#define RB_BLOCK_FWD 256
+#undef RB_MIN_BLOCKS_FWD
+#define RB_MIN_BLOCKS_FWD 2
+#endif
+#ifndef RB_BLOCK_TRACE
+#define RB_BLOCK_TRACE 256
+#undef RB_MIN_BLOCKS_TRACE
+#define RB_MIN_BLOCKS_TRACE 2
+#endif
+#ifndef RB_BLOCK_SEC
+#define RB_BLOCK_SEC RB_BLOCK
+#endif
+#ifndef RB_BLOCK_SWEEP
+#define RB_BLOCK_SWEEP 512
+#undef RB_MIN_BLOCKS_SWEEP
+#define RB_MIN_BLOCKS_SWEEP 1
+#endif
+#ifndef RB_BLOCK_PRIM
+#define RB_BLOCK_PRIM RB_BLOCK
+#endif
+// dynamic shared memory: per-thread columns of the camera accumulators (k_bwd_sweep, k_primary_edge)
+#define RB_SMEM_CAM(block) ((size_t)RB_CAM_ACC * (block) * sizeof(float))
 #ifndef RB_MIN_BLOCKS_FWD
 #define RB_MIN_BLOCKS_FWD 4
 #endif
@@ -57,7 +87,7 @@ RB_D WorkItem warp_work(const RenderParams& rp, int L, int owned_rows, long long
 
 // ------------------------------------------------------------------------------------------------ forward
 #define RB_FWD_SYNC() RB_PHASE_SYNC() // measured: k_forward 5.2 -> 3.7 ms on C2 (one I-cache miss serves the block)
-__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_FWD) k_forward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+__global__ void __launch_bounds__(RB_BLOCK_FWD, RB_MIN_BLOCKS_FWD) k_forward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     const RenderParams& rp = ka.rp;
     const int L = ka.lanes_per_pixel;
     const int P = 32 / L;
@@ -178,71 +208,207 @@ RB_D SampleId band_sample(const RenderParams& rp, long long I) {
 #define RB_BLOCK_LOOP(t, n) \
     for (long long t##_base = (long long)blockIdx.x * blockDim.x, t = t##_base + threadIdx.x; t##_base < (n); \
          t##_base += (long long)gridDim.x * blockDim.x, t = t##_base + threadIdx.x)
-// Stage 1: replay the primal path of every sample of the band, one VertexRec per vertex.
-__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_TRACE) k_bwd_trace(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+// Stage 1: replay the primal path of every sample of the band, one VertexRec per vertex.  Also decides, per vertex, whether the
+// boundary stage will look at it at all (secondary edges are only sampled until the first rough bounce, src/edge.cpp:1396-1401)
+// and which strategy its boundary sample takes: the first number of its edge-sampler point < 0.5 -> GATHER, else HIERARCHY
+// (the reference's own per-sample coin, src/edge.cpp:1461-1472); one bit per depth in `vmask`.
+__global__ void __launch_bounds__(RB_BLOCK_TRACE, RB_MIN_BLOCKS_TRACE) k_bwd_trace(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     const RenderParams& rp = ka.rp;
     RB_BLOCK_LOOP(t, ka.band_n) {
         bool act = t < ka.band_n;
         SampleId id = band_sample(rp, ka.band_i0 + (act ? t : 0));
-        int n = bwd_trace(sc, rp, id.pixel, id.px, id.py, id.s, ka.records + (size_t)(act ? t : 0) * ka.rec_per_sample, 1, act);
-        if (act) ka.nrec[t] = n;
+        VertexRec* recs = ka.records + (size_t)(act ? t : 0) * ka.rec_per_sample;
+        int n = bwd_trace(sc, rp, id.pixel, id.px, id.py, id.s, recs, 1, act);
+        if (!act) continue;
+        ka.nrec[t] = n;
+        if (ka.dpos != nullptr) {
+            unsigned long long has = 0, gather = 0;
+            for (int d = 0; d < n && d < 64; d++) {
+                ka.dpos[(size_t)t * ka.rec_per_sample + d] = zero3();
+                if (recs[d].min_rough <= Real(1e-2)) {
+                    has |= 1ULL << d;
+                    if (bwd_edge_sampler(sc, rp, id.pixel, id.s, d, 0).next() < 0.5) gather |= 1ULL << d;
+                }
+            }
+            ka.vmask[t] = make_ulonglong2(has, gather);
+        }
     }
 }
-#ifndef RB_LEAN // the compaction does not depend on scene features
-// (hit << 32 | vertices) of one sample: the scan input
-struct CountOp {
-    __host__ __device__ unsigned long long operator()(int nrec) const { return nrec < 0 ? 0ULL : ((1ULL << 32) | (unsigned long long)nrec); }
+#ifndef RB_LEAN // the work lists do not depend on scene features
+// Stage 2: the work lists of the later stages, in SAMPLE ORDER (an exclusive scan over the band + this kernel; the reference
+// compacts its wavefront with thrust::copy_if and a host read-back per bounce, src/active_pixels.cpp:17-49 -- here every
+// list size stays on the device, `counters`, and the later kernels run fixed persistent grids):
+//   path_list            samples whose primary ray hit something (work items of k_bwd_sweep)
+//   vert_list, front     path vertices whose boundary sample takes the GATHER strategy
+//   vert_list, back      ... the HIERARCHY strategy, filled downwards from the end of the same array: every warp of
+//                        k_bwd_sec_pick then runs one strategy, while the coin itself stays the reference's per-sample one
+struct ListCount {
+    unsigned paths, gather, hier, vertices;
 };
-// Stage 2: deterministic compaction from the exclusive scan: samples that hit something, and their vertices.
-__global__ void k_bwd_compact(const __grid_constant__ KernelArgs ka) {
+struct ListCountSum {
+    __host__ __device__ ListCount operator()(const ListCount& a, const ListCount& b) const {
+        ListCount r;
+        r.paths = a.paths + b.paths;
+        r.gather = a.gather + b.gather;
+        r.hier = a.hier + b.hier;
+        r.vertices = a.vertices + b.vertices;
+        return r;
+    }
+};
+struct ListCountOf {
+    const int* nrec;
+    const ulonglong2* vmask; // null without secondary edge sampling
+    __host__ __device__ ListCount operator()(int t) const {
+        ListCount r;
+        int n = nrec[t];
+        r.paths = n >= 0 ? 1u : 0u;
+        r.vertices = n > 0 ? (unsigned)n : 0u;
+        r.gather = r.hier = 0;
+#ifdef __CUDA_ARCH__
+        if (vmask != nullptr && n > 0) {
+            ulonglong2 m = vmask[t];
+            r.gather = (unsigned)__popcll(m.x & m.y);
+            r.hier = (unsigned)__popcll(m.x & ~m.y);
+        }
+#endif
+        return r;
+    }
+};
+__global__ void k_bwd_compact(const __grid_constant__ KernelArgs ka, const ListCount* offs) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ka.band_n; t += (long long)gridDim.x * blockDim.x) {
-        int n = ka.nrec[t];
-        unsigned long long o = ka.offs[t];
-        if (n >= 0) {
-            ka.path_list[(unsigned)(o >> 32)] = (int)t;
-            unsigned v = (unsigned)(o & 0xffffffffULL);
-            for (int d = 0; d < n; d++) ka.vert_list[v + d] = (int)t * ka.rec_per_sample + d;
+        ListCount o = offs[t];
+        ListCount c = ListCountOf{ka.nrec, ka.dpos != nullptr ? ka.vmask : nullptr}((int)t);
+        if (c.paths) ka.path_list[o.paths] = (int)t;
+        if (c.gather + c.hier > 0) {
+            ulonglong2 m = ka.vmask[t];
+            unsigned g = o.gather, h = o.hier;
+            for (unsigned long long bits = m.x; bits != 0; bits &= bits - 1) {
+                int d = __ffsll((long long)bits) - 1;
+                int e = (int)t * ka.rec_per_sample + d;
+                if ((m.y >> d) & 1ULL) ka.vert_list[g++] = e;
+                else ka.vert_list[(unsigned)ka.vert_cap - 1u - (h++)] = e;
+            }
         }
         if (t == ka.band_n - 1) {
-            unsigned long long tot = o + CountOp()(n);
-            *ka.totals = tot;
-            // statistics for the roofline accounting (mean executed bounces per sample)
-            atomicAdd(&ka.ds.cam_accum[RB_CAM_ACC], (double)(tot & 0xffffffffULL));
-            atomicAdd(&ka.ds.cam_accum[RB_CAM_ACC + 1], (double)(tot >> 32));
+            BandCounters* cnt = ka.counters;
+            cnt->n_paths = o.paths + c.paths;
+            cnt->n_gather = o.gather + c.gather;
+            cnt->n_hier = o.hier + c.hier;
+            cnt->total_vertices = o.vertices + c.vertices; // statistics for the roofline accounting (mean path length, hit fraction)
+            cnt->total_hits = o.paths + c.paths;
         }
     }
 }
 #endif
-// Stage 3a: edge pick of every path vertex (secondary edge sampling); full warps of vertices.  Key = picked edge
-// (num_edges = nothing picked), value = position in the vertex list.
-__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SEC) k_bwd_sec_pick(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+// Slot t of the boundary stage -> entry of vert_list: [0, n_gather) from the front, then (after padding to a warp boundary) the
+// hierarchy entries from the back.
+struct SecRange {
+    unsigned n_g, pad, total;
+};
+RB_D SecRange sec_range(const KernelArgs& ka) {
+    SecRange r;
+    r.n_g = ka.counters->n_gather;
+    r.pad = (r.n_g + 31u) & ~31u;
+    r.total = r.pad + ka.counters->n_hier;
+    return r;
+}
+RB_D int sec_entry(const KernelArgs& ka, const SecRange& r, long long t) {
+    if (t < (long long)r.n_g) return ka.vert_list[t];
+    if (t >= (long long)r.pad && t < (long long)r.total) return ka.vert_list[(unsigned)ka.vert_cap - 1u - (unsigned)(t - r.pad)];
+    return -1;
+}
+// Stage 2a: edge pick of every listed path vertex (secondary edge sampling).  Writes the pick, its vertex and its edge per
+// slot and counts the picks per edge (aggregated per warp) for the counting sort below.
+__global__ void __launch_bounds__(RB_BLOCK_SEC, RB_MIN_BLOCKS_SEC) k_bwd_sec_pick(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     const RenderParams& rp = ka.rp;
-    const long long n = ka.n_verts;
+    const SecRange r = sec_range(ka);
+    const long long n = r.total;
     RB_BLOCK_LOOP(t, n) {
         RB_PHASE_SYNC();
         if (t < n) {
-            int e = ka.vert_list[t];
-            int ts = e / ka.rec_per_sample, d = e - ts * ka.rec_per_sample;
-            SampleId id = band_sample(rp, ka.band_i0 + ts);
-            VertexRec cur = ka.records[e];
-            EdgePick pk;
-            bool ok = bwd_secondary_pick(sc, ka, id.pixel, id.s, d, cur, pk);
-            if (ok) ka.picks[t] = pk;
-            ka.sec_keys[t] = ok ? (unsigned)pk.edge_id : (unsigned)sc.num_edges;
-            ka.sec_vals[t] = (unsigned)t;
-            ka.dpos[e] = zero3();
+            int e = sec_entry(ka, r, t);
+            unsigned key = 0xffffffffu;
+            if (e >= 0) {
+                int ts = e / ka.rec_per_sample, d = e - ts * ka.rec_per_sample;
+                SampleId id = band_sample(rp, ka.band_i0 + ts);
+                VertexRec cur = ka.records[e];
+                EdgePick pk;
+                if (bwd_secondary_pick(sc, ka, id.pixel, id.s, d, cur, pk)) {
+                    ka.picks[t] = pk;
+                    key = (unsigned)pk.edge_id;
+                }
+            }
+            ka.sec_keys[t] = key;
+            ka.sec_vals[t] = (unsigned)e;
+            if (key != 0xffffffffu) {
+                unsigned peers = __match_any_sync(__activemask(), key);
+                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&ka.edge_hist[key], (unsigned)__popc(peers));
+            }
         }
     }
 }
-// Stage 3b: the two edge rays and their sub-paths, in edge order (neighbouring lanes aim at the same edge).
-__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SEC) k_bwd_sec_shade(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+#ifndef RB_LEAN // the counting sort does not depend on scene features
+// Stage 2b: exclusive scan of the per-edge pick counts (one block; the histogram is zeroed again for the next band).
+__global__ void __launch_bounds__(1024) k_sec_offsets(const __grid_constant__ KernelArgs ka, int num_edges) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < num_edges; base += 1024) {
+        int i = base + tid;
+        unsigned v = i < num_edges ? ka.edge_hist[i] : 0u, x = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = warp_sums[lane], ws = w;
+            for (int off = 1; off < 32; off <<= 1) {
+                unsigned y = __shfl_up_sync(0xffffffffu, ws, off);
+                if (lane >= off) ws += y;
+            }
+            warp_sums[lane] = ws - w; // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        unsigned carry = carry_s;
+        if (i < num_edges) {
+            ka.edge_offs[i] = carry + warp_sums[warp] + x - v;
+            ka.edge_hist[i] = 0;
+            ka.edge_cursor[i] = 0;
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + warp_sums[31] + x;
+        __syncthreads();
+    }
+    if (tid == 0) ka.counters->n_picked = carry_s;
+}
+// Stage 2c: scatter the slots into edge order (rank inside an edge: warp-aggregated cursor).
+__global__ void __launch_bounds__(256) k_sec_scatter(const __grid_constant__ KernelArgs ka) {
+    const SecRange r = sec_range(ka);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)r.total; t += (long long)gridDim.x * blockDim.x) {
+        unsigned key = ka.sec_keys[t];
+        if (key == 0xffffffffu) continue;
+        unsigned peers = __match_any_sync(__activemask(), key);
+        int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&ka.edge_cursor[key], (unsigned)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        ka.sec_order[ka.edge_offs[key] + base + __popc(peers & ((1u << lane) - 1u))] = (unsigned)t;
+    }
+}
+#endif
+// Stage 2d: the two edge rays and their sub-paths, in edge order (neighbouring lanes aim at the same edge).
+__global__ void __launch_bounds__(RB_BLOCK_SEC, RB_MIN_BLOCKS_SEC) k_bwd_sec_shade(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     const RenderParams& rp = ka.rp;
-    const long long n = ka.n_verts;
+    const long long n = ka.counters->n_picked;
     RB_BLOCK_LOOP(j, n) {
         RB_PHASE_SYNC();
-        if (j < n && ka.sec_keys_sorted[j] < (unsigned)sc.num_edges) {
-            unsigned t = ka.sec_vals_sorted[j];
-            int e = ka.vert_list[t];
+        if (j < n) {
+            unsigned t = ka.sec_order[j];
+            int e = (int)ka.sec_vals[t];
             int ts = e / ka.rec_per_sample, d = e - ts * ka.rec_per_sample;
             SampleId id = band_sample(rp, ka.band_i0 + ts);
             VertexRec cur = ka.records[e];
@@ -251,15 +417,15 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SEC) k_bwd_sec_shade(c
         }
     }
 }
-// Stage 4: reverse sweep of every path, first-hit and camera adjoints.
-__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_SWEEP) k_bwd_sweep(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
-    __shared__ float cam_smem[RB_CAM_ACC * RB_BLOCK];
-    for (int k = 0; k < RB_CAM_ACC; k++) cam_smem[k * RB_BLOCK + threadIdx.x] = 0.f;
+// Stage 3: reverse sweep of every path, first-hit and camera adjoints.
+__global__ void __launch_bounds__(RB_BLOCK_SWEEP, RB_MIN_BLOCKS_SWEEP) k_bwd_sweep(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+    extern __shared__ float cam_smem[]; // [RB_CAM_ACC][blockDim.x]
+    for (int k = 0; k < RB_CAM_ACC; k++) cam_smem[k * blockDim.x + threadIdx.x] = 0.f;
     CamAcc cam_acc;
     cam_acc.base = cam_smem + threadIdx.x;
-    cam_acc.stride = RB_BLOCK;
+    cam_acc.stride = blockDim.x;
     const RenderParams& rp = ka.rp;
-    const long long n = ka.n_paths;
+    const long long n = ka.counters->n_paths;
     RB_BLOCK_LOOP(t, n) {
         bool act = t < n;
         int ts = act ? ka.path_list[t] : 0;
@@ -292,13 +458,13 @@ __global__ void __launch_bounds__(256) k_prim_keys(const __grid_constant__ DevSc
         vals[t] = (unsigned)t;
     }
 }
-__global__ void __launch_bounds__(RB_BLOCK, RB_MIN_BLOCKS_BWD) k_primary_edge(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka, int dim_base,
+__global__ void __launch_bounds__(RB_BLOCK_PRIM, RB_MIN_BLOCKS_BWD) k_primary_edge(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka, int dim_base,
                                                                                long long t0, int n, const unsigned* keys, const unsigned* vals) {
-    __shared__ float cam_smem[RB_CAM_ACC * RB_BLOCK];
-    for (int k = 0; k < RB_CAM_ACC; k++) cam_smem[k * RB_BLOCK + threadIdx.x] = 0.f;
+    extern __shared__ float cam_smem[]; // [RB_CAM_ACC][blockDim.x]
+    for (int k = 0; k < RB_CAM_ACC; k++) cam_smem[k * blockDim.x + threadIdx.x] = 0.f;
     CamAcc cam_acc;
     cam_acc.base = cam_smem + threadIdx.x;
-    cam_acc.stride = RB_BLOCK;
+    cam_acc.stride = blockDim.x;
     RB_BLOCK_LOOP(t, n) {
         RB_PRIM_SYNC();
         if (t < n && keys[t] != 0xffffffffu) {

@@ -18,6 +18,10 @@
 #else
 #define RB_PHASE_SYNC() __syncthreads()
 #endif
+struct BandCounters {
+    unsigned n_paths, n_gather, n_hier, n_picked;
+    unsigned long long total_vertices, total_hits; // statistics (mean path length, primary-hit fraction)
+};
 struct KernelArgs {
     RenderParams rp;
     int lanes_per_pixel; // L
@@ -33,14 +37,15 @@ struct KernelArgs {
     VertexRec* records;          // [band_n][rec_per_sample]
     V3* dpos;                    // [band_n][rec_per_sample] boundary terms (null without secondary edge sampling)
     int* nrec;                   // [band_n] vertices with an estimate, -1: primary ray missed
-    unsigned long long* offs;    // [band_n] exclusive scan of (hit << 32 | nrec)
-    int* path_list;              // compacted samples that hit something
-    int* vert_list;              // compacted (sample * rec_per_sample + depth)
-    unsigned long long* totals;  // [1] (paths << 32 | vertices) of the band
-    EdgePick* picks;             // [vertices] edge chosen for each entry of vert_list
-    unsigned *sec_keys, *sec_vals; // [vertices] (edge id | invalid, index into vert_list), before and after the sort
-    unsigned *sec_keys_sorted, *sec_vals_sorted;
-    int n_paths, n_verts;        // host copies of `totals` (read back once per band)
+    ulonglong2* vmask;           // [band_n] per depth: (vertex takes part in the boundary stage, its sample uses the gather strategy)
+    BandCounters* counters;      // list sizes of THIS band, written by k_bwd_trace / k_sec_offsets, read by the later kernels
+    int* path_list;              // samples that hit something
+    int* vert_list;              // (sample * rec_per_sample + depth): gather-strategy vertices from the front, hierarchy from the back
+    int vert_cap;                // capacity of vert_list
+    EdgePick* picks;             // [slot] edge chosen for each listed vertex
+    unsigned *sec_keys, *sec_vals; // [slot] picked edge (or 0xffffffff) / vert_list entry
+    unsigned *edge_hist, *edge_offs, *edge_cursor; // [num_edges] counting sort of the picks by edge
+    unsigned* sec_order;         // [picks] slots in edge order
 };
 
 RB_HD int rb_channel_width(int ch, int max_generic) { // floats of one channel, src/channels.cpp:42-113

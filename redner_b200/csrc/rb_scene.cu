@@ -196,8 +196,9 @@ __device__ __forceinline__ void load_box(const float* leaf_box, const float* inn
     const float* p = child >= 0 ? inner_box + 6 * (size_t)child : leaf_box + 6 * (size_t)(~child);
     for (int k = 0; k < 6; k++) b[k] = p[k];
 }
+// (`height`: levels below each inner node; the root's bounds the traversal stack, checked by rb_build_bvh)
 __global__ void k_refit(int T, BVHNode* nodes, const int* parent_inner, const int* parent_leaf, const float* leaf_box, float* inner_box,
-                        int* flags) {
+                        int* flags, int* height) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     int node = parent_leaf[i];
@@ -215,6 +216,8 @@ __global__ void k_refit(int T, BVHNode* nodes, const int* parent_inner, const in
             inner_box[6 * (size_t)node + k] = fminf(l[k], r[k]);
             inner_box[6 * (size_t)node + 3 + k] = fmaxf(l[3 + k], r[3 + k]);
         }
+        int hl = nodes[node].left >= 0 ? height[nodes[node].left] : 0, hr = nodes[node].right >= 0 ? height[nodes[node].right] : 0;
+        height[node] = (hl > hr ? hl : hr) + 1;
         node = parent_inner[node];
     }
 }
@@ -236,13 +239,13 @@ int rb_build_bvh(rb_scene* sc, cudaStream_t stream) {
     unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     RB_CUDA_OK(cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream));
     unsigned long long *keys, *keys_sorted;
-    int *vals, *vals_sorted, *parent_inner, *parent_leaf, *flags;
+    int *vals, *vals_sorted, *parent_inner, *parent_leaf, *flags, *height;
     float *leaf_box, *inner_box;
     BVHTri* tris;
     BVHNode* nodes;
     if (dev_alloc(sc, &keys, T, stream) || dev_alloc(sc, &keys_sorted, T, stream) || dev_alloc(sc, &vals, T, stream) ||
         dev_alloc(sc, &vals_sorted, T, stream) || dev_alloc(sc, &parent_inner, T, stream) || dev_alloc(sc, &parent_leaf, T, stream) ||
-        dev_alloc(sc, &flags, T, stream) || dev_alloc(sc, &leaf_box, 6 * (size_t)T, stream) || dev_alloc(sc, &inner_box, 6 * (size_t)T, stream) ||
+        dev_alloc(sc, &flags, T, stream) || dev_alloc(sc, &height, T, stream) || dev_alloc(sc, &leaf_box, 6 * (size_t)T, stream) || dev_alloc(sc, &inner_box, 6 * (size_t)T, stream) ||
         dev_alloc(sc, &tris, T, stream) || dev_alloc(sc, &nodes, T, stream))
         return 1;
     int B = 256, G = (T + B - 1) / B;
@@ -257,8 +260,19 @@ int rb_build_bvh(rb_scene* sc, cudaStream_t stream) {
     if (T > 1) {
         RB_CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(int) * T, stream));
         k_karras<<<G, B, 0, stream>>>(keys_sorted, T, nodes, parent_inner, parent_leaf);
-        k_refit<<<G, B, 0, stream>>>(T, nodes, parent_inner, parent_leaf, leaf_box, inner_box, flags);
+        k_refit<<<G, B, 0, stream>>>(T, nodes, parent_inner, parent_leaf, leaf_box, inner_box, flags, height);
         sc->dev.bvh_root = 0;
+        // The traversal keeps at most one deferred sibling per level on a RB_BVH_STACK-entry stack.  Morton keys with an index
+        // tie-break can make a radix tree deeper than that on heavily clustered / duplicated geometry: refuse instead of
+        // silently dropping subtrees.
+        int root_height = 0;
+        RB_CUDA_OK(cudaMemcpyAsync(&root_height, height, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        RB_CUDA_OK(cudaStreamSynchronize(stream));
+        if (root_height >= RB_BVH_STACK) {
+            rb_set_error("rb_scene_create: triangle BVH is " + std::to_string(root_height) + " levels deep (limit " + std::to_string(RB_BVH_STACK - 1) +
+                         "): degenerate / heavily duplicated geometry");
+            return 1;
+        }
     } else {
         sc->dev.bvh_root = ~0;
     }
@@ -266,7 +280,7 @@ int rb_build_bvh(rb_scene* sc, cudaStream_t stream) {
     sc->dev.bvh_nodes = nodes;
     sc->dev.bvh_tris = tris;
     // builder temporaries (~100 B / triangle) go back to the pool in stream order; the scene keeps nodes + triangles only
-    void* temps[] = {d_offs, d_bounds, keys, keys_sorted, vals, vals_sorted, parent_inner, parent_leaf, flags, leaf_box, inner_box, tmp};
+    void* temps[] = {d_offs, d_bounds, keys, keys_sorted, vals, vals_sorted, parent_inner, parent_leaf, flags, height, leaf_box, inner_box, tmp};
     for (void* p : temps) {
         auto it = std::find(sc->allocs.begin(), sc->allocs.end(), p);
         if (it == sc->allocs.end()) continue;
@@ -529,6 +543,7 @@ extern "C" void rb_scene_destroy(rb_scene* sc) {
     cudaGetDevice(&prev);
     cudaSetDevice(sc->device);
     for (void* p : sc->allocs) cudaFreeAsync(p, 0);
+    sc->events.destroy();
     cudaSetDevice(prev);
     delete sc;
 }

@@ -9,8 +9,26 @@
 
 #include "rb_types.cuh"
 
+// Timing events owned by a scene and reused by every rb_render call on it.
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    bool ensure(size_t n) {
+        while (ev.size() < n) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return false;
+            ev.push_back(e);
+        }
+        return true;
+    }
+    void destroy() {
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        ev.clear();
+    }
+};
+
 struct rb_scene {
     int device = 0;
+    EventPool events;
     DevScene dev;   // passed by value to kernels
     rb_camera cam;  // host copy of the descriptor camera
     std::vector<void*> allocs; // device allocations owned by the scene
@@ -25,7 +43,7 @@ struct rb_scene {
     int last_launches = 0;
     float last_kernel_ms = 0.f;
     float last_stage_ms[4] = {0.f, 0.f, 0.f, 0.f}; // k_forward, backward bands, k_primary_edge, k_finish_camera
-    float last_bwd_ms[3] = {0.f, 0.f, 0.f};        // inside the bands: k_bwd_trace, scan + compaction + k_bwd_secondary, k_bwd_sweep
+    float last_bwd_ms[3] = {0.f, 0.f, 0.f};        // inside the bands: k_bwd_trace (+ work lists), boundary stage (pick, sort by edge, shade), k_bwd_sweep
     double last_path_vertices = 0, last_primary_hits = 0;
     // scene-build timings (ms, host clock) for reporting
     float build_ms_bvh = 0.f, build_ms_lights = 0.f, build_ms_edges = 0.f;

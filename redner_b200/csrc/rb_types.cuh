@@ -71,6 +71,7 @@ struct DevCamera {
 };
 
 // ---- BVH (own LBVH; replaces Embree/OptiX Prime) ----
+#define RB_BVH_STACK 64 // traversal stack entries per ray; rb_build_bvh refuses trees that could overflow it
 // Node i stores the AABBs of BOTH children so that one 64-byte fetch decides the descent.
 // child index >= 0: inner node; < 0: leaf, triangle slot = ~child.
 struct __align__(16) BVHNode {

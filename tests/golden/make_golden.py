@@ -53,6 +53,12 @@ def main():
         img = render_screen_gradient(ref, dev, cfg)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), image=img.numpy())
         print(name, tuple(img.shape), "norm %.6f" % img.norm().item())
+    if not only or "c2_full_size_forward_blocks" in only:
+        # the headline configuration itself (C2, 512 x 512 x 64 spp, forward): 8 x 8 block means of the reference's image
+        cfg = dict(scene="shadow_blocker", res=512, spp=64, mb=1, sampler="sobol", edges=0)
+        img, _ = render_case(ref, dev, cfg, 1, backward=False)
+        np.savez_compressed(os.path.join(OUT, "c2_full_size_forward_blocks.npz"), blocks=img.numpy().reshape(64, 8, 64, 8, 3).mean((1, 3)))
+        print("c2_full_size_forward_blocks", "mean %.6f" % img.mean().item())
     for name, cfg in STAT_CASES.items():
         if only and name not in only:
             continue

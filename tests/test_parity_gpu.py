@@ -199,6 +199,55 @@ def test_full_size_properties(rb, dev):
     assert torch.allclose(lhs, rhs, rtol=2e-4), (lhs, rhs)
 
 
+def test_c2_full_size_forward_against_the_reference(rb, dev):
+    """The headline configuration itself, C2 at 512 x 512 x 64 spp (forward, fixed Sobol seed): relative L2 against the compiled
+    reference within north_star's 1e-4 where oracle/_ref travelled with the snapshot (the reference needs ~1 s for the forward
+    pass), and against the committed 8 x 8 block means of the reference's image in any case."""
+    cfg = dict(scene="shadow_blocker", res=512, spp=64, mb=1, sampler="sobol", edges=0)
+    img_c, _ = pu.render_case(rb, dev, cfg, 1, backward=False)
+    img_c = img_c.numpy()
+    blocks = img_c.reshape(64, 8, 64, 8, 3).mean((1, 3))
+    g = pu.load_golden("c2_full_size_forward_blocks")["blocks"]
+    assert pu.rel_l2(blocks, g) < IMG_TOL, pu.rel_l2(blocks, g)
+    import ref_loader
+    if ref_loader.available():
+        img_r, _ = pu.render_case(ref_loader.load(), torch.device("cpu"), cfg, 1, backward=False)
+        assert pu.rel_l2(img_c, img_r.numpy()) < IMG_TOL, pu.rel_l2(img_c, img_r.numpy())
+
+
+def _translated_loss(rb, dev, scene, shape, shift, axis, res, spp, seed):
+    sc = scenes.SCENES[scene](dev, resolution=(res, res), grad=False)
+    v = sc.shapes[shape].vertices.clone()
+    v[:, axis] += shift
+    sc.shapes[shape].vertices = v
+    args = api.RenderFunction.serialize_scene(sc, spp, 1, sampler_type=rb.SamplerType.sobol, device=dev, backend=rb)
+    return float(api.RenderFunction.apply(seed, *args).double().sum())
+
+
+@pytest.mark.parametrize("scene,shape,axes,tol", [("single_triangle", 0, (0, 1), 0.03), ("shadow_blocker", 1, (0,), 0.15)])
+def test_gradients_against_finite_differences_end_to_end(rb, dev, scene, shape, axes, tol):
+    """End-to-end finite differences (the function-level checks of the reference, src/test_utils.h:15-23 / src/shape.cpp:5-331 /
+    src/material.cpp:6-400 / src/camera.cpp:98-475, are restated for our device functions in tests/test_fd_functions_cpu.py).
+    Translate a mesh by +-eps: central difference of sum(img) at 256 x 256 x 1024 spp (common random numbers) against the analytic
+    gradient sum_v d(sum img)/d(vertex v) with both edge samplers on.
+      C1 triangle seen by the camera: interior + primary-edge terms, agree to ~1 %.
+      C2 blocker (only its shadow is seen): the secondary-edge term alone.  Along x analytic and finite differences agree within the
+      noise; along y / z (towards the lamp) the REFERENCE's estimator itself gives about half of the finite difference
+      (profiles/r02_fd_check.txt: reference -471 vs -886, ours -3386 vs -6302 at 256 x 256) -- parity with the reference is pinned
+      by the statistical goldens, so only the x axis is asserted here."""
+    res, eps, seeds = 256, 0.02, (1, 2, 3, 4)
+    analytic = np.zeros(3)
+    for seed in seeds:
+        sc = scenes.SCENES[scene](dev, resolution=(res, res))
+        args = api.RenderFunction.serialize_scene(sc, 256, 1, sampler_type=rb.SamplerType.sobol, device=dev, backend=rb)
+        api.RenderFunction.apply(seed, *args).sum().backward()
+        analytic += sc.shapes[shape].vertices.grad.double().sum(0).cpu().numpy() / len(seeds)
+    for axis in axes:
+        fd = np.mean([(_translated_loss(rb, dev, scene, shape, eps, axis, res, 1024, s) - _translated_loss(rb, dev, scene, shape, -eps, axis, res, 1024, s)) / (2 * eps)
+                      for s in seeds])
+        assert abs(analytic[axis] - fd) < tol * max(abs(fd), 0.1 * np.abs(analytic).max()), (axis, analytic, fd)
+
+
 def test_ragged_and_degenerate_inputs(rb, dev):
     # spp that is not a power of two, non-square viewport crop, max_bounces 0, a scene without lights
     sc = scenes.shadow_blocker(dev, resolution=(37, 53))
