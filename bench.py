@@ -331,22 +331,41 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- end to end from pinned host memory (e2e) ----------------
     main_mode = modes[0]
     hosts = [HostScene(wl, pose=(p if (main_mode == "poses" or n_poses) else None)) for p in (my_poses if main_mode == "poses" else [None])]
-    h2d = sum(h.h2d_bytes for h in hosts)
+    h2d = hosts[0].h2d_bytes if n_poses else sum(h.h2d_bytes for h in hosts)
     d2h_box = [0]
 
     def step_e2e():
         outs, acc = [], None
-        for h in hosts:
-            scn, params = h.to_device(dev)
-            if main_mode == "tiles":
-                img = rdist.render_tiles(scn, SPP, MB, SEED, sampler_type=st, device=dev)
-            else:
-                img = api.RenderFunction.apply(SEED, *api.RenderFunction.serialize_scene(scn, SPP, MB, sampler_type=st, device=dev))
-            loss = img.pow(2).sum()
+        if n_poses:
+            # C5: ONE host->device copy and ONE native scene for all poses of this rank (api.render_batch / rb_scene_set_camera:
+            # per pose only the camera-dependent tables are rebuilt, on the device)
+            scn, params = hosts[0].to_device(dev)
+            views = []
+            for h in hosts:
+                v = api.Scene(h.sc.camera, scn.shapes, scn.materials, scn.area_lights)
+                for t in (v.camera.position, v.camera.look_at, v.camera.up):
+                    if t is not None and t.requires_grad:
+                        t.grad = None
+                        if all(t is not q for q in params):
+                            params.append(t)
+                views.append(v)
+            imgs = api.render_batch(views, SPP, MB, [SEED + k for k in range(len(views))], sampler_type=st, device=dev)
+            loss = imgs.pow(2).sum()
             loss.backward()
-            outs += [img.detach().to("cpu", non_blocking=True), loss.detach().cpu()]
-            gs = [p.grad for p in params]
-            acc = gs if acc is None else [a + b.to(a.device) for a, b in zip(acc, gs)]
+            outs += [imgs.detach().to("cpu", non_blocking=True), loss.detach().cpu()]
+            acc = [p.grad for p in params]
+        else:
+            for h in hosts:
+                scn, params = h.to_device(dev)
+                if main_mode == "tiles":
+                    img = rdist.render_tiles(scn, SPP, MB, SEED, sampler_type=st, device=dev)
+                else:
+                    img = api.RenderFunction.apply(SEED, *api.RenderFunction.serialize_scene(scn, SPP, MB, sampler_type=st, device=dev))
+                loss = img.pow(2).sum()
+                loss.backward()
+                outs += [img.detach().to("cpu", non_blocking=True), loss.detach().cpu()]
+                gs = [p.grad for p in params]
+                acc = gs if acc is None else [a + b.to(a.device) for a, b in zip(acc, gs)]
         if world > 1 and main_mode == "poses":
             cuda_g = [g.to(dev) for g in acc]
             acc = rdist.all_reduce_packed(cuda_g)

@@ -24,6 +24,7 @@
 
 #include <stdint.h>
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -186,6 +187,18 @@ int rb_compute_num_channels(const int* channels, int num_channels, int max_gener
 int rb_render(const rb_scene* scene, const rb_options* options, float* rendered_image, const float* d_rendered_image,
               const rb_dscene_desc* d_scene, float* screen_gradient_image, void* stream);
 
+/* Re-target a scene at another camera.  Only what depends on the camera is rebuilt, on the device: the primary-edge distribution
+ * (src/edge.cpp:298-331) and the two secondary-edge trees (src/edge_tree.cpp:724-882); geometry, BVH, light tables and the edge
+ * list are kept.  (The reference rebuilds the whole Scene per view, pyredner/render_pytorch.py:608-617.) */
+int rb_scene_set_camera(rb_scene* scene, const rb_camera* camera);
+
+/* A batch of views of one scene -- the native form of the per-view Python loops of pyredner/render_utils.py:407-430 and of
+ * BASELINE config 5: for k in [0, num_views): rb_scene_set_camera(cameras[k]) then rb_render(options[k], images[k], d_images[k],
+ * d_scenes[k]).  images / d_images / d_scenes may be NULL (or hold NULL entries) like the arguments of rb_render; gradients
+ * ACCUMULATE, so one descriptor passed for every view sums the batch's gradients into one set of buffers. */
+int rb_render_batch(rb_scene* scene, int num_views, const rb_camera* cameras, const rb_options* options, float* const* images,
+                    const float* const* d_images, const rb_dscene_desc* const* d_scenes, void* stream);
+
 /* Multi-GPU tile sharding (no reference counterpart).  Restricts subsequent rb_render calls on
  * this scene to the rows r with (r / rows_per_stripe) % num_parts == part of the viewport, while samplers stay
  * seeded by the full-viewport pixel index, so the union over parts equals the single-GPU result.  Primary-edge
@@ -210,6 +223,11 @@ int rb_scene_last_backward_stats(const rb_scene* scene, float* bwd_ms3);
 void rb_release_scratch(void);
 /* Host wall-clock milliseconds rb_scene_create spent in { BVH build, light tables, edge list + edge tree }. */
 int rb_scene_build_ms(const rb_scene* scene, float* bvh_lights_edges3);
+
+/* Test hook: the secondary-edge trees as the kernels see them.  info3 = { number of 128-byte records, root reference of the
+ * camera-silhouette tree, root reference of the other tree } (reference >= 0: record index, < 0: ~edge id, INT_MIN: empty tree);
+ * *expand = billboard size (src/edge_tree.cpp:773); records_out (may be NULL) receives up to records_bytes of the records. */
+int rb_scene_edge_trees(const rb_scene* scene, int* info3, float* expand, void* records_out, size_t records_bytes);
 
 const char* rb_last_error(void);
 const char* rb_version(void);

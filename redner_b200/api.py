@@ -279,7 +279,9 @@ class RenderFunction(torch.autograd.Function):
         return args
 
     @staticmethod
-    def _unpack(seed, args):
+    def _unpack(seed, args, scene=None):
+        """`scene`: an existing native scene of the SAME geometry / materials / lights to re-target at this argument list's camera
+        (rb_scene_set_camera) instead of building a new one -- the batch path."""
         it = iter(args)
         nxt = lambda: next(it)  # noqa: E731
         c = _Ctx()
@@ -341,7 +343,11 @@ class RenderFunction(torch.autograd.Function):
             env_tex = rb.Texture3([fp(m) for m in mips], [int(m.shape[1]) for m in mips], [int(m.shape[0]) for m in mips], 3, fp(uv_scale))
             envmap = rb.EnvironmentMap(env_tex, fp(e2w), fp(w2e), fp(cdf_ys), fp(cdf_xs), pdf_norm, visible)
         c.env_args, c.envmap = env_args, envmap
-        c.scene = rb.Scene(camera, shapes, materials, lights, envmap, use_gpu, gpu_index, use_prim, use_sec)
+        if scene is None:
+            c.scene = rb.Scene(camera, shapes, materials, lights, envmap, use_gpu, gpu_index, use_prim, use_sec)
+        else:
+            scene.set_camera(camera)
+            c.scene = scene
         ns = num_samples if isinstance(num_samples, (tuple, list)) else (num_samples, num_samples)
         channels = [rb.channels(int(ch)) for ch in channels]
         c.options = rb.RenderOptions(seed[0], ns[0], max_bounces, channels, rb.SamplerType(int(sampler_type)), pixel_center)
@@ -445,6 +451,51 @@ class RenderFunction(torch.autograd.Function):
             out.append(None)  # envmap
         out += [None] * 9  # num_samples .. backend
         return tuple(out)
+
+
+class BatchRenderFunction(torch.autograd.Function):
+    """A batch of views of ONE scene (BASELINE config 5; the pattern of the reference's tests/test_batch.py:10-33, whose Python loop
+    builds a full Scene per view).  `args` = the serialize_scene lists of the views, concatenated; the views must share geometry,
+    materials and lights (the same tensors) and may differ in camera and options.  The native scene -- BVH, light tables, edge list --
+    is built once; per view only the camera-dependent tables are rebuilt, on the device.  Returns [views, height, width, channels]."""
+
+    @staticmethod
+    def forward(ctx, seeds, num_views, *args):
+        assert num_views >= 1 and len(args) % num_views == 0
+        n = len(args) // num_views
+        seeds = list(seeds) if isinstance(seeds, (list, tuple)) else [seeds + k for k in range(num_views)]
+        views, imgs, scene = [], [], None
+        for k in range(num_views):
+            sd = seeds[k] if isinstance(seeds[k], tuple) else (seeds[k], seeds[k] + 1000003)
+            c = RenderFunction._unpack(sd, args[k * n:(k + 1) * n], scene=scene)
+            scene = c.scene
+            rb = c.backend
+            nch = rb.compute_num_channels(c.channels, c.scene.max_generic_texture_dimension)
+            h, w = c.viewport[2] - c.viewport[0], c.viewport[3] - c.viewport[1]
+            img = torch.zeros(h, w, nch, device=c.device)
+            rb.render(c.scene, c.options, rb.float_ptr(img.data_ptr()), rb.float_ptr(0), None, rb.float_ptr(0), rb.float_ptr(0))
+            views.append(c)
+            imgs.append(img)
+        ctx.views, ctx.args, ctx.n = views, args, n
+        return torch.stack(imgs)
+
+    @staticmethod
+    def backward(ctx, grad_imgs):
+        out = [None, None]
+        for k, c in enumerate(ctx.views):
+            c.scene.set_camera(c.camera)
+            one = _Ctx()
+            one.c, one.args = c, ctx.args[k * ctx.n:(k + 1) * ctx.n]
+            out += list(RenderFunction.backward(one, grad_imgs[k]))[1:]
+        return tuple(out)
+
+
+def render_batch(scenes, num_samples, max_bounces: int, seeds, **kw) -> torch.Tensor:
+    """Views of one scene: `scenes` are Scene objects that share shapes / materials / lights and differ in their camera."""
+    args = []
+    for sc in scenes:
+        args += RenderFunction.serialize_scene(sc, num_samples, max_bounces, **kw)
+    return BatchRenderFunction.apply(seeds, len(scenes), *args)
 
 
 def visualize_screen_gradient(grad_img: Optional[torch.Tensor], seed: int, scene: Scene, num_samples, max_bounces: int, channels=None, sampler_type=None,

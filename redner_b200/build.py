@@ -51,12 +51,16 @@ def build(force=False, double=False, verbose=False, defines=(), out=None, nvcc_f
     common += ["-D" + d for d in defines] + list(nvcc_flags)
     if verbose:
         common += ["-Xptxas", "-v"]
+    # rb_edge_tree.cu builds the secondary-edge trees and must round like the host builder it is tested against (no FMA contraction,
+    # IEEE division / square root); its bottom-up passes hand data between thread blocks, so its global loads bypass the L1.
+    per_file = {"rb_edge_tree.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-Xptxas", "-dlcm=cg"]}
     objs = []
     procs = []
     for src in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         objs.append(obj)
-        procs.append((src, subprocess.Popen([nvcc] + ARCH + common + ["-c", src, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        procs.append((src, subprocess.Popen([nvcc] + ARCH + common + per_file.get(os.path.basename(src), []) + ["-c", src, "-o", obj], stdout=subprocess.PIPE,
+                                            stderr=subprocess.STDOUT)))
     tab = os.path.join(objdir, "rb_tables.o")
     objs.append(tab)
     procs.append(("rb_tables.cpp", subprocess.Popen(["g++", "-O2", "-fPIC", "-DRB_DATA_DIR=" + DATA, "-c", os.path.join(CSRC, "rb_tables.cpp"), "-o", tab],

@@ -424,3 +424,20 @@ std::vector<cudaEvent_t>& ev = events.ev;
     }
     return 0;
 }
+
+// Batch of views of ONE scene (the multi-view loops of pyredner/render_utils.py:407-430 and of BASELINE config 5 rebuild the whole
+// Scene per view): geometry, BVH, light tables and the edge list are shared; per view only the camera-dependent tables are rebuilt,
+// on the device (rb_scene_set_camera), followed by the usual kernel set.  Gradients of all views ACCUMULATE into the buffers of
+// d_scenes[k] (pass the same descriptor for every view to sum them: one gradient buffer for the batch).
+extern "C" int rb_render_batch(rb_scene* scene, int num_views, const rb_camera* cameras, const rb_options* options, float* const* images,
+                               const float* const* d_images, const rb_dscene_desc* const* d_scenes, void* stream) {
+    if (!scene || num_views < 0 || (num_views > 0 && (!cameras || !options))) {
+        rb_set_error("rb_render_batch: null argument");
+        return 1;
+    }
+    for (int k = 0; k < num_views; k++) {
+        if (rb_scene_set_camera(scene, &cameras[k])) return 1;
+        if (rb_render(scene, &options[k], images ? images[k] : nullptr, d_images ? d_images[k] : nullptr, d_scenes ? d_scenes[k] : nullptr, nullptr, stream)) return 1;
+    }
+    return 0;
+}

@@ -6,17 +6,19 @@
 // Measured on B200 (profiles/r02_block_size_ab.txt; C2 / teapot 512x512x32 / bunny box 512x512x16, ms):
 //   k_forward     128 x 4: 3.55 / 16.8 / 22.1    256 x 2: 3.20 / 14.8 / 21.6    512 x 1: 3.30 / 14.2 / 21.1
 //   k_bwd_sweep   128 x 4: 5.06 / 31.9 / 18.5    256 x 2: 3.71 / 20.6 / 16.4    512 x 1: 3.84 / 14.4 / 16.9   (I-cache bound: 281 KB of SASS)
-//   k_bwd_trace, k_bwd_sec_*, k_primary_edge: within 3 % of each other, 128 or 256 best
+//   k_bwd_trace   256 x 2: 4.06 / 15.6 / 21.4    256 x 3: 3.65 / 13.9 / 18.6   (<= 80 registers: more warps hide the BVH fetch latency)
+//   k_forward     256 x 3: 3.22 / 14.4 / 19.2;   k_primary_edge 128 x 4: 6.88 / 12.8 / 13.5   128 x 5: 6.46 / 12.8 / 14.1
+//   k_bwd_sec_* : 128 x 6 (profiles/r02_boundary_stage_ab.txt)
 //   without the phase barriers (RB_NO_LOCKSTEP): k_bwd_sweep 12.1 / 234 / 146
 #ifndef RB_BLOCK_FWD
 #define RB_BLOCK_FWD 256
 #undef RB_MIN_BLOCKS_FWD
-#define RB_MIN_BLOCKS_FWD 2
+#define RB_MIN_BLOCKS_FWD 3
 #endif
 #ifndef RB_BLOCK_TRACE
 #define RB_BLOCK_TRACE 256
 #undef RB_MIN_BLOCKS_TRACE
-#define RB_MIN_BLOCKS_TRACE 2
+#define RB_MIN_BLOCKS_TRACE 3
 #endif
 #ifndef RB_BLOCK_SEC
 #define RB_BLOCK_SEC RB_BLOCK
@@ -38,7 +40,7 @@
 #define RB_MIN_BLOCKS_TRACE 4
 #endif
 #ifndef RB_MIN_BLOCKS_SEC
-#define RB_MIN_BLOCKS_SEC 4
+#define RB_MIN_BLOCKS_SEC 6 // the edge-tree walks wait on dependent node loads: 24 warps / SM at <= 80 registers beat 16 at 128 (profiles/r02_boundary_stage_ab.txt)
 #endif
 #ifndef RB_MIN_BLOCKS_SWEEP
 #define RB_MIN_BLOCKS_SWEEP 4
@@ -47,7 +49,7 @@
 #define RB_BAND_BYTES (1ULL << 30) // scratch budget of one backward band (records + lists)
 #endif
 #ifndef RB_MIN_BLOCKS_BWD
-#define RB_MIN_BLOCKS_BWD 4 // k_primary_edge
+#define RB_MIN_BLOCKS_BWD 5 // k_primary_edge
 #endif
 
 // j-th owned row -> viewport row, for the round-robin stripe partition
@@ -86,6 +88,41 @@ RB_D WorkItem warp_work(const RenderParams& rp, int L, int owned_rows, long long
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+// ---- optional: stage the Sobol rows of the main sampler in shared memory with ONE bulk asynchronous copy (TMA engine,
+// cp.async.bulk + mbarrier) issued by one thread at kernel start -- north_star's "Sobol state staged through TMA into shared memory".
+// Measured: no gain -- the <= 4 KB of rows a configuration touches sit in L1 anyway -- so it is off by default.
+#ifdef RB_TMA_SOBOL
+#define RB_TMA_SOBOL_DIMS 32
+RB_D unsigned rb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+RB_D const unsigned long long* stage_sobol_rows(const DevScene& sc, const RenderParams& rp, unsigned long long* smem_rows, unsigned long long* mbar) {
+    const int dims = (rp.sample_pixel_center ? 0 : 2) + 7 * rp.max_bounces;
+    if (rp.sampler_type != RB_SAMPLER_SOBOL || dims > RB_TMA_SOBOL_DIMS || dims == 0) return sc.sobol_matrices;
+    const unsigned bytes = (unsigned)(dims * RB_SOBOL_BITS * sizeof(unsigned long long)); // 416 B per dimension: a multiple of 16
+    const unsigned bar = rb_smem_addr(mbar), dst = rb_smem_addr(smem_rows);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(sc.sobol_matrices), "r"(bytes),
+                     "r"(bar)
+                     : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra RB_DONE;\n"
+        "bra RB_WAIT;\n"
+        "RB_DONE:\n"
+        "}\n" ::"r"(bar)
+        : "memory");
+    return smem_rows;
+}
+#endif
 #define RB_FWD_SYNC() RB_PHASE_SYNC() // measured: k_forward 5.2 -> 3.7 ms on C2 (one I-cache miss serves the block)
 __global__ void __launch_bounds__(RB_BLOCK_FWD, RB_MIN_BLOCKS_FWD) k_forward(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     const RenderParams& rp = ka.rp;
@@ -96,6 +133,13 @@ __global__ void __launch_bounds__(RB_BLOCK_FWD, RB_MIN_BLOCKS_FWD) k_forward(con
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int nb = (rp.spp + L - 1) / L;
+#ifdef RB_TMA_SOBOL
+    __shared__ alignas(16) unsigned long long sobol_rows[RB_TMA_SOBOL_DIMS * RB_SOBOL_BITS];
+    __shared__ alignas(8) unsigned long long sobol_bar;
+    const unsigned long long* sobol = stage_sobol_rows(sc, rp, sobol_rows, &sobol_bar);
+#else
+    const unsigned long long* sobol = nullptr;
+#endif
     for (long long g0 = 0; g0 < groups; g0 += nwarps) { // block-uniform trip count (phase barrier inside)
         long long g = g0 + warp;
         WorkItem w = warp_work(rp, L, ka.owned_rows, g < groups ? g : 0);
@@ -104,7 +148,7 @@ __global__ void __launch_bounds__(RB_BLOCK_FWD, RB_MIN_BLOCKS_FWD) k_forward(con
         for (int b = 0; b < nb; b++) {
             int s = b * L + w.sample_lane;
             RB_FWD_SYNC();
-            if (w.valid && s < rp.spp) acc += forward_sample(sc, rp, w.pixel, w.px, w.py, s);
+            if (w.valid && s < rp.spp) acc += forward_sample(sc, rp, w.pixel, w.px, w.py, s, sobol);
         }
         for (int off = L >> 1; off > 0; off >>= 1) {
             acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);

@@ -95,10 +95,11 @@ RB_D void primary_ray_for(const DevScene& sc, const RenderParams& rp, int px, in
 }
 
 // Radiance of one pixel sample, already multiplied by 1/spp.
-RB_D V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, int px, int py, int s) {
+// `sobol`: the Sobol rows of the main sampler (global memory, or the block's shared-memory copy when k_forward stages them)
+RB_D V3 forward_sample(const DevScene& sc, const RenderParams& rp, int pixel, int px, int py, int s, const unsigned long long* sobol = nullptr) {
     const Real weight = Real(1) / Real(rp.spp);
     Sampler smp;
-    smp.init(rp.sampler_type, rp.seed, pixel, (unsigned)s, sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
+    smp.init(rp.sampler_type, rp.seed, pixel, (unsigned)s, sobol ? sobol : sc.sobol_matrices, RB_SOBOL_BITS, (unsigned long long)s * main_draws_per_sample(rp));
     double sx, sy;
     Ray ray;
     RayDiff rd;

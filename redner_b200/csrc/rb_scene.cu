@@ -343,8 +343,12 @@ int rb_build_edges(rb_scene* sc, cudaStream_t stream) {
     sc->dev.num_edges = 0;
     sc->dev.prim_edge_pmf = sc->dev.prim_edge_cdf = nullptr;
     if (!sc->dev.use_primary_edge && !sc->dev.use_secondary_edge) return 0;
+    // The edge LIST (topology: sort, merge, seam repair, flat-edge filter) is built on the host; everything that depends on the
+    // camera -- the primary-edge distribution and the two secondary-edge trees -- on the device (rb_edge_tree.cu), so that
+    // rb_scene_set_camera / rb_render_batch re-target a scene without touching the host.  RB_HOST_TREES=1: host tables (tests).
+    const bool host_tables = getenv("RB_HOST_TREES") != nullptr;
     HostEdgeTables t;
-    host_build_edges(sc->shapes, host_meshes(sc), sc->dev.cam, sc->dev.use_primary_edge != 0, t);
+    host_build_edges(sc->shapes, host_meshes(sc), sc->dev.cam, sc->dev.use_primary_edge != 0 && host_tables, t);
     int E = (int)t.edges.size();
     sc->dev.num_edges = E;
     if (E == 0) return 0;
@@ -352,21 +356,31 @@ int rb_build_edges(rb_scene* sc, cudaStream_t stream) {
     if (dev_upload(sc, &d_edges, t.edges.data(), E, stream)) return 1;
     sc->dev.edges = d_edges;
     if (sc->dev.use_primary_edge) {
-        double *d_pmf, *d_cdf;
-        if (dev_upload(sc, &d_pmf, t.prim_pmf.data(), E, stream) || dev_upload(sc, &d_cdf, t.prim_cdf.data(), E, stream)) return 1;
-        sc->dev.prim_edge_pmf = d_pmf;
-        sc->dev.prim_edge_cdf = d_cdf;
+        if (host_tables) {
+            double *d_pmf, *d_cdf;
+            if (dev_upload(sc, &d_pmf, t.prim_pmf.data(), E, stream) || dev_upload(sc, &d_cdf, t.prim_cdf.data(), E, stream)) return 1;
+            sc->dev.prim_edge_pmf = d_pmf;
+            sc->dev.prim_edge_cdf = d_cdf;
+        } else if (rb_build_primary_edge_cdf_gpu(sc, stream)) {
+            return 1;
+        }
     }
     if (sc->dev.use_secondary_edge) {
-        HostEdgeTree tree;
-        host_build_edge_tree(sc->shapes, host_meshes(sc), t.edges, sc->dev.cam, tree);
-        EdgeNode* d_nodes;
-        if (dev_upload(sc, &d_nodes, tree.nodes.data(), tree.nodes.size(), stream)) return 1;
-        RB_CUDA_OK(cudaStreamSynchronize(stream));
-        sc->dev.edge_nodes = d_nodes;
-        sc->dev.edge_root_cs = tree.root_cs;
-        sc->dev.edge_root_ncs = tree.root_ncs;
-        sc->dev.edge_bounds_expand = tree.expand;
+        if (!host_tables) {
+            if (rb_build_edge_trees_gpu(sc, stream)) return 1;
+        } else {
+            HostEdgeTree tree;
+            host_build_edge_tree(sc->shapes, host_meshes(sc), t.edges, sc->dev.cam, tree);
+            EdgeNode* d_nodes;
+            sc->num_edge_nodes = (int)tree.nodes.size();
+            if (tree.nodes.empty()) tree.nodes.push_back(EdgeNode()); // (single-edge trees have no inner node)
+            if (dev_upload(sc, &d_nodes, tree.nodes.data(), tree.nodes.size(), stream)) return 1;
+            RB_CUDA_OK(cudaStreamSynchronize(stream));
+            sc->dev.edge_nodes = d_nodes;
+            sc->dev.edge_root_cs = tree.root_cs;
+            sc->dev.edge_root_ncs = tree.root_ncs;
+            sc->dev.edge_bounds_expand = tree.expand;
+        }
     }
     RB_CUDA_OK(cudaStreamSynchronize(stream));
     return 0;
@@ -491,7 +505,7 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
     sc->dev.sobol_dims = tabs.sobol_dims;
     sc->dev.ltc_table = tabs.ltc;
     sc->dev.edge_nodes = nullptr;
-    sc->dev.edge_root_cs = sc->dev.edge_root_ncs = -1;
+    sc->dev.edge_root_cs = sc->dev.edge_root_ncs = RB_EDGE_EMPTY;
     sc->dev.edge_bounds_expand = 0.f;
 
     auto t0 = std::chrono::high_resolution_clock::now();
@@ -546,6 +560,58 @@ extern "C" void rb_scene_destroy(rb_scene* sc) {
     sc->events.destroy();
     cudaSetDevice(prev);
     delete sc;
+}
+
+// Test hook: the secondary-edge trees as the kernels see them ({records, root of the camera-silhouette tree, root of the other tree},
+// the billboard size, and optionally the records themselves).
+extern "C" int rb_scene_edge_trees(const rb_scene* sc, int* info3, float* expand, void* records_out, size_t records_bytes) {
+    if (!sc) return 1;
+    if (info3) {
+        info3[0] = sc->num_edge_nodes;
+        info3[1] = sc->dev.edge_root_cs;
+        info3[2] = sc->dev.edge_root_ncs;
+    }
+    if (expand) *expand = sc->dev.edge_bounds_expand;
+    if (records_out && sc->dev.edge_nodes && records_bytes > 0) {
+        size_t n = std::min(records_bytes, sizeof(EdgeNode) * (size_t)sc->num_edge_nodes);
+        if (cudaMemcpy(records_out, sc->dev.edge_nodes, n, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+
+// Re-target the scene at another camera: only the camera-dependent tables are rebuilt (on the device).
+extern "C" int rb_scene_set_camera(rb_scene* sc, const rb_camera* cam) {
+    if (!sc || !cam) {
+        rb_set_error("rb_scene_set_camera: null argument");
+        return 1;
+    }
+    if (cam->width <= 0 || cam->height <= 0 || cam->viewport_end[0] <= cam->viewport_beg[0] || cam->viewport_end[1] <= cam->viewport_beg[1]) {
+        rb_set_error("rb_scene_set_camera: empty image / viewport");
+        return 1;
+    }
+    if ((cam->camera_type != RB_CAMERA_PERSPECTIVE || cam->has_distortion) && sc->dev.cam.type == RB_CAMERA_PERSPECTIVE && !sc->dev.cam.has_distortion) {
+        // (allowed; the general kernels serve it)
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(sc->device) != cudaSuccess) {
+        rb_set_error("rb_scene_set_camera: cudaSetDevice failed");
+        return 1;
+    }
+    sc->cam = *cam;
+    host_setup_camera(*cam, sc->dev.cam);
+    cudaStream_t stream = 0;
+    int rc = 0;
+    if (sc->dev.num_edges > 0) {
+        if (sc->dev.use_primary_edge) rc = rb_build_primary_edge_cdf_gpu(sc, stream);
+        if (rc == 0 && sc->dev.use_secondary_edge) rc = rb_build_edge_trees_gpu(sc, stream);
+    }
+    if (rc == 0 && cudaStreamSynchronize(stream) != cudaSuccess) {
+        rb_set_error("rb_scene_set_camera: device failure");
+        rc = 1;
+    }
+    cudaSetDevice(prev);
+    return rc;
 }
 
 extern "C" int rb_scene_max_generic_texture_dimension(const rb_scene* sc) { return sc ? sc->max_generic_texture_dimension : 0; }

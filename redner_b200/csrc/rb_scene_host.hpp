@@ -266,10 +266,10 @@ inline void host_build_edges(const std::vector<rb_shape>& shapes, const std::vec
 //   billboard size from the mean absolute deviation (:763-773), Morton codes (:166-266), stable sort (:795, :846),
 //   Karras radix tree with the reference's tie break (:282-376), bottom-up bounds and weighted lengths (:391-445)
 //   and the treelet (<= 7 leaves) SAH re-optimisation (:464-711) including its quirks.
-// The result is flattened into the 64-byte EdgeNode array the kernels traverse.
+// The result is flattened into the EdgeNode array the kernels traverse (one record per inner node, both children's bounds).
 struct HostEdgeTree {
     std::vector<EdgeNode> nodes;
-    int root_cs = -1, root_ncs = -1;
+    int root_cs = RB_EDGE_EMPTY, root_ncs = RB_EDGE_EMPTY;
     float expand = 0.f;
 };
 struct HNode { // node of the reference-shaped tree (double precision like the reference's Real)
@@ -586,7 +586,7 @@ inline V3 host_edge_normal(const rb_shape* hs, const Edge& e, int which) {
 inline void host_build_edge_tree(const std::vector<rb_shape>& shapes, const std::vector<HostMesh>& meshes, const std::vector<Edge>& edges,
                                  const DevCamera& cam, HostEdgeTree& out) {
     out.nodes.clear();
-    out.root_cs = out.root_ncs = -1;
+    out.root_cs = out.root_ncs = RB_EDGE_EMPTY;
     out.expand = 0.f;
     int E = (int)edges.size();
     if (E == 0) return;
@@ -640,7 +640,7 @@ inline void host_build_edge_tree(const std::vector<rb_shape>& shapes, const std:
     for (int k = 0; k < 3; k++) mad[k] /= E;
     out.expand = (float)(0.01 * std::sqrt(mad[0] * mad[0] + mad[1] * mad[1] + mad[2] * mad[2]));
     auto build = [&](std::vector<int>& ids, bool six) -> int {
-        if (ids.empty()) return -1;
+        if (ids.empty()) return RB_EDGE_EMPTY;
         double lo[6], hi[6];
         for (int k = 0; k < 6; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
         for (int id : ids)
@@ -672,38 +672,38 @@ inline void host_build_edge_tree(const std::vector<rb_shape>& shapes, const std:
         HostTreeBuilder tb;
         tb.six = six;
         int root = tb.build(leaves, codes, ids);
-        // flatten (depth-first) into EdgeNode
+        // flatten the inner nodes (depth-first) into EdgeNode records that carry both children's bounds
+        auto ref_of = [&](int i, const std::vector<int>& map) { return tb.n[i].edge_id != -1 ? ~tb.n[i].edge_id : map[i]; };
         int base = (int)out.nodes.size();
         std::vector<int> map(tb.n.size(), -1);
         std::vector<int> st;
-        st.push_back(root);
         std::vector<int> order;
+        if (tb.n[root].edge_id == -1) st.push_back(root);
         while (!st.empty()) {
             int i = st.back();
             st.pop_back();
             map[i] = base + (int)order.size();
             order.push_back(i);
-            if (tb.n[i].edge_id == -1) {
-                st.push_back(tb.n[i].child[1]);
-                st.push_back(tb.n[i].child[0]);
-            }
+            for (int k = 1; k >= 0; k--)
+                if (tb.n[tb.n[i].child[k]].edge_id == -1) st.push_back(tb.n[i].child[k]);
         }
         for (int i : order) {
-            const HNode& h = tb.n[i];
             EdgeNode en;
-            for (int k = 0; k < 3; k++) {
-                en.pmin[k] = (float)h.pmin[k];
-                en.pmax[k] = (float)h.pmax[k];
-                en.dmin[k] = (float)h.dmin[k];
-                en.dmax[k] = (float)h.dmax[k];
+            memset(&en, 0, sizeof(en));
+            for (int c = 0; c < 2; c++) {
+                const HNode& h = tb.n[tb.n[i].child[c]];
+                for (int k = 0; k < 3; k++) {
+                    en.c[c].pmin[k] = (float)h.pmin[k];
+                    en.c[c].pmax[k] = (float)h.pmax[k];
+                    en.c[c].dmin[k] = (float)h.dmin[k];
+                    en.c[c].dmax[k] = (float)h.dmax[k];
+                }
+                en.c[c].wlen = (float)h.wlen;
+                en.c[c].ref = ref_of(tb.n[i].child[c], map);
             }
-            en.wlen = (float)h.wlen;
-            en.edge_id = h.edge_id;
-            en.left = h.edge_id == -1 ? map[h.child[0]] : -1;
-            en.right = h.edge_id == -1 ? map[h.child[1]] : -1;
             out.nodes.push_back(en);
         }
-        return base;
+        return ref_of(root, map);
     };
     out.root_cs = build(ids_cs, false);
     out.root_ncs = build(ids_ncs, true);

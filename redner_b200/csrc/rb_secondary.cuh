@@ -55,55 +55,68 @@ struct EdgeCtx { // per-vertex constants of the sampler
     const DevScene* sc;
     SurfacePoint p;
     M3 m, m_inv;
+    M3 abs_m_inv; // |M^-1| element-wise (box transform)
     V3 cam_org;
+    // Olson & Zhang sphere of the shading point: centre 0.5 (p - cam_org), radius^2
+    V3 hough_center;
+    Real hough_r2;
 };
+RB_HD void edge_ctx_finish(EdgeCtx& c) { // call after m_inv / cam_org / p are set
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) c.abs_m_inv.m[i][j] = fabs(c.m_inv.m[i][j]);
+    c.hough_center = Real(0.5) * (c.p.position - c.cam_org);
+    c.hough_r2 = rb_sq(Real(0.5) * length(c.p.position - c.cam_org));
+}
 
 RB_HD Real min_abs_bound(Real lo, Real hi) {
     if (lo <= 0 && hi >= 0) return 0;
     if (lo <= 0 && hi <= 0) return hi;
     return lo;
 }
-RB_HD bool node_contains(const EdgeNode& n, V3 p) {
+// p inside the PARENT's box == inside the union of its children's boxes (the builder takes exact min / max)
+RB_HD bool parent_contains(const EdgeNode& n, V3 p) {
+    for (int k = 0; k < 3; k++) {
+        Real lo = n.c[0].pmin[k] < n.c[1].pmin[k] ? n.c[0].pmin[k] : n.c[1].pmin[k], hi = n.c[0].pmax[k] > n.c[1].pmax[k] ? n.c[0].pmax[k] : n.c[1].pmax[k];
+        if (!(p[k] >= lo && p[k] <= hi)) return false;
+    }
+    return true;
+}
+RB_HD bool node_contains(const EdgeChild& n, V3 p) {
     return p.x >= n.pmin[0] && p.x <= n.pmax[0] && p.y >= n.pmin[1] && p.y <= n.pmax[1] && p.z >= n.pmin[2] && p.z <= n.pmax[2];
 }
-// Upper bound of the (linearly transformed) cosine lobe over a position box, src/edge.cpp:838-875
-RB_D Real ltc_bound(const EdgeNode& n, const EdgeCtx& c) {
-    V3 dir = mk3(0, 0, 1);
-    if (!node_contains(n, c.p.position)) {
-        // Bounding box of the 8 transformed corners (the reference transforms every corner and takes min/max): the map
-        // is affine, so it is the transformed centre +- |M^-1| * half-extent -- a fifth of the arithmetic.
-        V3 ctr = Real(0.5) * (mk3(n.pmin[0], n.pmin[1], n.pmin[2]) + mk3(n.pmax[0], n.pmax[1], n.pmax[2])) - c.p.position;
-        V3 ext = Real(0.5) * (mk3(n.pmax[0], n.pmax[1], n.pmax[2]) - mk3(n.pmin[0], n.pmin[1], n.pmin[2]));
-        V3 q = mul(c.m_inv, ctr);
-        V3 r = mk3(fabs(c.m_inv.m[0][0]) * ext.x + fabs(c.m_inv.m[0][1]) * ext.y + fabs(c.m_inv.m[0][2]) * ext.z,
-                   fabs(c.m_inv.m[1][0]) * ext.x + fabs(c.m_inv.m[1][1]) * ext.y + fabs(c.m_inv.m[1][2]) * ext.z,
-                   fabs(c.m_inv.m[2][0]) * ext.x + fabs(c.m_inv.m[2][1]) * ext.y + fabs(c.m_inv.m[2][2]) * ext.z);
-        V3 lo = q - r, hi = q + r;
-        if (hi.z < 0) return 0;
-        dir = mk3(min_abs_bound(lo.x, hi.x), min_abs_bound(lo.y, hi.y), hi.z);
-        Real l = length(dir);
-        dir = l <= 0 ? mk3(0, 0, 1) : dir / l;
-    }
-    V3 max_dir = normalize(mul(c.m, dir));
-    V3 local = mul(c.m_inv, max_dir);
-    if (local.z <= 0) return 0;
-    return local.z / rb_sq(length_sq(local));
+// Upper bound of the (linearly transformed) cosine lobe over a position box, src/edge.cpp:838-875.
+//  * The reference transforms the 8 corners and takes min / max: the map is affine, so that box is the transformed centre
+//    +- |M^-1| * half-extent -- a fifth of the arithmetic.
+//  * Its tail  max_dir = normalize(M dir); local = M^-1 max_dir; return local.z / |local|^4  is  dir.z * |M dir|^3  for a unit `dir`
+//    (local == dir / |M dir|): one matrix product and one normalisation less.
+//  * Written without divergent branches: lanes of a warp walk different nodes, and "shading point inside the box" is a per-lane fact.
+RB_D Real ltc_bound(const EdgeChild& n, const EdgeCtx& c) {
+    const bool inside = node_contains(n, c.p.position);
+    V3 ctr = Real(0.5) * (mk3(n.pmin[0], n.pmin[1], n.pmin[2]) + mk3(n.pmax[0], n.pmax[1], n.pmax[2])) - c.p.position;
+    V3 ext = Real(0.5) * (mk3(n.pmax[0], n.pmax[1], n.pmax[2]) - mk3(n.pmin[0], n.pmin[1], n.pmin[2]));
+    V3 q = mul(c.m_inv, ctr), r = mul(c.abs_m_inv, ext);
+    V3 lo = q - r, hi = q + r;
+    V3 dir = mk3(min_abs_bound(lo.x, hi.x), min_abs_bound(lo.y, hi.y), hi.z);
+    Real l = length(dir);
+    dir = (inside || l <= 0) ? mk3(0, 0, 1) : dir / l;
+    if (!inside && hi.z < 0) return 0;
+    if (dir.z <= 0) return 0;
+    Real len2 = length_sq(mul(c.m, dir));
+    return dir.z * len2 * sqrt(len2);
 }
-// Olson & Zhang: an edge of the non-camera-silhouette set can only be a silhouette from p if the sphere with
-// diameter (cam_org, p) touches its Hough-space box; src/edge.cpp:906-911, box/sphere test src/aabb.h:155-171
-RB_HD bool hough_may_be_silhouette(const EdgeNode& n, V3 p, V3 cam_org) {
-    V3 center = Real(0.5) * (p - cam_org);
-    Real r2 = rb_sq(Real(0.5) * length(p - cam_org));
-    Real d = 0;
-    for (int i = 0; i < 3; i++) {
-        if (center[i] < n.dmin[i]) d += rb_sq(center[i] - n.dmin[i]);
-        else if (center[i] > n.dmax[i]) d += rb_sq(center[i] - n.dmax[i]);
-        if (d <= r2) return true;
-    }
-    return false;
+// Olson & Zhang: an edge of the non-camera-silhouette set can only be a silhouette from p if the sphere with diameter
+// (cam_org, p) touches its Hough-space box.  The reference's box / sphere test (Arvo's, src/aabb.h:155-171) returns from INSIDE
+// its loop over the axes as soon as the accumulated distance is within the radius; the accumulated distance only grows, so its
+// verdict is the verdict of the FIRST axis alone -- which is what this evaluates (same result, a third of the work).
+RB_HD bool hough_may_be_silhouette_at(const EdgeChild& n, V3 center, Real r2) {
+    Real d = center.x < n.dmin[0] ? rb_sq(center.x - n.dmin[0]) : (center.x > n.dmax[0] ? rb_sq(center.x - n.dmax[0]) : Real(0));
+    return d <= r2;
 }
-RB_D Real node_importance(const EdgeNode& n, bool is6d, const EdgeCtx& c) {
-    if (is6d && !hough_may_be_silhouette(n, c.p.position, c.cam_org)) return 0;
+RB_HD bool hough_may_be_silhouette(const EdgeChild& n, V3 p, V3 cam_org) {
+    return hough_may_be_silhouette_at(n, Real(0.5) * (p - cam_org), rb_sq(Real(0.5) * length(p - cam_org)));
+}
+RB_D Real node_importance(const EdgeChild& n, bool is6d, const EdgeCtx& c) {
+    if (is6d && !hough_may_be_silhouette_at(n, c.hough_center, c.hough_r2)) return 0;
     Real brdf = ltc_bound(n, c);
     V3 center = Real(0.5) * (mk3(n.pmin[0], n.pmin[1], n.pmin[2]) + mk3(n.pmax[0], n.pmax[1], n.pmax[2]));
     return brdf * n.wlen / rb_max(length(center - c.p.position), Real(1e-3));
@@ -142,7 +155,7 @@ RB_D Real leaf_importance_l(const Edge& e, const EdgeCtx& c, const Ray& nee, Rea
     return edge_ltc_integral(v0, v1, c);
 }
 // pbrt-style slab test with the box grown by `expand`, src/aabb.h:172-195
-RB_HD bool node_hit_by_ray(const EdgeNode& n, const Ray& r, Real expand) {
+RB_HD bool node_hit_by_ray(const EdgeChild& n, const Ray& r, Real expand) {
     Real t0 = r.tmin, t1 = r.tmax;
     for (int i = 0; i < 3; i++) {
         Real inv = 1 / r.dir[i];
@@ -189,7 +202,7 @@ RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sampl
     int sp = 0;
     int selected = -1;
     Real edge_weight = 0, wsum = 0;
-    Real imp_cs = sc.edge_root_cs >= 0 ? Real(1) : Real(0), imp_ncs = sc.edge_root_ncs >= 0 ? Real(1) : Real(0);
+    Real imp_cs = sc.edge_root_cs != RB_EDGE_EMPTY ? Real(1) : Real(0), imp_ncs = sc.edge_root_ncs != RB_EDGE_EMPTY ? Real(1) : Real(0);
     if (imp_cs <= 0 && imp_ncs <= 0) return -1;
     Real prob_cs = imp_cs / (imp_cs + imp_ncs);
     int n_cs, n_ncs;
@@ -203,27 +216,27 @@ RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sampl
     int nl = 0;
     while (sp > 0) {
         StackH it = stack[--sp];
-        const EdgeNode& n = sc.edge_nodes[it.node];
-        if (n.edge_id >= 0) {
+        if (it.node < 0) { // leaf: ~edge id
             if (nl < RB_EDGE_H_SAMPLES) {
                 leaves[nl] = it;
-                leaves[nl].node = n.edge_id;
+                leaves[nl].node = ~it.node;
                 nl++;
             }
         } else {
+            const EdgeNode n = sc.edge_nodes[it.node]; // one 128-byte fetch: both children's bounds and references
             Real i0, i1;
-            if (node_contains(n, c.p.position)) {
+            if (parent_contains(n, c.p.position)) {
                 i0 = i1 = 1;
             } else {
-                i0 = node_importance(sc.edge_nodes[n.left], it.is6d != 0, c);
-                i1 = node_importance(sc.edge_nodes[n.right], it.is6d != 0, c);
+                i0 = node_importance(n.c[0], it.is6d != 0, c);
+                i1 = node_importance(n.c[1], it.is6d != 0, c);
             }
             if (i0 > 0 || i1 > 0) {
                 Real p0 = i0 / (i0 + i1);
                 int n0, n1;
                 split_samples(it.num, p0, u, n0, n1);
-                if (n0 > 0 && sp < RB_EDGE_STACK_H) { stack[sp].node = n.left; stack[sp].num = (short)n0; stack[sp].is6d = it.is6d; stack[sp].pmf = it.pmf * p0; sp++; }
-                if (n1 > 0 && sp < RB_EDGE_STACK_H) { stack[sp].node = n.right; stack[sp].num = (short)n1; stack[sp].is6d = it.is6d; stack[sp].pmf = it.pmf * (1 - p0); sp++; }
+                if (n0 > 0 && sp < RB_EDGE_STACK_H) { stack[sp].node = n.c[0].ref; stack[sp].num = (short)n0; stack[sp].is6d = it.is6d; stack[sp].pmf = it.pmf * p0; sp++; }
+                if (n1 > 0 && sp < RB_EDGE_STACK_H) { stack[sp].node = n.c[1].ref; stack[sp].num = (short)n1; stack[sp].is6d = it.is6d; stack[sp].pmf = it.pmf * (1 - p0); sp++; }
             }
         }
     }
@@ -256,9 +269,9 @@ RB_D int sample_edge_gather(const EdgeCtx& c, const Ray& nee, const Isect& lis, 
     int selected = -1;
     Real edge_weight = 0, wsum = 0;
     Real expand = sc.edge_bounds_expand;
-    // encode the tree kind in bit 30
-    if (sc.edge_root_cs >= 0) stack[sp++] = sc.edge_root_cs;
-    if (sc.edge_root_ncs >= 0) stack[sp++] = sc.edge_root_ncs | (1 << 30);
+    // stack items: child references.  Inner nodes (index >= 0) carry the tree kind in bit 30; leaves (~edge id < 0) need none.
+    if (sc.edge_root_cs != RB_EDGE_EMPTY) stack[sp++] = sc.edge_root_cs;
+    if (sc.edge_root_ncs != RB_EDGE_EMPTY) stack[sp++] = sc.edge_root_ncs < 0 ? sc.edge_root_ncs : (sc.edge_root_ncs | (1 << 30));
     // Same two-phase structure as the hierarchical sampler: box tests run until RB_GATHER_BATCH leaves are pending (or the
     // stack is empty), then the pending leaves are weighed in arrival order.
     int pending[RB_GATHER_BATCH];
@@ -266,18 +279,17 @@ RB_D int sample_edge_gather(const EdgeCtx& c, const Ray& nee, const Isect& lis, 
     while (sp > 0 || np > 0) {
         while (sp > 0 && np < RB_GATHER_BATCH) {
             int item = stack[--sp];
+            if (item < 0) {
+                pending[np++] = ~item;
+                continue;
+            }
             bool is6d = (item & (1 << 30)) != 0;
-            const EdgeNode& n = sc.edge_nodes[item & ~(1 << 30)];
-            if (n.edge_id >= 0) {
-                pending[np++] = n.edge_id;
-            } else {
-                for (int k = 0; k < 2; k++) {
-                    int ci = k == 0 ? n.left : n.right;
-                    const EdgeNode& ch = sc.edge_nodes[ci];
-                    bool ok = true;
-                    if (is6d) ok = hough_may_be_silhouette(ch, c.p.position, c.cam_org) && hough_may_be_silhouette(ch, lp.position, c.cam_org);
-                    if (ok && node_hit_by_ray(ch, nee, expand) && sp < RB_EDGE_STACK_L) stack[sp++] = ci | (is6d ? (1 << 30) : 0);
-                }
+            const EdgeNode n = sc.edge_nodes[item & ~(1 << 30)];
+            for (int k = 0; k < 2; k++) {
+                const EdgeChild& ch = n.c[k];
+                bool ok = true;
+                if (is6d) ok = hough_may_be_silhouette_at(ch, c.hough_center, c.hough_r2) && hough_may_be_silhouette(ch, lp.position, c.cam_org);
+                if (ok && node_hit_by_ray(ch, nee, expand) && sp < RB_EDGE_STACK_L) stack[sp++] = ch.ref < 0 ? ch.ref : (ch.ref | (is6d ? (1 << 30) : 0));
             }
         }
         for (int k = 0; k < np; k++) {
@@ -396,6 +408,7 @@ RB_D bool secondary_edge_pick(const DevScene& sc, const VertexRec& cur, Sampler&
         c.m = m3_inverse(c.m_inv);
         m_pmf = ps;
     }
+    edge_ctx_finish(c);
     int edge_id = -1;
     Real edge_weight = 0;
     V3 sample_p = zero3(), mwt = zero3();

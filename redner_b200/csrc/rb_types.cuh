@@ -99,15 +99,22 @@ struct DevLight {
     int two_sided, directly_visible;
 };
 
-// Secondary-edge tree node (own flat layout, 64 B; replaces the pointer-linked BVHNode3 / BVHNode6 of
-// src/edge_tree.h:14-30).  The camera-silhouette tree only uses the position box, the other tree also the box in
-// Hough space (src/edge_tree.cpp:23-66).  Leaf <=> edge_id >= 0.
-struct __align__(16) EdgeNode {
+// Secondary-edge trees (own flat layout; replaces the pointer-linked BVHNode3 / BVHNode6 of src/edge_tree.h:14-30).  One 128-byte
+// record per INNER node holding BOTH children's bounds: every step of the two edge-tree walks is one fetch followed by
+// arithmetic, instead of "load node, then load its two children" (the walks were bound by those dependent loads: 40 % of the
+// boundary stage's stall samples were long-scoreboard, profiles/r02_teapot_*).  The camera-silhouette tree only uses the position
+// box, the other tree also the box in Hough space (src/edge_tree.cpp:23-66).
+// A child reference is >= 0: index of an inner node, < 0: leaf, edge id = ~ref; RB_EDGE_EMPTY: no tree.
+#define RB_EDGE_EMPTY ((int)0x80000000)
+struct EdgeChild {
     float pmin[3], pmax[3];
     float dmin[3], dmax[3];
-    float wlen; // sum of length * exterior dihedral angle below this node
-    int left, right;
-    int edge_id;
+    float wlen; // sum of length * exterior dihedral angle below this child
+    int ref;
+};
+struct __align__(16) EdgeNode {
+    EdgeChild c[2];
+    int pad[4];
 };
 
 // EnvironmentMap, src/envmap.h:19-51 (the texture and the two sampling tables are caller-owned device memory)
@@ -147,7 +154,7 @@ struct DevScene {
     const double* prim_edge_cdf;
     // secondary edge trees
     const EdgeNode* edge_nodes;
-    int edge_root_cs, edge_root_ncs; // camera-silhouette tree / rest (index into edge_nodes, -1 if empty)
+    int edge_root_cs, edge_root_ncs; // camera-silhouette tree / rest: child reference of the root (RB_EDGE_EMPTY if empty)
     float edge_bounds_expand;
     const float* ltc_table;
     // samplers

@@ -345,6 +345,11 @@ class Scene:  # src/redner.cpp:62-73, src/scene.cpp:63-307
         if self._lib.rb_scene_set_partition(self._handle, int(part), int(num_parts), int(rows_per_stripe)) != 0:
             raise RuntimeError("redner.Scene.set_partition: " + L.last_error(self._lib))
 
+    def set_camera(self, camera):
+        """Re-target this scene at another camera; only the camera-dependent tables are rebuilt, on the device (rb_scene_set_camera)."""
+        if self._lib.rb_scene_set_camera(self._handle, C.byref(camera._c)) != 0:
+            raise RuntimeError("redner.Scene.set_camera: " + L.last_error(self._lib))
+
     def last_stats(self):
         n = C.c_int(0)
         ms = C.c_float(0)
@@ -363,6 +368,17 @@ class Scene:  # src/redner.cpp:62-73, src/scene.cpp:63-307
             self._lib.rb_scene_last_backward_stats(self._handle, b)
             out.update(dict(zip(("k_bwd_trace", "k_bwd_secondary", "k_bwd_sweep"), list(b))))
         return out, v.value, h.value
+
+    def edge_trees(self):
+        """(records [n, 32] as uint32 words, root of the camera-silhouette tree, root of the other tree, billboard size): test hook."""
+        import numpy as np
+        info = (C.c_int * 3)()
+        ex = C.c_float(0)
+        self._lib.rb_scene_edge_trees(self._handle, info, C.byref(ex), None, 0)
+        rec = np.zeros((max(info[0], 0), 32), dtype=np.uint32)
+        if info[0] > 0:
+            self._lib.rb_scene_edge_trees(self._handle, info, C.byref(ex), rec.ctypes.data_as(C.c_void_p), rec.nbytes)
+        return rec, info[1], info[2], ex.value
 
     def build_ms(self):
         ms = (C.c_float * 3)()

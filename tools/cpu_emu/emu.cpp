@@ -89,7 +89,7 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
     for (const rb_material& m : sc->materials)
         if (m.generic_texture.num_levels > 0) sc->max_generic = std::max(sc->max_generic, m.generic_texture.channels);
     DevScene& d = sc->dev;
-    d.edge_root_cs = d.edge_root_ncs = -1;
+    d.edge_root_cs = d.edge_root_ncs = RB_EDGE_EMPTY;
     d.shapes = sc->shapes.data();
     d.num_shapes = (int)sc->shapes.size();
     d.materials = sc->materials.data();
@@ -172,7 +172,7 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
         d.num_edges = (int)sc->et.edges.size();
         d.prim_edge_pmf = sc->et.prim_pmf.data();
         d.prim_edge_cdf = sc->et.prim_cdf.data();
-        d.edge_root_cs = d.edge_root_ncs = -1;
+        d.edge_root_cs = d.edge_root_ncs = RB_EDGE_EMPTY;
         if (d.use_secondary_edge) {
             host_build_edge_tree(sc->shapes, meshes, sc->et.edges, d.cam, sc->tree);
             d.edge_nodes = sc->tree.nodes.data();
