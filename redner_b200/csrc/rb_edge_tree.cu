@@ -52,6 +52,10 @@ __device__ __forceinline__ double ord2d(unsigned long long o) {
     unsigned long long b = (o & 0x8000000000000000ULL) ? (o & 0x7fffffffffffffffULL) : ~o;
     return __longlong_as_double((long long)b);
 }
+// std::min / std::max semantics: the FIRST argument wins ties -- fmin / fmax order -0 below +0, and the Hough bounds are full of
+// signed zeros (axis-aligned faces); the records must equal the host builder's bit for bit
+__device__ __forceinline__ double et_min(double a, double b) { return b < a ? b : a; }
+__device__ __forceinline__ double et_max(double a, double b) { return a < b ? b : a; }
 __device__ V3 et_edge_normal(const rb_shape* shapes, const Edge& e, int which) { // host_edge_normal
     V3 v0 = edge_v0(shapes, e), v1 = edge_v1(shapes, e);
     V3 n;
@@ -91,13 +95,13 @@ __global__ void k_et_leaves(const rb_shape* shapes, const Edge* edges, int E, do
         }
         for (int k = 0; k < 3; k++) {
             double h0 = (double)n0[k] * p0d, h1 = (double)n1[k] * p1d;
-            n.pmin[k] = fmin((double)v0[k], (double)v1[k]);
-            n.pmax[k] = fmax((double)v0[k], (double)v1[k]);
-            n.dmin[k] = fmin(h0, h1);
-            n.dmax[k] = fmax(h0, h1);
+            n.pmin[k] = et_min((double)v0[k], (double)v1[k]);
+            n.pmax[k] = et_max((double)v0[k], (double)v1[k]);
+            n.dmin[k] = et_min(h0, h1);
+            n.dmax[k] = et_max(h0, h1);
         }
         double ext = M_PI;
-        if (e.f1 != -1) ext = acos(fmin(1.0, fmax(-1.0, (double)dot(n0, n1))));
+        if (e.f1 != -1) ext = acos(et_min(1.0, et_max(-1.0, (double)dot(n0, n1))));
         n.wlen = (double)length(v1 - v0) * ext;
         n.parent = -1;
         n.child[0] = n.child[1] = -1;
@@ -277,10 +281,10 @@ struct ETOps {
     int six;
     __device__ static void merge_into(ETNode& o, const ETNode& a, const ETNode& b) {
         for (int k = 0; k < 3; k++) {
-            o.pmin[k] = fmin(a.pmin[k], b.pmin[k]);
-            o.pmax[k] = fmax(a.pmax[k], b.pmax[k]);
-            o.dmin[k] = fmin(a.dmin[k], b.dmin[k]);
-            o.dmax[k] = fmax(a.dmax[k], b.dmax[k]);
+            o.pmin[k] = et_min(a.pmin[k], b.pmin[k]);
+            o.pmax[k] = et_max(a.pmax[k], b.pmax[k]);
+            o.dmin[k] = et_min(a.dmin[k], b.dmin[k]);
+            o.dmax[k] = et_max(a.dmax[k], b.dmax[k]);
         }
     }
     __device__ double area(const ETNode& a) const {
@@ -349,94 +353,108 @@ struct ETOps {
         }
         propagate_cost(parent, lv, cnt);
     }
-    __device__ void treelet_optimize(int root) { // src/edge_tree.cpp:627-684
-        if (n[root].edge_id != -1) return;
-        int lv[7], inner[5];
-        int cnt = 0, icnt = 0;
-        lv[cnt++] = n[root].child[0];
-        lv[cnt++] = n[root].child[1];
-        int max_idx = 0;
-        while (cnt < 7 && max_idx != -1) {
-            max_idx = -1;
-            double max_area = -1;
-            for (int i = 0; i < cnt; i++)
-                if (n[lv[i]].edge_id == -1) {
-                    double a = area(n[lv[i]]);
-                    if (a > max_area) {
-                        max_area = a;
-                        max_idx = i;
-                    }
-                }
-            if (max_idx != -1) {
-                int tmp = lv[max_idx];
-                inner[icnt++] = tmp;
-                lv[max_idx] = lv[cnt - 1];
-                lv[cnt - 1] = n[tmp].child[0];
-                lv[cnt] = n[tmp].child[1];
-                cnt++;
-            }
-        }
-        // Algorithm 2 of Karras & Aila 2013 (src/edge_tree.cpp:502-544)
+    // One WARP optimises one treelet: lane 0 forms it and rewires the tree afterwards; the 127 subset areas and, round by round, the
+    // optimal partition of every subset of k leaves (Karras & Aila 2013, Algorithm 2, src/edge_tree.cpp:502-544) are spread over the
+    // lanes.  Each subset is still evaluated by ONE lane in the reference's order, so ties resolve identically.  (A single thread
+    // per treelet -- the host builder's shape -- costs ~0.2 ms per node here and the pass climbs ~30 levels.)
+    struct Scratch { // shared memory, per warp
+        double a[128], c_opt[128], bx[7][12];
         unsigned char optimal[128];
-        double a[128], c_opt[128];
-        const unsigned num_subsets = (1u << cnt) - 1;
-        {
-            // a[s] = area(union(leaf 0, leaves of s)) -- the reference's union always starts from leaf 0 (src/edge_tree.cpp:491-500)
-            double bx[7][12];
-            for (int i = 0; i < cnt; i++) {
-                const ETNode& l = n[lv[i]];
-                for (int k = 0; k < 3; k++) {
-                    bx[i][k] = l.pmin[k];
-                    bx[i][3 + k] = l.pmax[k];
-                    bx[i][6 + k] = l.dmin[k];
-                    bx[i][9 + k] = l.dmax[k];
+        int lv[7], inner[5], cnt;
+    };
+    __device__ void treelet_optimize_warp(int root, Scratch& w) {
+        const int lane = threadIdx.x & 31;
+        if (n[root].edge_id != -1) return; // (warp-uniform)
+        if (lane == 0) { // src/edge_tree.cpp:627-684
+            int cnt = 0, icnt = 0;
+            w.lv[cnt++] = n[root].child[0];
+            w.lv[cnt++] = n[root].child[1];
+            int max_idx = 0;
+            while (cnt < 7 && max_idx != -1) {
+                max_idx = -1;
+                double max_area = -1;
+                for (int i = 0; i < cnt; i++)
+                    if (n[w.lv[i]].edge_id == -1) {
+                        double ar = area(n[w.lv[i]]);
+                        if (ar > max_area) {
+                            max_area = ar;
+                            max_idx = i;
+                        }
+                    }
+                if (max_idx != -1) {
+                    int tmp = w.lv[max_idx];
+                    w.inner[icnt++] = tmp;
+                    w.lv[max_idx] = w.lv[cnt - 1];
+                    w.lv[cnt - 1] = n[tmp].child[0];
+                    w.lv[cnt] = n[tmp].child[1];
+                    cnt++;
                 }
             }
-            for (unsigned s = 1; s <= num_subsets; s++) {
-                ETNode t;
+            w.cnt = cnt;
+            for (int i = 0; i < cnt; i++) {
+                const ETNode& l = n[w.lv[i]];
                 for (int k = 0; k < 3; k++) {
-                    t.pmin[k] = bx[0][k];
-                    t.pmax[k] = bx[0][3 + k];
-                    t.dmin[k] = bx[0][6 + k];
-                    t.dmax[k] = bx[0][9 + k];
+                    w.bx[i][k] = l.pmin[k];
+                    w.bx[i][3 + k] = l.pmax[k];
+                    w.bx[i][6 + k] = l.dmin[k];
+                    w.bx[i][9 + k] = l.dmax[k];
                 }
-                for (int i = 1; i < cnt; i++)
-                    if ((s >> i) & 1u)
-                        for (int k = 0; k < 3; k++) {
-                            t.pmin[k] = fmin(t.pmin[k], bx[i][k]);
-                            t.pmax[k] = fmax(t.pmax[k], bx[i][3 + k]);
-                            t.dmin[k] = fmin(t.dmin[k], bx[i][6 + k]);
-                            t.dmax[k] = fmax(t.dmax[k], bx[i][9 + k]);
-                        }
-                a[s] = area(t);
+                w.c_opt[1u << i] = l.cost;
             }
         }
-        for (int i = 0; i < cnt; i++) c_opt[1u << i] = n[lv[i]].cost;
-        for (int k = 2; k <= cnt; k++)
-            for (unsigned s = 1; s <= num_subsets; s++)
+        __syncwarp();
+        const int cnt = w.cnt;
+        const unsigned num_subsets = (1u << cnt) - 1;
+        // a[s] = area(union(leaf 0, leaves of s)) -- the reference's union always starts from leaf 0 (src/edge_tree.cpp:491-500)
+        for (unsigned s = 1 + lane; s <= num_subsets; s += 32) {
+            ETNode t;
+            for (int k = 0; k < 3; k++) {
+                t.pmin[k] = w.bx[0][k];
+                t.pmax[k] = w.bx[0][3 + k];
+                t.dmin[k] = w.bx[0][6 + k];
+                t.dmax[k] = w.bx[0][9 + k];
+            }
+            for (int i = 1; i < cnt; i++)
+                if ((s >> i) & 1u)
+                    for (int k = 0; k < 3; k++) {
+                        t.pmin[k] = et_min(t.pmin[k], w.bx[i][k]);
+                        t.pmax[k] = et_max(t.pmax[k], w.bx[i][3 + k]);
+                        t.dmin[k] = et_min(t.dmin[k], w.bx[i][6 + k]);
+                        t.dmax[k] = et_max(t.dmax[k], w.bx[i][9 + k]);
+                    }
+            w.a[s] = area(t);
+        }
+        __syncwarp();
+        for (int k = 2; k <= cnt; k++) {
+            for (unsigned s = 1 + lane; s <= num_subsets; s += 32)
                 if (__popc(s) == k) {
                     double c_s = INFINITY;
                     unsigned p_s = 0;
                     unsigned d = (s - 1u) & s;
                     unsigned p = (0u - d) & s;
                     do {
-                        double c = c_opt[p] + c_opt[s ^ p];
+                        double c = w.c_opt[p] + w.c_opt[s ^ p];
                         if (c < c_s) {
                             c_s = c;
                             p_s = p;
                         }
                         p = (p - d) & s;
                     } while (p != 0);
-                    c_opt[s] = a[s] + c_s;
-                    optimal[s] = (unsigned char)p_s;
+                    w.c_opt[s] = w.a[s] + c_s;
+                    w.optimal[s] = (unsigned char)p_s;
                 }
-        unsigned char mask = (unsigned char)((1u << cnt) - 1);
-        int index = 0;
-        unsigned char left = optimal[mask];
-        restruct(root, 0, lv, inner, left, optimal, index, cnt);
-        unsigned char right = (unsigned char)((~left) & mask);
-        restruct(root, 1, lv, inner, right, optimal, index, cnt);
-        refresh(root);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            unsigned char mask = (unsigned char)((1u << cnt) - 1);
+            int index = 0;
+            unsigned char left = w.optimal[mask];
+            restruct(root, 0, w.lv, w.inner, left, w.optimal, index, cnt);
+            unsigned char right = (unsigned char)((~left) & mask);
+            restruct(root, 1, w.lv, w.inner, right, w.optimal, index, cnt);
+            refresh(root);
+        }
+        __syncwarp();
     }
 };
 // Bottom-up pass: every thread starts at a leaf and climbs; the SECOND thread to arrive at a node processes it (its two subtrees are
@@ -446,7 +464,6 @@ template <int PASS>
 __global__ void k_et_climb(ETTree t, ETNode* nodes, int* arrived, int* inner_count) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= t.L || t.L < 2) return;
-    ETOps ops{nodes, t.six};
     int cur = nodes[t.base + et_lb(t) + j].parent;
     while (cur != -1) {
         __threadfence();
@@ -458,12 +475,33 @@ __global__ void k_et_climb(ETTree t, ETNode* nodes, int* arrived, int* inner_cou
             ETOps::merge_into(o, a, b);
             o.wlen = a.wlen + b.wlen;
             nodes[cur] = o;
-        } else if (PASS == 1) {
-            ops.treelet_optimize(cur);
         } else {
             int c0 = nodes[cur].child[0], c1 = nodes[cur].child[1];
             inner_count[cur] = 1 + (nodes[c0].edge_id == -1 ? inner_count[c0] : 0) + (nodes[c1].edge_id == -1 ? inner_count[c1] : 0);
         }
+        cur = nodes[cur].parent;
+    }
+}
+// The treelet pass (src/edge_tree.cpp:685-707): one warp per leaf climbs; lane 0 owns the arrival counters.
+#define RB_ET_WARPS 4
+__global__ void __launch_bounds__(32 * RB_ET_WARPS) k_et_optimize(ETTree t, ETNode* nodes, int* arrived) {
+    __shared__ ETOps::Scratch scratch[RB_ET_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int j = blockIdx.x * RB_ET_WARPS + warp;
+    if (j >= t.L || t.L < 2) return;
+    ETOps ops{nodes, t.six};
+    int cur = nodes[t.base + et_lb(t) + j].parent;
+    while (cur != -1) {
+        int go = 0;
+        if (lane == 0) {
+            __threadfence();
+            go = atomicAdd(&arrived[cur], 1) != 0;
+            __threadfence();
+        }
+        go = __shfl_sync(0xffffffffu, go, 0);
+        if (!go) break; // first arrival: the sibling subtree is not done
+        ops.treelet_optimize_warp(cur, scratch[warp]);
+        __threadfence();
         cur = nodes[cur].parent;
     }
 }
@@ -583,7 +621,7 @@ int rb_build_edge_trees_gpu(rb_scene* sc, cudaStream_t stream) {
             for (int pass = 0; pass < 3; pass++) {
                 RB_CUDA_OK(cudaMemsetAsync(arrived, 0, sizeof(int) * NN, stream));
                 if (pass == 0) k_et_climb<0><<<GL, B, 0, stream>>>(tr, nodes, arrived, inner_count);
-                else if (pass == 1) k_et_climb<1><<<(tr.L + 63) / 64, 64, 0, stream>>>(tr, nodes, arrived, inner_count);
+                else if (pass == 1) k_et_optimize<<<(tr.L + RB_ET_WARPS - 1) / RB_ET_WARPS, 32 * RB_ET_WARPS, 0, stream>>>(tr, nodes, arrived);
                 else k_et_climb<2><<<GL, B, 0, stream>>>(tr, nodes, arrived, inner_count);
             }
             k_et_rank<<<GL, B, 0, stream>>>(tr, nodes, inner_count, rank_base, rank);

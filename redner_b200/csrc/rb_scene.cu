@@ -338,6 +338,9 @@ int rb_build_lights(rb_scene* sc, cudaStream_t stream) {
     return 0;
 }
 
+#ifndef RB_GPU_TABLES_MIN_EDGES
+#define RB_GPU_TABLES_MIN_EDGES 1024
+#endif
 int rb_build_edges(rb_scene* sc, cudaStream_t stream) {
     sc->dev.edges = nullptr;
     sc->dev.num_edges = 0;
@@ -346,10 +349,13 @@ int rb_build_edges(rb_scene* sc, cudaStream_t stream) {
     // The edge LIST (topology: sort, merge, seam repair, flat-edge filter) is built on the host; everything that depends on the
     // camera -- the primary-edge distribution and the two secondary-edge trees -- on the device (rb_edge_tree.cu), so that
     // rb_scene_set_camera / rb_render_batch re-target a scene without touching the host.  RB_HOST_TREES=1: host tables (tests).
-    const bool host_tables = getenv("RB_HOST_TREES") != nullptr;
+    // Small edge sets (a few hundred edges: C1, C2) are faster on the host than ~25 kernel launches and two synchronisations; the
+    // two builders produce the same tables (tests/test_scene_build_gpu.py), RB_GPU_TREES=1 / RB_HOST_TREES=1 force one of them.
     HostEdgeTables t;
-    host_build_edges(sc->shapes, host_meshes(sc), sc->dev.cam, sc->dev.use_primary_edge != 0 && host_tables, t);
+    host_build_edges(sc->shapes, host_meshes(sc), sc->dev.cam, false, t);
     int E = (int)t.edges.size();
+    const bool host_tables = getenv("RB_HOST_TREES") != nullptr || (E < RB_GPU_TABLES_MIN_EDGES && getenv("RB_GPU_TREES") == nullptr);
+    if (host_tables && sc->dev.use_primary_edge != 0) host_primary_edge_distribution(sc->shapes, host_meshes(sc), sc->dev.cam, t);
     sc->dev.num_edges = E;
     if (E == 0) return 0;
     Edge* d_edges;

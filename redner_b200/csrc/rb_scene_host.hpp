@@ -151,6 +151,8 @@ inline void host_merge_sort_like_reference(std::vector<T>& v, Comp comp) {
     host_merge_sort_range(v, 0, v.size(), comp);
 }
 
+
+inline void host_primary_edge_distribution(const std::vector<rb_shape>& shapes, const std::vector<HostMesh>& meshes, const DevCamera& cam, HostEdgeTables& out);
 // `shapes` carries device (or emulator-host) pointers; only material / light ids and the null-ness of `normals` are
 // read from it here, geometry comes from `meshes`.
 inline void host_build_edges(const std::vector<rb_shape>& shapes, const std::vector<HostMesh>& meshes, const DevCamera& cam, bool want_primary,
@@ -235,8 +237,18 @@ inline void host_build_edges(const std::vector<rb_shape>& shapes, const std::vec
     int E = (int)out.edges.size();
     out.prim_pmf.assign(E, 0);
     out.prim_cdf.assign(E, 0);
-    if (!want_primary || E == 0) return;
-    // screen-space length of camera silhouettes -> PMF / CDF (src/edge.cpp:186-214, :298-331)
+    if (want_primary && E > 0) host_primary_edge_distribution(shapes, meshes, cam, out);
+}
+// screen-space length of camera silhouettes -> PMF / CDF (src/edge.cpp:186-214, :298-331)
+inline void host_primary_edge_distribution(const std::vector<rb_shape>& shapes, const std::vector<HostMesh>& meshes, const DevCamera& cam, HostEdgeTables& out) {
+    int S = (int)shapes.size(), E = (int)out.edges.size();
+    std::vector<rb_shape> hs(shapes);
+    for (int s = 0; s < S; s++) {
+        hs[s].vertices = meshes[s].vertices.data();
+        hs[s].indices = meshes[s].indices.data();
+    }
+    out.prim_pmf.assign(E, 0);
+    out.prim_cdf.assign(E, 0);
     double iw = 1.0 / cam.c2w[15];
     V3 org = mk3((Real)(cam.c2w[3] * iw), (Real)(cam.c2w[7] * iw), (Real)(cam.c2w[11] * iw));
     double total = 0;

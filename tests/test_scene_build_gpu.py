@@ -27,7 +27,9 @@ def _trees(rb, dev, scene, res):
 def test_gpu_edge_trees_equal_the_host_builder(scene, res, monkeypatch):
     from redner_b200 import redner as rb
     dev = torch.device("cuda:0")
+    monkeypatch.setenv("RB_GPU_TREES", "1")  # (scenes with few edges use the host builder by default)
     (rec_g, cs_g, ncs_g, ex_g), ms_g = _trees(rb, dev, scene, res)
+    monkeypatch.delenv("RB_GPU_TREES")
     monkeypatch.setenv("RB_HOST_TREES", "1")
     (rec_h, cs_h, ncs_h, ex_h), ms_h = _trees(rb, dev, scene, res)
     assert rec_g.shape == rec_h.shape and (cs_g, ncs_g) == (cs_h, ncs_h), (rec_g.shape, rec_h.shape, cs_g, cs_h, ncs_g, ncs_h)

@@ -26,7 +26,9 @@ def trees(scene, res):
 
 for scene, res in [(a, 32) for a in sys.argv[1:]]:
     os.environ.pop("RB_HOST_TREES", None)
+    os.environ["RB_GPU_TREES"] = "1"
     (g, cs_g, ncs_g, ex_g), ms_g, wall_g = trees(scene, res)
+    os.environ.pop("RB_GPU_TREES", None)
     os.environ["RB_HOST_TREES"] = "1"
     (h, cs_h, ncs_h, ex_h), ms_h, wall_h = trees(scene, res)
     print("== %s: records %d / %d, roots gpu (%d, %d) host (%d, %d), expand %.9g / %.9g; third build: gpu %s wall %.2f ms | host %s wall %.2f ms" %
