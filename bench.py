@@ -22,7 +22,7 @@ One "step" = one forward render + one backward render == W*H*spp pixel samples t
   roofline      dominant kernel / stage of the step: algorithmic bytes of SURVEY.md section 8(d) over its CUDA-event duration;
   cpu_baseline  the unmodified reference (oracle/_ref, CPU/Embree) on a bounded sample of the same workload (rank 0, N = 1 only).
 
-N > 1, one process per GPU.  `tiles` (the partition north_star names; the headline `value`): ONE image split into 16-row stripes
+N > 1, one process per GPU.  `tiles` (the partition north_star names; the headline `value`): ONE image split into 4-row stripes
 round-robin over the ranks, all-reduce of framebuffer and gradients (strong scaling).  `poses`: every rank renders its own camera
 poses of the workload, one packed gradient all-reduce (weak scaling, BASELINE config 5 pattern).  By default both are measured at
 N > 1 and the weak-scaling result is reported in the extra key "poses".
@@ -43,6 +43,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 SEED = 1
+ROWS_PER_STRIPE = 4  # tiles mode: 4-row stripes round-robin (at 8 ranks and 512 rows every rank owns 16 stripes spread over the image)
 WORKLOADS = {
     "c2": dict(scene="shadow_blocker", res=512, spp=64, mb=1, label="C2 shadow_blocker (tests/test_shadow_blocker.py)"),
     "c3": dict(scene="teapot", res=512, spp=256, mb=2, label="C3 teapot.xml 15712 tris (tests/test_teapot_reflectance.py)"),
@@ -272,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             builds.append((time.perf_counter() - t0) * 1e3)
             if mode == "tiles":
-                c.scene.set_partition(rank, world, 16)
+                c.scene.set_partition(rank, world, ROWS_PER_STRIPE)
             nch = rb.compute_num_channels(c.channels, c.scene.max_generic_texture_dimension)
             img = torch.zeros(RES, RES, nch, device=dev)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
@@ -358,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
             for h in hosts:
                 scn, params = h.to_device(dev)
                 if main_mode == "tiles":
-                    img = rdist.render_tiles(scn, SPP, MB, SEED, sampler_type=st, device=dev)
+                    img = rdist.render_tiles(scn, SPP, MB, SEED, rows_per_stripe=ROWS_PER_STRIPE, sampler_type=st, device=dev)
                 else:
                     img = api.RenderFunction.apply(SEED, *api.RenderFunction.serialize_scene(scn, SPP, MB, sampler_type=st, device=dev))
                 loss = img.pow(2).sum()
@@ -406,7 +407,7 @@ def run_ours(args, rank, world, local_rank):
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     info = next((i for i in reversed(main["infos"]) if i), None)
     cfg = {"workload": "%s %dx%dx%dspp max_bounces=%d sobol, primary+secondary edge sampling, loss=sum(img^2)" % (wl["label"], RES, RES, SPP, MB),
-           "parallelism": "single GPU" if world == 1 else {"tiles": "%d ranks, one image in 16-row stripes round-robin, NCCL all-reduce of framebuffer + gradients" % world,
+           "parallelism": "single GPU" if world == 1 else {"tiles": "%d ranks, one image in %d-row stripes round-robin, NCCL all-reduce of framebuffer + gradients" % (world, ROWS_PER_STRIPE),
                                                            "poses": "%d ranks, %d camera poses per rank, one NCCL gradient all-reduce" % (world, main["imgs_per_rank"])}[main_mode],
            "l2": "256 MB flush between timed steps", "scene_build_ms": sum(main["builds"]) / max(1, len(main["builds"])),
            "e2e": "pinned host tensors -> H2D -> scene build -> forward -> loss -> backward -> D2H of image, loss and every gradient (host clock)"}

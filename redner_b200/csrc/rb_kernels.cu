@@ -321,6 +321,7 @@ std::vector<cudaEvent_t>& ev = events.ev;
         ka.edge_hist = (unsigned*)(scratch + o_hist);
         ka.edge_offs = (unsigned*)(scratch + o_eoffs);
         ka.edge_cursor = (unsigned*)(scratch + o_ecur);
+        ka.hier_persistent = getenv("RB_NO_PERSISTENT_PICK") == nullptr ? 1 : 0; // (test / measurement hook)
         int grid_t, grid_p, grid_s, grid_w;
         if (lean) {
             grid_t = la::grid(la::K_BWD_TRACE, scene->device);
@@ -352,6 +353,11 @@ std::vector<cudaEvent_t>& ev = events.ev;
             if (secondary) {
                 if (lean) la::bwd_sec_pick(&scene->dev, &ka, grid_p, stream);
                 else k_bwd_sec_pick<<<grid_p, RB_BLOCK_SEC, 0, stream>>>(scene->dev, ka);
+                if (ka.hier_persistent) {
+                    if (lean) la::bwd_sec_pick_hier(&scene->dev, &ka, grid_p, stream);
+                    else k_bwd_sec_pick_hier<<<grid_p, RB_BLOCK_SEC, 0, stream>>>(scene->dev, ka);
+                    launches++;
+                }
                 k_sec_offsets<<<1, 1024, 0, stream>>>(ka, scene->dev.num_edges);
                 k_sec_scatter<<<sms * 8, 256, 0, stream>>>(ka);
                 if (lean) la::bwd_sec_shade(&scene->dev, &ka, grid_s, stream);

@@ -366,7 +366,7 @@ RB_D int sec_entry(const KernelArgs& ka, const SecRange& r, long long t) {
 __global__ void __launch_bounds__(RB_BLOCK_SEC, RB_MIN_BLOCKS_SEC) k_bwd_sec_pick(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
     const RenderParams& rp = ka.rp;
     const SecRange r = sec_range(ka);
-    const long long n = r.total;
+    const long long n = ka.hier_persistent ? (long long)r.pad : (long long)r.total; // (the hierarchy range has its own kernel)
     RB_BLOCK_LOOP(t, n) {
         RB_PHASE_SYNC();
         if (t < n) {
@@ -389,6 +389,86 @@ __global__ void __launch_bounds__(RB_BLOCK_SEC, RB_MIN_BLOCKS_SEC) k_bwd_sec_pic
                 if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&ka.edge_hist[key], (unsigned)__popc(peers));
             }
         }
+    }
+}
+// Stage 2a': the HIERARCHY part of the vertex list with persistent warps.  The 16 stochastic descents of a vertex visit between
+// ~20 and ~300 tree nodes, so in a plain "one vertex per lane" loop a warp waits for its longest walk (half of the lanes idle in the
+// node evaluation on the teapot, profiles/r02_teapot_*).  Here every lane owns a resumable walk (hier_begin / hier_step / hier_end,
+// rb_secondary.cuh); a warp advances all live walks a few steps at a time and, as soon as RB_REFILL_MIN lanes have ended theirs (or
+// nobody walks), finishes those picks together and refills the lanes from a global work counter.
+#ifndef RB_REFILL_MIN
+#define RB_REFILL_MIN 12
+#endif
+#ifndef RB_WALK_BURST
+#define RB_WALK_BURST 4
+#endif
+__global__ void __launch_bounds__(RB_BLOCK_SEC, RB_MIN_BLOCKS_SEC) k_bwd_sec_pick_hier(const __grid_constant__ DevScene sc, const __grid_constant__ KernelArgs ka) {
+    const RenderParams& rp = ka.rp;
+    const SecRange r = sec_range(ka);
+    const unsigned n_h = r.total - r.pad; // hierarchy slots are [pad, total)
+    unsigned* cursor = &ka.counters->hier_cursor;
+    const int lane = threadIdx.x & 31;
+    PickSetup ps;
+    HierWalk w;
+    w.sp = 0;
+    unsigned slot = 0;
+    int phase = 0; // 0 idle, 1 walking, 2 walk ended (pick to be finished), 3 no work left
+    bool exhausted = false; // (warp-uniform)
+    while (true) {
+        const unsigned walking = __ballot_sync(0xffffffffu, phase == 1);
+        const unsigned waiting = __ballot_sync(0xffffffffu, phase == 0 || phase == 2);
+        if (waiting && (__popc(waiting) >= RB_REFILL_MIN || walking == 0)) {
+            if (phase == 2) { // finish the pick of this lane's vertex
+                Real ew = 0;
+                int edge = hier_end(ps.c, w, ps.resample, ew);
+                EdgePick pk;
+                unsigned key = 0xffffffffu;
+                if (pick_finish_hier(sc, ps, edge, ew, pk)) {
+                    ka.picks[slot] = pk;
+                    key = (unsigned)pk.edge_id;
+                    unsigned peers = __match_any_sync(__activemask(), key);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&ka.edge_hist[key], (unsigned)__popc(peers));
+                }
+                ka.sec_keys[slot] = key;
+                phase = 0;
+            }
+            const unsigned want = __ballot_sync(0xffffffffu, phase == 0);
+            if (!exhausted && want) {
+                const int leader = __ffs(want) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(cursor, (unsigned)__popc(want));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                exhausted = base + (unsigned)__popc(want) >= n_h;
+                if (phase == 0) {
+                    unsigned k = base + (unsigned)__popc(want & ((1u << lane) - 1u));
+                    if (k < n_h) {
+                        slot = r.pad + k;
+                        int e = ka.vert_list[(unsigned)ka.vert_cap - 1u - k];
+                        int ts = e / ka.rec_per_sample, d = e - ts * ka.rec_per_sample;
+                        SampleId id = band_sample(rp, ka.band_i0 + ts);
+                        VertexRec cur = ka.records[e];
+                        ka.sec_vals[slot] = (unsigned)e;
+                        Sampler es = bwd_edge_sampler(sc, rp, id.pixel, id.s, d, 0);
+                        if (pick_setup(sc, cur, es, ps, nullptr, nullptr) && hier_begin(ps.c, ps.edge_sel, w)) phase = w.sp > 0 ? 1 : 2;
+                        else ka.sec_keys[slot] = 0xffffffffu; // (stays idle until the next refill)
+                    } else {
+                        phase = 3;
+                    }
+                }
+            } else if (exhausted && phase == 0) {
+                phase = 3;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, phase == 1) == 0) {
+            if (__ballot_sync(0xffffffffu, phase != 3) == 0) break;
+            continue;
+        }
+#pragma unroll 1
+        for (int it = 0; it < RB_WALK_BURST; it++)
+            if (phase == 1) {
+                hier_step(ps.c, w);
+                if (w.sp == 0) phase = 2;
+            }
     }
 }
 #ifndef RB_LEAN // the counting sort does not depend on scene features

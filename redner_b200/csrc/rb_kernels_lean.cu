@@ -54,6 +54,9 @@ void bwd_trace(const void* sc, const void* ka, int grid, cudaStream_t stream) {
 void bwd_sec_pick(const void* sc, const void* ka, int grid, cudaStream_t stream) {
     rb_lean::k_bwd_sec_pick<<<grid, RB_BLOCK_SEC, 0, stream>>>(*(const DevScene*)sc, *(const KernelArgs*)ka);
 }
+void bwd_sec_pick_hier(const void* sc, const void* ka, int grid, cudaStream_t stream) {
+    rb_lean::k_bwd_sec_pick_hier<<<grid, RB_BLOCK_SEC, 0, stream>>>(*(const DevScene*)sc, *(const KernelArgs*)ka);
+}
 void bwd_sec_shade(const void* sc, const void* ka, int grid, cudaStream_t stream) {
     rb_lean::k_bwd_sec_shade<<<grid, RB_BLOCK_SEC, 0, stream>>>(*(const DevScene*)sc, *(const KernelArgs*)ka);
 }

@@ -9,6 +9,7 @@ int grid(Kernel k, int device); // SMs x resident blocks per SM
 void forward(const void* sc, const void* ka, int grid, cudaStream_t stream);
 void bwd_trace(const void* sc, const void* ka, int grid, cudaStream_t stream);
 void bwd_sec_pick(const void* sc, const void* ka, int grid, cudaStream_t stream);
+void bwd_sec_pick_hier(const void* sc, const void* ka, int grid, cudaStream_t stream);
 void bwd_sec_shade(const void* sc, const void* ka, int grid, cudaStream_t stream);
 void bwd_sweep(const void* sc, const void* ka, int grid, cudaStream_t stream);
 void prim_keys(const void* sc, const void* ka, int dim_base, long long t0, int n, unsigned* keys, unsigned* vals, int grid, cudaStream_t stream);

@@ -20,6 +20,7 @@
 #endif
 struct BandCounters {
     unsigned n_paths, n_gather, n_hier, n_picked;
+    unsigned hier_cursor, pad0; // work counter of the persistent hierarchy kernel
     unsigned long long total_vertices, total_hits; // statistics (mean path length, primary-hit fraction)
 };
 struct KernelArgs {
@@ -46,6 +47,7 @@ struct KernelArgs {
     unsigned *sec_keys, *sec_vals; // [slot] picked edge (or 0xffffffff) / vert_list entry
     unsigned *edge_hist, *edge_offs, *edge_cursor; // [num_edges] counting sort of the picks by edge
     unsigned* sec_order;         // [picks] slots in edge order
+    int hier_persistent;         // the hierarchy part of the vertex list is served by k_bwd_sec_pick_hier
 };
 
 RB_HD int rb_channel_width(int ch, int max_generic) { // floats of one channel, src/channels.cpp:42-113

@@ -53,7 +53,7 @@ RB_HD M3 m3_inverse(const M3& m) {
 
 struct EdgeCtx { // per-vertex constants of the sampler
     const DevScene* sc;
-    SurfacePoint p;
+    V3 pos; // shading point
     M3 m, m_inv;
     M3 abs_m_inv; // |M^-1| element-wise (box transform)
     V3 cam_org;
@@ -64,8 +64,8 @@ struct EdgeCtx { // per-vertex constants of the sampler
 RB_HD void edge_ctx_finish(EdgeCtx& c) { // call after m_inv / cam_org / p are set
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) c.abs_m_inv.m[i][j] = fabs(c.m_inv.m[i][j]);
-    c.hough_center = Real(0.5) * (c.p.position - c.cam_org);
-    c.hough_r2 = rb_sq(Real(0.5) * length(c.p.position - c.cam_org));
+    c.hough_center = Real(0.5) * (c.pos - c.cam_org);
+    c.hough_r2 = rb_sq(Real(0.5) * length(c.pos - c.cam_org));
 }
 
 RB_HD Real min_abs_bound(Real lo, Real hi) {
@@ -91,8 +91,8 @@ RB_HD bool node_contains(const EdgeChild& n, V3 p) {
 //    (local == dir / |M dir|): one matrix product and one normalisation less.
 //  * Written without divergent branches: lanes of a warp walk different nodes, and "shading point inside the box" is a per-lane fact.
 RB_D Real ltc_bound(const EdgeChild& n, const EdgeCtx& c) {
-    const bool inside = node_contains(n, c.p.position);
-    V3 ctr = Real(0.5) * (mk3(n.pmin[0], n.pmin[1], n.pmin[2]) + mk3(n.pmax[0], n.pmax[1], n.pmax[2])) - c.p.position;
+    const bool inside = node_contains(n, c.pos);
+    V3 ctr = Real(0.5) * (mk3(n.pmin[0], n.pmin[1], n.pmin[2]) + mk3(n.pmax[0], n.pmax[1], n.pmax[2])) - c.pos;
     V3 ext = Real(0.5) * (mk3(n.pmax[0], n.pmax[1], n.pmax[2]) - mk3(n.pmin[0], n.pmin[1], n.pmin[2]));
     V3 q = mul(c.m_inv, ctr), r = mul(c.abs_m_inv, ext);
     V3 lo = q - r, hi = q + r;
@@ -119,12 +119,12 @@ RB_D Real node_importance(const EdgeChild& n, bool is6d, const EdgeCtx& c) {
     if (is6d && !hough_may_be_silhouette_at(n, c.hough_center, c.hough_r2)) return 0;
     Real brdf = ltc_bound(n, c);
     V3 center = Real(0.5) * (mk3(n.pmin[0], n.pmin[1], n.pmin[2]) + mk3(n.pmax[0], n.pmax[1], n.pmax[2]));
-    return brdf * n.wlen / rb_max(length(center - c.p.position), Real(1e-3));
+    return brdf * n.wlen / rb_max(length(center - c.pos), Real(1e-3));
 }
 // Integral of the transformed cosine along the (clipped) edge, src/edge.cpp:951-983
 RB_D Real edge_ltc_integral(V3 v0, V3 v1, const EdgeCtx& c) {
     if (!(length_sq(v1 - v0) > Real(1e-10))) return 0;
-    V3 a = mul(c.m_inv, v0 - c.p.position), b = mul(c.m_inv, v1 - c.p.position);
+    V3 a = mul(c.m_inv, v0 - c.pos), b = mul(c.m_inv, v1 - c.pos);
     if (!(a.z > 0 || b.z > 0)) return 0;
     if (a.z < 0) a = (a * b.z - b * a.z) / (b.z - a.z);
     if (b.z < 0) b = (a * b.z - b * a.z) / (b.z - a.z);
@@ -136,13 +136,13 @@ RB_D Real edge_ltc_integral(V3 v0, V3 v1, const EdgeCtx& c) {
     return rb_max(I(l1) - I(l0), Real(0));
 }
 RB_D Real leaf_importance_h(const Edge& e, const EdgeCtx& c) {
-    if (!edge_is_silhouette(c.sc->shapes, c.p.position, e)) return 0;
+    if (!edge_is_silhouette(c.sc->shapes, c.pos, e)) return 0;
     return edge_ltc_integral(edge_v0(c.sc->shapes, e), edge_v1(c.sc->shapes, e), c);
 }
 // gather variant: the edge must also be a silhouette seen from the light point and its "billboard" must be hit
 // by the shadow ray, src/edge.cpp:998-1067
 RB_D Real leaf_importance_l(const Edge& e, const EdgeCtx& c, const Ray& nee, Real billboard) {
-    if (!edge_is_silhouette(c.sc->shapes, c.p.position, e)) return 0;
+    if (!edge_is_silhouette(c.sc->shapes, c.pos, e)) return 0;
     V3 nee_pt = nee.org + nee.tmax * nee.dir;
     if (!edge_is_silhouette(c.sc->shapes, nee_pt, e)) return 0;
     V3 v0 = edge_v0(c.sc->shapes, e), v1 = edge_v1(c.sc->shapes, e);
@@ -195,61 +195,73 @@ RB_D void split_samples(int num, Real prob0, Real& u, int& n0, int& n1) {
         }
     }
 }
-// 16 correlated stochastic descents through both trees followed by reservoir resampling among the reached leaves.
-RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sample_weight) {
-    const DevScene& sc = *c.sc;
+// 16 correlated stochastic descents through both trees followed by reservoir resampling among the reached leaves, as three
+// resumable pieces: hier_begin, hier_step (ONE stack item per call) and hier_end.  sample_edge_hier runs them back to back; the
+// persistent kernel k_bwd_sec_pick_hier interleaves the steps of 32 vertices and refills lanes whose walk has ended.
+struct HierWalk {
     StackH stack[RB_EDGE_STACK_H];
-    int sp = 0;
-    int selected = -1;
-    Real edge_weight = 0, wsum = 0;
+    StackH leaves[RB_EDGE_H_SAMPLES];
+    int sp, nl;
+    Real u;
+};
+RB_D bool hier_begin(const EdgeCtx& c, Real u, HierWalk& w) {
+    const DevScene& sc = *c.sc;
+    w.sp = 0;
+    w.nl = 0;
     Real imp_cs = sc.edge_root_cs != RB_EDGE_EMPTY ? Real(1) : Real(0), imp_ncs = sc.edge_root_ncs != RB_EDGE_EMPTY ? Real(1) : Real(0);
-    if (imp_cs <= 0 && imp_ncs <= 0) return -1;
+    if (imp_cs <= 0 && imp_ncs <= 0) return false;
     Real prob_cs = imp_cs / (imp_cs + imp_ncs);
     int n_cs, n_ncs;
     split_samples(RB_EDGE_H_SAMPLES, prob_cs, u, n_cs, n_ncs);
-    if (n_cs > 0) { stack[sp].node = sc.edge_root_cs; stack[sp].num = (short)n_cs; stack[sp].is6d = 0; stack[sp].pmf = prob_cs; sp++; }
-    if (n_ncs > 0) { stack[sp].node = sc.edge_root_ncs; stack[sp].num = (short)n_ncs; stack[sp].is6d = 1; stack[sp].pmf = 1 - prob_cs; sp++; }
-    // Interior nodes first, leaves afterwards (in the order the descent reached them, so the reservoir below consumes
-    // `resample_u` exactly as a combined loop would): lanes of a warp would otherwise sit in the leaf branch (silhouette
-    // test + LTC line integral) and the interior branch (two box bounds) of the same loop at the same time.
-    StackH leaves[RB_EDGE_H_SAMPLES];
-    int nl = 0;
-    while (sp > 0) {
-        StackH it = stack[--sp];
-        if (it.node < 0) { // leaf: ~edge id
-            if (nl < RB_EDGE_H_SAMPLES) {
-                leaves[nl] = it;
-                leaves[nl].node = ~it.node;
-                nl++;
-            }
-        } else {
-            const EdgeNode n = sc.edge_nodes[it.node]; // one 128-byte fetch: both children's bounds and references
-            Real i0, i1;
-            if (parent_contains(n, c.p.position)) {
-                i0 = i1 = 1;
-            } else {
-                i0 = node_importance(n.c[0], it.is6d != 0, c);
-                i1 = node_importance(n.c[1], it.is6d != 0, c);
-            }
-            if (i0 > 0 || i1 > 0) {
-                Real p0 = i0 / (i0 + i1);
-                int n0, n1;
-                split_samples(it.num, p0, u, n0, n1);
-                if (n0 > 0 && sp < RB_EDGE_STACK_H) { stack[sp].node = n.c[0].ref; stack[sp].num = (short)n0; stack[sp].is6d = it.is6d; stack[sp].pmf = it.pmf * p0; sp++; }
-                if (n1 > 0 && sp < RB_EDGE_STACK_H) { stack[sp].node = n.c[1].ref; stack[sp].num = (short)n1; stack[sp].is6d = it.is6d; stack[sp].pmf = it.pmf * (1 - p0); sp++; }
-            }
+    if (n_cs > 0) { w.stack[w.sp].node = sc.edge_root_cs; w.stack[w.sp].num = (short)n_cs; w.stack[w.sp].is6d = 0; w.stack[w.sp].pmf = prob_cs; w.sp++; }
+    if (n_ncs > 0) { w.stack[w.sp].node = sc.edge_root_ncs; w.stack[w.sp].num = (short)n_ncs; w.stack[w.sp].is6d = 1; w.stack[w.sp].pmf = 1 - prob_cs; w.sp++; }
+    w.u = u;
+    return true;
+}
+// Interior nodes first, leaves afterwards (in the order the descent reached them, so the reservoir of hier_end consumes
+// `resample_u` exactly as a combined loop would): lanes of a warp would otherwise sit in the leaf branch (silhouette
+// test + LTC line integral) and the interior branch (two box bounds) of the same loop at the same time.
+RB_D void hier_step(const EdgeCtx& c, HierWalk& w) { // requires w.sp > 0
+    const DevScene& sc = *c.sc;
+    StackH it = w.stack[--w.sp];
+    if (it.node < 0) { // leaf: ~edge id
+        if (w.nl < RB_EDGE_H_SAMPLES) {
+            w.leaves[w.nl] = it;
+            w.leaves[w.nl].node = ~it.node;
+            w.nl++;
         }
+        return;
     }
-    for (int k = 0; k < nl; k++) {
-        const StackH it = leaves[k];
-        Real w = it.num * leaf_importance_h(sc.edges[it.node], c) / it.pmf;
-        if (w > 0) {
+    const EdgeNode n = sc.edge_nodes[it.node]; // one 128-byte fetch: both children's bounds and references
+    Real i0, i1;
+    if (parent_contains(n, c.pos)) {
+        i0 = i1 = 1;
+    } else {
+        i0 = node_importance(n.c[0], it.is6d != 0, c);
+        i1 = node_importance(n.c[1], it.is6d != 0, c);
+    }
+    if (i0 > 0 || i1 > 0) {
+        Real p0 = i0 / (i0 + i1);
+        int n0, n1;
+        split_samples(it.num, p0, w.u, n0, n1);
+        if (n0 > 0 && w.sp < RB_EDGE_STACK_H) { w.stack[w.sp].node = n.c[0].ref; w.stack[w.sp].num = (short)n0; w.stack[w.sp].is6d = it.is6d; w.stack[w.sp].pmf = it.pmf * p0; w.sp++; }
+        if (n1 > 0 && w.sp < RB_EDGE_STACK_H) { w.stack[w.sp].node = n.c[1].ref; w.stack[w.sp].num = (short)n1; w.stack[w.sp].is6d = it.is6d; w.stack[w.sp].pmf = it.pmf * (1 - p0); w.sp++; }
+    }
+}
+RB_D int hier_end(const EdgeCtx& c, const HierWalk& w, Real resample_u, Real& sample_weight) {
+    const DevScene& sc = *c.sc;
+    int selected = -1;
+    Real edge_weight = 0, wsum = 0;
+    for (int k = 0; k < w.nl; k++) {
+        const StackH it = w.leaves[k];
+        Real wt = it.num * leaf_importance_h(sc.edges[it.node], c) / it.pmf;
+        if (wt > 0) {
             Real prev = wsum;
-            wsum += w;
-            Real nw = w / wsum;
+            wsum += wt;
+            Real nw = wt / wsum;
             if (resample_u <= nw || prev == 0) {
                 selected = it.node;
-                edge_weight = w * it.pmf;
+                edge_weight = wt * it.pmf;
                 resample_u /= nw;
             } else {
                 resample_u = (resample_u - nw) / (1 - nw);
@@ -259,6 +271,12 @@ RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sampl
     if (edge_weight <= 0 || wsum <= 0) return -1;
     sample_weight = 1 / (edge_weight * RB_EDGE_H_SAMPLES / wsum);
     return selected;
+}
+RB_D int sample_edge_hier(const EdgeCtx& c, Real u, Real resample_u, Real& sample_weight) {
+    HierWalk w;
+    if (!hier_begin(c, u, w)) return -1;
+    while (w.sp > 0) hier_step(c, w);
+    return hier_end(c, w, resample_u, sample_weight);
 }
 // Gather all silhouette edges whose billboard the shadow ray crosses and pick one by reservoir resampling.
 RB_D int sample_edge_gather(const EdgeCtx& c, const Ray& nee, const Isect& lis, const SurfacePoint& lp, Real resample_u, Real& sample_weight,
@@ -352,8 +370,17 @@ struct alignas(16) EdgePick {
     float w;   // edge_weight / strategy pmf
     V3 sample_p, mwt;
 };
-// `smp` is the edge sampler positioned at this depth's first dimension (4 dimensions are consumed here).
-RB_D bool secondary_edge_pick(const DevScene& sc, const VertexRec& cur, Sampler& smp, EdgePick& pk) {
+// The pick in three pieces -- pick_setup (frame, lobe, LTC matrices, strategy), the edge choice (hierarchy walk or gather), and
+// pick_finish_hier (point on the chosen edge by inverting the LTC line CDF) -- so that the persistent hierarchy kernel can interleave
+// the walks of many vertices; secondary_edge_pick runs them back to back.
+struct PickSetup {
+    EdgeCtx c;
+    Real m_pmf, nee_pmf, edge_sel, resample, t_sel;
+    int flags; // bit 0: diffuse lobe, bit 1: gather strategy, bit 2: diffuse or glossy
+};
+// `smp` is the edge sampler positioned at this depth's first dimension (4 dimensions are consumed here).  `nee` / `lp` (may be null)
+// receive the vertex's shadow ray and light point, which only the gather strategy needs.
+RB_D bool pick_setup(const DevScene& sc, const VertexRec& cur, Sampler& smp, PickSetup& ps, Ray* nee_out, SurfacePoint* lp_out) {
     double s_edge_sel = smp.next(), s_resample = smp.next(), s_component = smp.next(), s_t = smp.next();
     Real min_rough = cur.min_rough;
     // secondary edges are only sampled until the first rough bounce (src/edge.cpp:1396-1401)
@@ -363,38 +390,38 @@ RB_D bool secondary_edge_pick(const DevScene& sc, const VertexRec& cur, Sampler&
     RayDiff rd;
     SurfacePoint sp = make_surface_point(shape, cur.isect.tri_id, cur.ray, cur.rd_in, rd);
     V3 wi = -cur.ray.dir;
-    // shadow ray of this vertex with its true length (src/edge.cpp:1377-1385)
-    const rb_shape& lshape = sc.shapes[cur.light.isect.shape_id];
-    SurfacePoint lp = sample_light_triangle(lshape, cur.light.isect.tri_id, cur.light.uv);
-    Ray nee;
-    nee.org = sp.position;
-    nee.dir = normalize(lp.position - sp.position);
-    nee.tmin = Real(1e-3);
-    nee.tmax = length(lp.position - sp.position);
-
+    if (nee_out != nullptr) {
+        // shadow ray of this vertex with its true length (src/edge.cpp:1377-1385)
+        const rb_shape& lshape = sc.shapes[cur.light.isect.shape_id];
+        SurfacePoint lp = sample_light_triangle(lshape, cur.light.isect.tri_id, cur.light.uv);
+        nee_out->org = sp.position;
+        nee_out->dir = normalize(lp.position - sp.position);
+        nee_out->tmin = Real(1e-3);
+        nee_out->tmax = length(lp.position - sp.position);
+        *lp_out = lp;
+    }
     V3 kd = mat_diffuse(mat, sp), ks = mat_specular(mat, sp);
     Real wd = luminance(kd), ws = luminance(ks), wsum = wd + ws;
     if (wsum <= 0) return false;
-    Real pd = wd / wsum, ps = ws / wsum;
+    Real pd = wd / wsum, pspec = ws / wsum;
     V3 n = sp.shading_frame.n;
     if (mat.two_sided && dot(wi, n) < 0) n = -n;
     V3 fx = normalize(wi - n * dot(wi, n));
     V3 fy = cross(n, fx);
     if (dot(wi, n) > 1 - Real(1e-6)) coordinate_system(n, fx, fy);
-    EdgeCtx c;
+    EdgeCtx& c = ps.c;
     c.sc = &sc;
-    c.p = sp;
+    c.pos = sp.position;
     {
         double iw = 1.0 / sc.cam.c2w[15];
         c.cam_org = mk3((Real)(sc.cam.c2w[3] * iw), (Real)(sc.cam.c2w[7] * iw), (Real)(sc.cam.c2w[11] * iw));
     }
     Real roughness = rb_max(mat_roughness(mat, sp), min_rough);
-    Real m_pmf;
     bool diffuse_lobe = s_component <= (double)pd;
     if (diffuse_lobe) {
         c.m_inv = m3_rows(fx, fy, n);
         c.m = m3_inverse(c.m_inv);
-        m_pmf = pd;
+        ps.m_pmf = pd;
     } else {
         // LTC fitted to the Blinn-Phong lobe, src/edge.cpp:803-814
         Real theta = acos(dot(wi, sp.shading_frame.n));
@@ -406,15 +433,14 @@ RB_D bool secondary_edge_pick(const DevScene& sc, const VertexRec& cur, Sampler&
             for (int j = 0; j < 3; j++) ltc.m[i][j] = t[3 * i + j];
         c.m_inv = m3_mul(m3_inverse(ltc), m3_rows(fx, fy, n));
         c.m = m3_inverse(c.m_inv);
-        m_pmf = ps;
+        ps.m_pmf = pspec;
     }
     edge_ctx_finish(c);
-    int edge_id = -1;
-    Real edge_weight = 0;
-    V3 sample_p = zero3(), mwt = zero3();
-    Real edge_sel = (Real)s_edge_sel;
+    ps.edge_sel = (Real)s_edge_sel;
+    ps.resample = (Real)s_resample;
+    ps.t_sel = (Real)s_t;
     bool use_nee = false;
-    Real nee_pmf = 1;
+    ps.nee_pmf = 1;
     bool diffuse_or_glossy = diffuse_lobe || roughness > Real(0.1);
     if (diffuse_or_glossy) {
         // The strategy coin is the reference's: the upper half of `edge_sel` goes to the hierarchy (rescaled), the lower half
@@ -425,57 +451,75 @@ RB_D bool secondary_edge_pick(const DevScene& sc, const VertexRec& cur, Sampler&
         // off by 22 % with an independent coin, 0.6 standard errors with this one).  It also makes the pick a pure function of
         // (pixel, sample, depth), independent of bands, stripes and block size.
         use_nee = s_edge_sel < 0.5;
-        if (!use_nee) edge_sel = (Real)((s_edge_sel - 0.5) * 2);
-        if (roughness > Real(0.1)) nee_pmf = Real(0.5);
-        else nee_pmf = use_nee ? pd * Real(0.5) : 1 - pd * Real(0.5);
+        if (!use_nee) ps.edge_sel = (Real)((s_edge_sel - 0.5) * 2);
+        if (roughness > Real(0.1)) ps.nee_pmf = Real(0.5);
+        else ps.nee_pmf = use_nee ? pd * Real(0.5) : 1 - pd * Real(0.5);
     }
-    if (!use_nee) {
-        edge_id = sample_edge_hier(c, edge_sel, (Real)s_resample, edge_weight);
-        if (edge_id == -1 || edge_weight <= 0) return false;
-        const Edge& e = sc.edges[edge_id];
-        if (!edge_is_silhouette(sc.shapes, sp.position, e)) return false;
-        V3 a = mul(c.m_inv, edge_v0(sc.shapes, e) - sp.position), b = mul(c.m_inv, edge_v1(sc.shapes, e) - sp.position);
-        if (a.z <= 0 && b.z <= 0) return false;
-        if (a.z < 0) a = (a * b.z - b * a.z) / (b.z - a.z);
-        if (b.z < 0) b = (a * b.z - b * a.z) / (b.z - a.z);
-        V3 wt = normalize(b - a);
-        Real l0 = dot(a, wt), l1 = dot(b, wt);
-        V3 vo = a - l0 * wt;
-        Real d = length(vo);
-        auto I = [&](Real l) { return (l / (d * (d * d + l * l)) + atan(l / d) / (d * d)) * vo.z + (l * l / (d * (d * d + l * l))) * wt.z; };
-        Real Il0 = I(l0), Il1 = I(l1);
-        Real norm = Il1 - Il0;
-        auto line_pdf = [&](Real l) {
-            Real ds2 = d * d + l * l;
-            return 2 * d * (vo + l * wt).z / (norm * ds2 * ds2);
-        };
-        // invert the line CDF by bisection-safeguarded Newton, src/edge.cpp:1618-1643
-        Real lb = l0, ub = l1;
-        if (lb > ub) {
-            Real tmp = lb;
-            lb = ub;
-            ub = tmp;
-        }
-        Real l = Real(0.5) * (lb + ub);
-        for (int it = 0; it < 20; it++) {
-            if (!(l >= lb && l <= ub)) l = Real(0.5) * (lb + ub);
-            Real value = (I(l) - Il0) / norm - (Real)s_t;
-            if (fabs(value) < Real(1e-5) || it == 19) break;
-            if (value > 0) ub = l; else lb = l;
-            l -= value / line_pdf(l);
-        }
-        Real lpdf = line_pdf(l);
-        if (!(lpdf > 0)) return false;
-        sample_p = mul(c.m, vo + l * wt);
-        edge_weight /= (m_pmf * lpdf);
-        mwt = mul(c.m, wt);
-    } else {
-        edge_id = sample_edge_gather(c, nee, cur.light.isect, lp, (Real)s_resample, edge_weight, sample_p, mwt);
-        if (edge_id == -1 || edge_weight <= 0) return false;
+    ps.flags = (diffuse_lobe ? 1 : 0) | (use_nee ? 2 : 0) | (diffuse_or_glossy ? 4 : 0);
+    return true;
+}
+// Point on the edge the hierarchy chose: invert the CDF of the transformed cosine along the (clipped) edge.
+RB_D bool pick_finish_hier(const DevScene& sc, const PickSetup& ps, int edge_id, Real edge_weight, EdgePick& pk) {
+    const EdgeCtx& c = ps.c;
+    if (edge_id == -1 || edge_weight <= 0) return false;
+    const Edge& e = sc.edges[edge_id];
+    if (!edge_is_silhouette(sc.shapes, c.pos, e)) return false;
+    V3 a = mul(c.m_inv, edge_v0(sc.shapes, e) - c.pos), b = mul(c.m_inv, edge_v1(sc.shapes, e) - c.pos);
+    if (a.z <= 0 && b.z <= 0) return false;
+    if (a.z < 0) a = (a * b.z - b * a.z) / (b.z - a.z);
+    if (b.z < 0) b = (a * b.z - b * a.z) / (b.z - a.z);
+    V3 wt = normalize(b - a);
+    Real l0 = dot(a, wt), l1 = dot(b, wt);
+    V3 vo = a - l0 * wt;
+    Real d = length(vo);
+    auto I = [&](Real l) { return (l / (d * (d * d + l * l)) + atan(l / d) / (d * d)) * vo.z + (l * l / (d * (d * d + l * l))) * wt.z; };
+    Real Il0 = I(l0), Il1 = I(l1);
+    Real norm = Il1 - Il0;
+    auto line_pdf = [&](Real l) {
+        Real ds2 = d * d + l * l;
+        return 2 * d * (vo + l * wt).z / (norm * ds2 * ds2);
+    };
+    // invert the line CDF by bisection-safeguarded Newton, src/edge.cpp:1618-1643
+    Real lb = l0, ub = l1;
+    if (lb > ub) {
+        Real tmp = lb;
+        lb = ub;
+        ub = tmp;
     }
+    Real l = Real(0.5) * (lb + ub);
+    for (int it = 0; it < 20; it++) {
+        if (!(l >= lb && l <= ub)) l = Real(0.5) * (lb + ub);
+        Real value = (I(l) - Il0) / norm - ps.t_sel;
+        if (fabs(value) < Real(1e-5) || it == 19) break;
+        if (value > 0) ub = l; else lb = l;
+        l -= value / line_pdf(l);
+    }
+    Real lpdf = line_pdf(l);
+    if (!(lpdf > 0)) return false;
     pk.edge_id = edge_id;
-    pk.flags = (diffuse_lobe ? 1 : 0) | (use_nee ? 2 : 0) | (diffuse_or_glossy ? 4 : 0);
-    pk.w = (float)(edge_weight / nee_pmf);
+    pk.flags = ps.flags;
+    pk.w = (float)(edge_weight / (ps.m_pmf * lpdf) / ps.nee_pmf);
+    pk.sample_p = mul(c.m, vo + l * wt);
+    pk.mwt = mul(c.m, wt);
+    return true;
+}
+RB_D bool secondary_edge_pick(const DevScene& sc, const VertexRec& cur, Sampler& smp, EdgePick& pk) {
+    PickSetup ps;
+    Ray nee;
+    SurfacePoint lp;
+    if (!pick_setup(sc, cur, smp, ps, &nee, &lp)) return false;
+    if (!(ps.flags & 2)) {
+        Real edge_weight = 0;
+        int edge_id = sample_edge_hier(ps.c, ps.edge_sel, ps.resample, edge_weight);
+        return pick_finish_hier(sc, ps, edge_id, edge_weight, pk);
+    }
+    Real edge_weight = 0;
+    V3 sample_p = zero3(), mwt = zero3();
+    int edge_id = sample_edge_gather(ps.c, nee, cur.light.isect, lp, ps.resample, edge_weight, sample_p, mwt);
+    if (edge_id == -1 || edge_weight <= 0) return false;
+    pk.edge_id = edge_id;
+    pk.flags = ps.flags;
+    pk.w = (float)(edge_weight / ps.nee_pmf);
     pk.sample_p = sample_p;
     pk.mwt = mwt;
     return true;

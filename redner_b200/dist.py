@@ -88,7 +88,7 @@ class TileRenderFunction(torch.autograd.Function):
         return (None, None, None) + tuple(out[1:])
 
 
-def render_tiles(scene, num_samples, max_bounces, seed, group=None, rows_per_stripe: int = 16, **kw):
+def render_tiles(scene, num_samples, max_bounces, seed, group=None, rows_per_stripe: int = 4, **kw):
     args = api.RenderFunction.serialize_scene(scene, num_samples, max_bounces, **kw)
     return TileRenderFunction.apply(seed, group, rows_per_stripe, *args)
 
