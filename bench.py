@@ -556,7 +556,7 @@ def run_reference(args, rank, world):
     probe = best_thread_count(args.workload, cores)
     th = max(probe, key=probe.get)
     n = max(1, args.steps + args.warmup)
-    budget = max(2.0, 240.0 / n)  # the whole --steps K --warmup W run stays within a few minutes
+    budget = max(2.0, float(os.environ.get("RB_REF_TOTAL_S", "240")) / n)  # the whole --steps K --warmup W run stays within a few minutes
     res, spp = pick_sample(wl, probe[th], budget)
     same = (res, spp) == (wl["res"], wl["spp"])
     ts = reference_steps(args.workload, res, spp, n, threads=th)[args.warmup:]

@@ -173,6 +173,10 @@ typedef struct rb_scene rb_scene;
  * src/scene.cpp:78-155), the light PMF/CDF and per-light area CDFs (src/scene.cpp:197-253), the edge list and
  * primary-edge distribution (src/edge.cpp:233-383). */
 int rb_scene_create(const rb_scene_desc* desc, rb_scene** out);
+/* The same on a caller-chosen CUDA stream (a cudaStream_t; NULL == legacy default stream, which is what rb_scene_create uses): uploads,
+ * mesh read-back and build kernels are ordered after the work already queued on that stream -- pass the stream the geometry tensors
+ * were produced on.  rb_scene_set_camera and rb_scene_destroy keep using it. */
+int rb_scene_create_on_stream(const rb_scene_desc* desc, rb_scene** out, void* stream);
 void rb_scene_destroy(rb_scene* scene);
 /* Scene::max_generic_texture_dimension (src/scene.cpp:293-300, bound at src/redner.cpp:72) */
 int rb_scene_max_generic_texture_dimension(const rb_scene* scene);

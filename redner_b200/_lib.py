@@ -109,7 +109,7 @@ class rb_dscene_desc(C.Structure):
 
 
 EXPORTS = [
-    "rb_scene_create", "rb_scene_destroy", "rb_scene_max_generic_texture_dimension", "rb_compute_num_channels", "rb_render",
+    "rb_scene_create", "rb_scene_create_on_stream", "rb_scene_destroy", "rb_scene_max_generic_texture_dimension", "rb_compute_num_channels", "rb_render",
     "rb_scene_set_partition", "rb_scene_last_stats", "rb_scene_last_stage_stats", "rb_scene_last_backward_stats", "rb_release_scratch", "rb_scene_build_ms", "rb_scene_edge_trees", "rb_scene_set_camera", "rb_render_batch", "rb_last_error", "rb_version",
 ]
 
@@ -117,6 +117,9 @@ EXPORTS = [
 def _bind(lib):
     lib.rb_scene_create.argtypes = [C.POINTER(rb_scene_desc), C.POINTER(C.c_void_p)]
     lib.rb_scene_create.restype = C.c_int
+    if hasattr(lib, "rb_scene_create_on_stream"):
+        lib.rb_scene_create_on_stream.argtypes = [C.POINTER(rb_scene_desc), C.POINTER(C.c_void_p), C.c_void_p]
+        lib.rb_scene_create_on_stream.restype = C.c_int
     lib.rb_scene_destroy.argtypes = [C.c_void_p]
     lib.rb_scene_destroy.restype = None
     lib.rb_scene_max_generic_texture_dimension.argtypes = [C.c_void_p]

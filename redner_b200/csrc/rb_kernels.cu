@@ -321,7 +321,11 @@ std::vector<cudaEvent_t>& ev = events.ev;
         ka.edge_hist = (unsigned*)(scratch + o_hist);
         ka.edge_offs = (unsigned*)(scratch + o_eoffs);
         ka.edge_cursor = (unsigned*)(scratch + o_ecur);
-        ka.hier_persistent = getenv("RB_NO_PERSISTENT_PICK") == nullptr ? 1 : 0; // (test / measurement hook)
+        // Persistent-warp hierarchy pick (k_bwd_sec_pick_hier: resumable walks, finished lanes refilled from a work counter): identical
+        // picks, but measured SLOWER than the plain kernel (boundary stage C2 4.5 -> 5.3 ms, teapot 44.2 -> 47.6 ms,
+        // profiles/r02_persistent_pick_ab.txt): the stage waits on dependent loads, not on issue slots, so idle lanes cost nothing
+        // and the refill logic is pure overhead.  Opt-in for measurements.
+        ka.hier_persistent = getenv("RB_PERSISTENT_PICK") != nullptr ? 1 : 0;
         int grid_t, grid_p, grid_s, grid_w;
         if (lean) {
             grid_t = la::grid(la::K_BWD_TRACE, scene->device);

@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(RB_BLOCK_SEC, RB_MIN_BLOCKS_SEC) k_bwd_sec_pic
 // node evaluation on the teapot, profiles/r02_teapot_*).  Here every lane owns a resumable walk (hier_begin / hier_step / hier_end,
 // rb_secondary.cuh); a warp advances all live walks a few steps at a time and, as soon as RB_REFILL_MIN lanes have ended theirs (or
 // nobody walks), finishes those picks together and refills the lanes from a global work counter.
+// MEASURED SLOWER than the plain kernel (rb_kernels.cu, RB_PERSISTENT_PICK): kept as an opt-in experiment.
 #ifndef RB_REFILL_MIN
 #define RB_REFILL_MIN 12
 #endif

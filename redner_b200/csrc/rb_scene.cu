@@ -417,7 +417,10 @@ static int get_tables(int device, DeviceTables& out) {
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
-extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
+extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) { return rb_scene_create_on_stream(desc, out, nullptr); }
+// Uploads, the device->host mesh mirror and the build kernels run on `stream_` (the stream the caller's geometry tensors were produced
+// on: work queued there is ordered before the build; with the legacy default stream a non-blocking side stream would not be).
+extern "C" int rb_scene_create_on_stream(const rb_scene_desc* desc, rb_scene** out, void* stream_) {
     if (!desc || !out) {
         rb_set_error("rb_scene_create: null argument");
         return 1;
@@ -455,7 +458,8 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
     rb_scene* sc = new rb_scene();
     sc->device = device;
     sc->cam = c;
-    cudaStream_t stream = 0;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    sc->stream = stream;
     auto fail = [&]() {
         rb_scene_destroy(sc);
         cudaSetDevice(prev);
@@ -562,7 +566,7 @@ extern "C" void rb_scene_destroy(rb_scene* sc) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(sc->device);
-    for (void* p : sc->allocs) cudaFreeAsync(p, 0);
+    for (void* p : sc->allocs) cudaFreeAsync(p, sc->stream);
     sc->events.destroy();
     cudaSetDevice(prev);
     delete sc;
@@ -606,7 +610,7 @@ extern "C" int rb_scene_set_camera(rb_scene* sc, const rb_camera* cam) {
     }
     sc->cam = *cam;
     host_setup_camera(*cam, sc->dev.cam);
-    cudaStream_t stream = 0;
+    cudaStream_t stream = sc->stream;
     int rc = 0;
     if (sc->dev.num_edges > 0) {
         if (sc->dev.use_primary_edge) rc = rb_build_primary_edge_cdf_gpu(sc, stream);

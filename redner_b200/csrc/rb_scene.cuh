@@ -28,6 +28,7 @@ struct EventPool {
 
 struct rb_scene {
     int device = 0;
+    cudaStream_t stream = 0; // stream of rb_scene_create_on_stream: builds, rb_scene_set_camera and the frees of rb_scene_destroy
     EventPool events;
     DevScene dev;   // passed by value to kernels
     rb_camera cam;  // host copy of the descriptor camera

@@ -333,7 +333,19 @@ class Scene:  # src/redner.cpp:62-73, src/scene.cpp:63-307
             use_secondary_edge_sampling = False
         d.use_secondary_edge_sampling = int(bool(use_secondary_edge_sampling))
         h = C.c_void_p()
-        if lib.rb_scene_create(C.byref(d), C.byref(h)) != 0:
+        # build on the current PyTorch stream of the scene's device: the geometry tensors were produced there
+        stream = 0
+        try:
+            import torch
+            if use_gpu and torch.cuda.is_available():
+                stream = torch.cuda.current_stream(gpu_index if gpu_index >= 0 else None).cuda_stream
+        except ImportError:
+            pass
+        if hasattr(lib, "rb_scene_create_on_stream"):
+            rc = lib.rb_scene_create_on_stream(C.byref(d), C.byref(h), C.c_void_p(stream or 0))
+        else:
+            rc = lib.rb_scene_create(C.byref(d), C.byref(h))
+        if rc != 0:
             raise RuntimeError("redner.Scene: " + L.last_error(lib))
         self._handle = h
         self.max_generic_texture_dimension = lib.rb_scene_max_generic_texture_dimension(h)

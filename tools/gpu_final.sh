@@ -1,23 +1,11 @@
 #!/usr/bin/env bash
-# End-of-round evidence on one GPU box: parity suite, smoke, both bench arms, ncu launch list of the bench command,
-# per-kernel metrics of exactly one step, and ONE full ncu capture of the kernel given as $1 (default k_primary_edge).
+# round-end evidence on one box: GPU suite, per-kernel ncu tables of one step (C2 and teapot), one full capture each, bench lines
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-K=${1:-k_primary_edge}
-nvidia-smi -L
-echo "=== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-echo "=== bench ours"; timeout 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_ours.json | cut -c1-300
-echo "=== bench reference"; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_ref.json | cut -c1-400
-echo "=== ncu launch list of the bench command"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-echo "=== one profiled step"
-timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,sm__icc_request_hit_rate.pct,gcc__average_cache_request_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread \
-    --clock-control none --csv --log-file gpurun_out/step_kernels.csv python tools/one_step.py > gpurun_out/one_step.log 2>&1
-python tools/summarize_step.py gpurun_out/step_kernels.csv gpurun_out/dram_traffic.json | head -16
-echo "=== ncu full $K"
-rm -f gpurun_out/*.ncu-rep
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -o gpurun_out/prof_$K -f \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-du -sh gpurun_out
+echo "=== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/pytest_full.log; tail -4 gpurun_out/pytest_full.log | cut -c1-200
+echo "=== bench c2"; timeout 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_ours_n1_c2.json | cut -c1-400
+echo "=== bench c3"; timeout 900 python bench.py --steps 3 --warmup 3 --workload c3 2>&1 | tail -1 | tee gpurun_out/bench_ours_n1_c3.json | cut -c1-300
+echo "=== bench c4"; timeout 900 python bench.py --steps 3 --warmup 3 --workload c4 2>&1 | tail -1 | tee gpurun_out/bench_ours_n1_c4.json | cut -c1-300
+echo "=== bench reference arm (short)"; RB_REF_TOTAL_S=40 timeout 900 python bench.py --impl reference --steps 1 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_reference_n1_c2.json | cut -c1-900
+echo "=== ncu C2"; bash tools/gpu_prof_scene.sh r02_c2 shadow_blocker 512 64 1 3 k_primary_edge 2>&1 | grep -v "^at::\|^cub::\|^void at" | cut -c1-330 | head -40
+echo "=== ncu teapot"; bash tools/gpu_prof_scene.sh r02_teapot teapot 256 32 2 3 k_bwd_sec_pick 2>&1 | grep -v "^at::\|^cub::\|^void at" | cut -c1-330 | head -40

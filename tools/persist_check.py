@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Persistent-warp hierarchy pick vs the plain pick kernel (RB_NO_PERSISTENT_PICK=1): same gradients up to the order of the atomics,
+"""Persistent-warp hierarchy pick vs the plain pick kernel (default; RB_PERSISTENT_PICK=1 selects the persistent kernel): same gradients up to the order of the atomics,
 and the stage times of both on one box."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,7 +20,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "worker":
     sys.exit(0)
 import numpy as np
 res = {}
-for tag, env in (("persistent", {}), ("plain", {"RB_NO_PERSISTENT_PICK": "1"})):
+for tag, env in (("persistent", {"RB_PERSISTENT_PICK": "1"}), ("plain", {})):
     path = "/tmp/persist_%s.npz" % tag
     subprocess.run([sys.executable, __file__, "worker", path], check=True, env=dict(os.environ, **env), timeout=600)
     res[tag] = dict(np.load(path))
