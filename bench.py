@@ -556,7 +556,7 @@ def run_reference(args, rank, world):
     probe = best_thread_count(args.workload, cores)
     th = max(probe, key=probe.get)
     n = max(1, args.steps + args.warmup)
-    budget = max(2.0, float(os.environ.get("RB_REF_TOTAL_S", "240")) / n)  # the whole --steps K --warmup W run stays within a few minutes
+    budget = max(2.0, float(os.environ.get("RB_REF_TOTAL_S", "180")) / n)  # the whole --steps K --warmup W run stays within a few minutes
     res, spp = pick_sample(wl, probe[th], budget)
     same = (res, spp) == (wl["res"], wl["spp"])
     ts = reference_steps(args.workload, res, spp, n, threads=th)[args.warmup:]
@@ -565,7 +565,7 @@ def run_reference(args, rank, world):
     v = res * res * spp / (f + b) / 1e6
     # one step of the FULL configuration next to the bounded sample, when the sample's rate says it fits in ~2 minutes
     full = None
-    if not same and wl["res"] * wl["res"] * wl["spp"] / (v * 1e6) <= 120.0:
+    if not same and wl["res"] * wl["res"] * wl["spp"] / (v * 1e6) <= float(os.environ.get("RB_REF_FULL_STEP_MAX_S", "100")):
         try:
             (ff, fb), = reference_steps(args.workload, wl["res"], wl["spp"], 1, threads=th)
             full = {"fwd_s": ff, "bwd_s": fb, "value": wl["res"] * wl["res"] * wl["spp"] / (ff + fb) / 1e6, "unit": "Msamples/s", "threads": th}

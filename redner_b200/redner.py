@@ -9,6 +9,7 @@ To run an unmodified pyredner on top of the B200 kernels, put `redner_b200/dropi
 Error behaviour: where the reference assert()s / exit(1)s, this module raises RuntimeError carrying rb_last_error().
 """
 import ctypes as C
+import os
 import enum
 
 from . import _lib as L
@@ -326,10 +327,17 @@ class Scene:  # src/redner.cpp:62-73, src/scene.cpp:63-307
         d.use_primary_edge_sampling = int(bool(use_primary_edge_sampling))
         if envmap is not None and use_secondary_edge_sampling:
             # The C ABI rejects this combination (the reference differentiates sky-side edge rays at stale hit points, DESIGN.md
-            # section 7).  pyredner switches both edge samplers on by default, so the shim degrades loudly instead of failing.
+            # section 7).  pyredner switches both edge samplers on by default, so an environment-lit scene arrives here with the flag
+            # set: fail loudly unless the caller accepts the difference (RB_ENVMAP_WITHOUT_SECONDARY_EDGES=1, or pass
+            # use_secondary_edge_sampling=False), in which case the scene is rendered WITHOUT shadow / interreflection boundary terms.
+            if os.environ.get("RB_ENVMAP_WITHOUT_SECONDARY_EDGES", "") in ("", "0"):
+                raise RuntimeError("redner_b200: secondary edge sampling together with an environment map is not available (DESIGN.md section 7). "
+                                   "Pass use_secondary_edge_sampling=False, or set RB_ENVMAP_WITHOUT_SECONDARY_EDGES=1 to have it switched off "
+                                   "automatically: such scenes then lose their secondary (shadow / interreflection) boundary gradients compared "
+                                   "with the reference.")
             import warnings
-            warnings.warn("redner_b200: secondary edge sampling is switched off for this scene (environment map); interior terms and "
-                          "primary edges are rendered and differentiated")
+            warnings.warn("redner_b200: secondary edge sampling is switched off for this scene (environment map, "
+                          "RB_ENVMAP_WITHOUT_SECONDARY_EDGES=1); interior terms and primary edges are rendered and differentiated")
             use_secondary_edge_sampling = False
         d.use_secondary_edge_sampling = int(bool(use_secondary_edge_sampling))
         h = C.c_void_p()
