@@ -120,6 +120,9 @@ RB_BVH_FN BvhHit bvh_trace_impl(const float4* __restrict__ nodes4, const float4*
                 int first = left, second = right;
                 if (tr < tl) { first = right; second = left; }
                 if (sp < RB_BVH_STACK) stack[sp++] = second;
+#ifdef RB_BVH_PREFETCH
+                if (second >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes4 + 4 * (size_t)second));
+#endif
                 node = first;
                 continue;
             } else if (hl) {
