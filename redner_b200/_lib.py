@@ -146,6 +146,7 @@ def _bind(lib):
     if hasattr(lib, "rb_scene_set_camera"):
         lib.rb_scene_set_camera.argtypes = [C.c_void_p, C.POINTER(rb_camera)]
         lib.rb_scene_set_camera.restype = C.c_int
+    if hasattr(lib, "rb_render_batch"):
         lib.rb_render_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(rb_camera), C.POINTER(rb_options), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.POINTER(C.POINTER(rb_dscene_desc)), C.c_void_p]
         lib.rb_render_batch.restype = C.c_int

@@ -77,6 +77,12 @@ def test_device_headers_meet_the_boundary_term_statistics(emulator):
     _check(emulator, list(pu.STAT_CASES))
 
 
+def test_batch_of_views_through_one_native_scene(emulator):
+    """api.render_batch / rb_scene_set_camera: host logic of the batch path (views share geometry, per view only the camera-dependent
+    tables are rebuilt), checked against one full Scene per view; the GPU twin is tests/test_scene_build_gpu.py."""
+    _check(emulator, ["batch_of_views"])
+
+
 def test_lean_instantiation_meets_the_goldens_it_serves(emulator_lean):
     names = [n for n, c in pu.CASES.items() if "channels" not in c and c["scene"] in ("single_triangle", "shadow_blocker", "glossy_room", "nmap_room")]
     assert len(names) >= 7

@@ -190,6 +190,33 @@ extern "C" int rb_scene_create(const rb_scene_desc* desc, rb_scene** out) {
     *out = sc;
     return 0;
 }
+// Re-target at another camera: the camera-dependent tables (primary-edge distribution, both edge trees) are rebuilt with the host
+// builders; geometry, BVH, lights and the edge list are kept (mirrors rb_scene_set_camera of the product, which rebuilds them on the GPU).
+extern "C" int rb_scene_set_camera(rb_scene* sc, const rb_camera* cam) {
+    DevScene& d = sc->dev;
+    sc->cam = *cam;
+    host_setup_camera(*cam, d.cam);
+    if (d.num_edges > 0) {
+        std::vector<HostMesh> meshes(d.num_shapes);
+        for (int s = 0; s < d.num_shapes; s++) {
+            meshes[s].vertices.assign(sc->shapes[s].vertices, sc->shapes[s].vertices + 3 * (size_t)sc->shapes[s].num_vertices);
+            meshes[s].indices.assign(sc->shapes[s].indices, sc->shapes[s].indices + 3 * (size_t)sc->shapes[s].num_triangles);
+        }
+        if (d.use_primary_edge) {
+            host_primary_edge_distribution(sc->shapes, meshes, d.cam, sc->et);
+            d.prim_edge_pmf = sc->et.prim_pmf.data();
+            d.prim_edge_cdf = sc->et.prim_cdf.data();
+        }
+        if (d.use_secondary_edge) {
+            host_build_edge_tree(sc->shapes, meshes, sc->et.edges, d.cam, sc->tree);
+            d.edge_nodes = sc->tree.nodes.data();
+            d.edge_root_cs = sc->tree.root_cs;
+            d.edge_root_ncs = sc->tree.root_ncs;
+            d.edge_bounds_expand = sc->tree.expand;
+        }
+    }
+    return 0;
+}
 extern "C" void rb_scene_destroy(rb_scene* sc) { delete sc; }
 extern "C" int rb_scene_max_generic_texture_dimension(const rb_scene* sc) { return sc->max_generic; }
 extern "C" int rb_compute_num_channels(const int* ch, int n, int mg) { return host_compute_num_channels(ch, n, mg); }
