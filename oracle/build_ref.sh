@@ -33,8 +33,9 @@ CXXFLAGS="-std=c++14 -O3 -fPIC -fvisibility=hidden -w -DTHRUST_DEVICE_SYSTEM=THR
 # The reference's Python package, unmodified, next to its native module (git-ignored like everything under oracle/_ref): the
 # GPU box has no /root/reference, and the drop-in test there runs THIS pyredner on redner_b200/dropin/redner.py.
 mkdir -p "$OUT"
-rm -rf "$OUT/pyredner"
+[ -d "$OUT/pyredner" ] && chmod -R u+w "$OUT/pyredner" && rm -rf "$OUT/pyredner"   # (the checkout is read-only and cp keeps its modes)
 cp -r "$REF/pyredner" "$OUT/pyredner"
+chmod -R u+w "$OUT/pyredner"
 find "$OUT/pyredner" -name __pycache__ -prune -exec rm -rf {} + 2>/dev/null || true
 if [ -f "$TARGET" ] && [ -z "${FORCE:-}" ]; then
     echo "[oracle] $TARGET already built"

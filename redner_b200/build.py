@@ -44,11 +44,12 @@ def build(force=False, double=False, verbose=False, defines=(), out=None, nvcc_f
     # -prec-div=false / -prec-sqrt=false: the path tracer is full of normalisations and quotients; the IEEE-exact
     # division / square-root sequences (FCHK + slow path) cost 1.6x on the backward kernel (measured on B200) while the
     # 2-ulp approximations move the image by < 1e-6 relative L2.  sin/cos/pow/log stay accurate (no --use_fast_math).
-    common = ["-O3", "-std=c++17", "-lineinfo", "-fmad=true", "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-I",
-              os.path.join(HERE, "..", "include")]
+    common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(HERE, "..", "include")]
+    fast = ["-fmad=true", "-prec-div=false", "-prec-sqrt=false"]
     if double:
         common += ["-DRB_REAL_DOUBLE"]
-    common += ["-D" + d for d in defines] + list(nvcc_flags)
+    common += ["-D" + d for d in defines]
+    extra = list(nvcc_flags)  # (command-line overrides come last: nvcc keeps the last value of a repeated option)
     if verbose:
         common += ["-Xptxas", "-v"]
     # rb_edge_tree.cu builds the secondary-edge trees and must round like the host builder it is tested against (no FMA contraction,
@@ -59,7 +60,7 @@ def build(force=False, double=False, verbose=False, defines=(), out=None, nvcc_f
     for src in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         objs.append(obj)
-        procs.append((src, subprocess.Popen([nvcc] + ARCH + common + per_file.get(os.path.basename(src), []) + ["-c", src, "-o", obj], stdout=subprocess.PIPE,
+        procs.append((src, subprocess.Popen([nvcc] + ARCH + common + per_file.get(os.path.basename(src), fast) + extra + ["-c", src, "-o", obj], stdout=subprocess.PIPE,
                                             stderr=subprocess.STDOUT)))
     tab = os.path.join(objdir, "rb_tables.o")
     objs.append(tab)
