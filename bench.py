@@ -446,6 +446,9 @@ def run_ours(args, rank, world, local_rank):
         cfg["kernel_ms"] = {"k_forward": info["fwd_k"]["k_forward"], **{k: v for k, v in info["bwd_k"].items() if k != "k_forward"}}
         cfg["scene_build_detail_ms"] = info["build"]
         cfg["fwd_ms"], cfg["bwd_ms"], cfg["comm_ms"] = info["fwd_ms"], info["bwd_ms"], info["comm_ms"]
+        # forward-only and backward-only ("grad") rates of this rank's samples, from the two render calls
+        cfg["fwd_msamples_per_s"] = n_samples / (info["fwd_ms"] * 1e-3) / 1e6
+        cfg["grad_msamples_per_s"] = n_samples / (info["bwd_ms"] * 1e-3) / 1e6
     if main["per_rank_ms"]:
         cfg["per_rank_step_ms"] = main["per_rank_ms"]
         cfg["per_rank_compute_ms"] = main["per_rank_compute_ms"]  # the two rb_render calls only (without the collectives)
