@@ -232,6 +232,9 @@ int rb_scene_build_ms(const rb_scene* scene, float* bvh_lights_edges3);
  * camera-silhouette tree, root reference of the other tree } (reference >= 0: record index, < 0: ~edge id, INT_MIN: empty tree);
  * *expand = billboard size (src/edge_tree.cpp:773); records_out (may be NULL) receives up to records_bytes of the records. */
 int rb_scene_edge_trees(const rb_scene* scene, int* info3, float* expand, void* records_out, size_t records_bytes);
+/* Test hook: the scene's edge list (what collect_edges builds, src/edge.cpp:233-296): *num_edges, and up to edges_bytes of
+ * { shape, v0, v1, f0, f1 } int records into edges_out (may be NULL). */
+int rb_scene_edge_list(const rb_scene* scene, int* num_edges, int* edges_out, size_t edges_bytes);
 
 const char* rb_last_error(void);
 const char* rb_version(void);

@@ -110,7 +110,7 @@ class rb_dscene_desc(C.Structure):
 
 EXPORTS = [
     "rb_scene_create", "rb_scene_create_on_stream", "rb_scene_destroy", "rb_scene_max_generic_texture_dimension", "rb_compute_num_channels", "rb_render",
-    "rb_scene_set_partition", "rb_scene_last_stats", "rb_scene_last_stage_stats", "rb_scene_last_backward_stats", "rb_release_scratch", "rb_scene_build_ms", "rb_scene_edge_trees", "rb_scene_set_camera", "rb_render_batch", "rb_last_error", "rb_version",
+    "rb_scene_set_partition", "rb_scene_last_stats", "rb_scene_last_stage_stats", "rb_scene_last_backward_stats", "rb_release_scratch", "rb_scene_build_ms", "rb_scene_edge_trees", "rb_scene_edge_list", "rb_scene_set_camera", "rb_render_batch", "rb_last_error", "rb_version",
 ]
 
 
@@ -153,6 +153,9 @@ def _bind(lib):
     if hasattr(lib, "rb_scene_edge_trees"):
         lib.rb_scene_edge_trees.argtypes = [C.c_void_p, c_int_p, c_float_p, C.c_void_p, C.c_size_t]
         lib.rb_scene_edge_trees.restype = C.c_int
+    if hasattr(lib, "rb_scene_edge_list"):
+        lib.rb_scene_edge_list.argtypes = [C.c_void_p, c_int_p, c_int_p, C.c_size_t]
+        lib.rb_scene_edge_list.restype = C.c_int
     lib.rb_last_error.argtypes = []
     lib.rb_last_error.restype = C.c_char_p
     lib.rb_version.argtypes = []

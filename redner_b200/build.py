@@ -54,7 +54,9 @@ def build(force=False, double=False, verbose=False, defines=(), out=None, nvcc_f
         common += ["-Xptxas", "-v"]
     # rb_edge_tree.cu builds the secondary-edge trees and must round like the host builder it is tested against (no FMA contraction,
     # IEEE division / square root); its bottom-up passes hand data between thread blocks, so its global loads bypass the L1.
-    per_file = {"rb_edge_tree.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-Xptxas", "-dlcm=cg"]}
+    # rb_edge_list.cu drops coplanar edges by a threshold on a dot product of unit normals: same rounding rule.
+    per_file = {"rb_edge_tree.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-Xptxas", "-dlcm=cg"],
+                "rb_edge_list.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"]}
     objs = []
     procs = []
     for src in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):

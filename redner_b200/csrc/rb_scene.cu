@@ -341,16 +341,29 @@ int rb_build_lights(rb_scene* sc, cudaStream_t stream) {
 #ifndef RB_GPU_TABLES_MIN_EDGES
 #define RB_GPU_TABLES_MIN_EDGES 1024
 #endif
+#ifndef RB_GPU_EDGE_LIST_MIN_TRIANGLES
+#define RB_GPU_EDGE_LIST_MIN_TRIANGLES 1024
+#endif
 int rb_build_edges(rb_scene* sc, cudaStream_t stream) {
     sc->dev.edges = nullptr;
     sc->dev.num_edges = 0;
     sc->dev.prim_edge_pmf = sc->dev.prim_edge_cdf = nullptr;
     if (!sc->dev.use_primary_edge && !sc->dev.use_secondary_edge) return 0;
-    // The edge LIST (topology: sort, merge, seam repair, flat-edge filter) is built on the host; everything that depends on the
-    // camera -- the primary-edge distribution and the two secondary-edge trees -- on the device (rb_edge_tree.cu), so that
-    // rb_scene_set_camera / rb_render_batch re-target a scene without touching the host.  RB_HOST_TREES=1: host tables (tests).
-    // Small edge sets (a few hundred edges: C1, C2) are faster on the host than ~25 kernel launches and two synchronisations; the
-    // two builders produce the same tables (tests/test_scene_build_gpu.py), RB_GPU_TREES=1 / RB_HOST_TREES=1 force one of them.
+    // Small scenes (a few hundred edges: C1, C2) build the edge list and the tables that depend on the camera -- the primary-edge
+    // distribution and the two secondary-edge trees -- on the host: faster than ~35 kernel launches and four synchronisations.  From
+    // RB_GPU_EDGE_LIST_MIN_TRIANGLES triangles on everything is built on the device (rb_edge_list.cu, rb_edge_tree.cu); in between
+    // (host list of >= RB_GPU_TABLES_MIN_EDGES edges, or RB_HOST_EDGE_LIST=1) the list comes from the host and the tables from the
+    // device.  rb_scene_set_camera / rb_render_batch always rebuild the tables on the device.  The builders produce the same list and
+    // the same tables (tests/test_scene_build_gpu.py); RB_GPU_TREES=1 / RB_HOST_TREES=1 force everything onto one side.
+    if (sc->edge_list_on_device) {
+        // Larger scenes: the list too is built on the device (rb_edge_list.cu), and no mesh leaves the GPU for it.
+        if (rb_build_edge_list_gpu(sc, stream)) return 1;
+        if (sc->dev.num_edges == 0) return 0;
+        if (sc->dev.use_primary_edge && rb_build_primary_edge_cdf_gpu(sc, stream)) return 1;
+        if (sc->dev.use_secondary_edge && rb_build_edge_trees_gpu(sc, stream)) return 1;
+        RB_CUDA_OK(cudaStreamSynchronize(stream));
+        return 0;
+    }
     HostEdgeTables t;
     host_build_edges(sc->shapes, host_meshes(sc), sc->dev.cam, false, t);
     int E = (int)t.edges.size();
@@ -523,9 +536,13 @@ extern "C" int rb_scene_create_on_stream(const rb_scene_desc* desc, rb_scene** o
     auto t1 = std::chrono::high_resolution_clock::now();
     // host mirrors (lights need serial double CDFs; edges need topology + positions)
     bool need_edges = sc->dev.use_primary_edge || sc->dev.use_secondary_edge;
+    long long num_triangles = 0;
+    for (const rb_shape& s : sc->shapes) num_triangles += s.num_triangles;
+    sc->edge_list_on_device = need_edges && getenv("RB_HOST_TREES") == nullptr && getenv("RB_HOST_EDGE_LIST") == nullptr &&
+                              (num_triangles >= RB_GPU_EDGE_LIST_MIN_TRIANGLES || getenv("RB_GPU_TREES") != nullptr || getenv("RB_GPU_EDGE_LIST") != nullptr);
     auto& meshes = host_meshes(sc);
     meshes.assign(sc->shapes.size(), HostMesh());
-    std::vector<char> need(sc->shapes.size(), (need_edges || desc->envmap != nullptr) ? 1 : 0); // (envmap: bounding sphere of everything)
+    std::vector<char> need(sc->shapes.size(), ((need_edges && !sc->edge_list_on_device) || desc->envmap != nullptr) ? 1 : 0); // (envmap: bounding sphere of everything)
     for (const DevLight& l : sc->lights) need[l.shape_id] = 1;
     for (size_t s = 0; s < sc->shapes.size(); s++)
         if (need[s] && fetch_mesh(sc->shapes[s], meshes[s], stream)) return fail();
@@ -585,6 +602,17 @@ extern "C" int rb_scene_edge_trees(const rb_scene* sc, int* info3, float* expand
     if (records_out && sc->dev.edge_nodes && records_bytes > 0) {
         size_t n = std::min(records_bytes, sizeof(EdgeNode) * (size_t)sc->num_edge_nodes);
         if (cudaMemcpy(records_out, sc->dev.edge_nodes, n, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+
+// Test hook: the edge list as the kernels see it (5 ints per edge: shape, v0, v1, f0, f1).
+extern "C" int rb_scene_edge_list(const rb_scene* sc, int* num_edges, int* edges_out, size_t edges_bytes) {
+    if (!sc) return 1;
+    if (num_edges) *num_edges = sc->dev.num_edges;
+    if (edges_out && sc->dev.edges && edges_bytes > 0) {
+        size_t n = std::min(edges_bytes, sizeof(Edge) * (size_t)sc->dev.num_edges);
+        if (cudaMemcpy(edges_out, sc->dev.edges, n, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
     }
     return 0;
 }

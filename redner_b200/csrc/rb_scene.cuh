@@ -47,6 +47,7 @@ struct rb_scene {
     float last_bwd_ms[3] = {0.f, 0.f, 0.f};        // inside the bands: k_bwd_trace (+ work lists), boundary stage (pick, sort by edge, shade), k_bwd_sweep
     double last_path_vertices = 0, last_primary_hits = 0;
     int num_edge_nodes = 0; // records of the secondary-edge trees (dev.edge_nodes)
+    bool edge_list_on_device = false;   // this scene's edge list was built by rb_edge_list.cu (else on the host)
     EdgeNode* edge_nodes_buf = nullptr; // device buffer of the GPU tree builder (num_edges records), reused by rb_scene_set_camera
     // scene-build timings (ms, host clock) for reporting
     float build_ms_bvh = 0.f, build_ms_lights = 0.f, build_ms_edges = 0.f;
@@ -72,5 +73,6 @@ extern "C" const unsigned char rb_ltc_table_end[];
 int rb_build_bvh(rb_scene* sc, cudaStream_t stream);
 int rb_build_lights(rb_scene* sc, cudaStream_t stream);
 int rb_build_edges(rb_scene* sc, cudaStream_t stream);
+int rb_build_edge_list_gpu(rb_scene* sc, cudaStream_t stream);  // rb_edge_list.cu
 int rb_build_edge_trees_gpu(rb_scene* sc, cudaStream_t stream); // rb_edge_tree.cu
 int rb_build_primary_edge_cdf_gpu(rb_scene* sc, cudaStream_t stream);

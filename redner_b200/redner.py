@@ -400,6 +400,16 @@ class Scene:  # src/redner.cpp:62-73, src/scene.cpp:63-307
             self._lib.rb_scene_edge_trees(self._handle, info, C.byref(ex), rec.ctypes.data_as(C.c_void_p), rec.nbytes)
         return rec, info[1], info[2], ex.value
 
+    def edge_list(self):
+        """[num_edges, 5] int32 rows (shape, v0, v1, f0, f1): test hook."""
+        import numpy as np
+        n = C.c_int(0)
+        self._lib.rb_scene_edge_list(self._handle, C.byref(n), None, 0)
+        out = np.zeros((max(n.value, 0), 5), dtype=np.int32)
+        if n.value > 0:
+            self._lib.rb_scene_edge_list(self._handle, C.byref(n), out.ctypes.data_as(C.POINTER(C.c_int)), out.nbytes)
+        return out
+
     def build_ms(self):
         ms = (C.c_float * 3)()
         self._lib.rb_scene_build_ms(self._handle, ms)
