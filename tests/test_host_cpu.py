@@ -157,3 +157,62 @@ def test_gloo_world_size_2_renders_the_same_image_and_gradients_as_one_rank(tmp_
         n = np.linalg.norm(a[k])
         if k != "image" and n > 0:
             assert np.linalg.norm(a[k] - b[k]) / n < 1e-5, k
+
+
+def _batch_worker(rank, world, port, emu_so, out_path):
+    """One rank of the C5 shape on CPU: the rank's share of the camera poses through ONE native scene (api.render_batch ->
+    rb_scene_set_camera per view, host build of the device headers behind the C ABI), then one packed all-reduce of the gradients of the
+    shared geometry / materials / lights (bench.py --workload c5 under torchrun does this with NCCL)."""
+    import ctypes
+    import numpy as np
+    from redner_b200 import _lib
+    _lib._lib = _lib._bind(ctypes.CDLL(emu_so))  # this process only
+    from redner_b200 import api, redner as rb
+    import parity_utils as pu
+    import scenes
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dev = torch.device("cpu")
+        poses = [([0.3, 1.4, -4.5], [0.0, 0.6, 0.0]), ([1.2, 1.1, -4.0], [0.1, 0.5, 0.1]), ([-0.8, 1.8, -4.2], [0.0, 0.7, 0.2]), ([0.0, 2.2, -3.8], [0.0, 0.5, 0.0])]
+        mine = list(range(rank, len(poses), world))
+        views = [scenes.glossy_room(dev, resolution=(20, 20)) for _ in mine]
+        for v, k in zip(views, mine):
+            p, l = poses[k]
+            v.camera = api.Camera(position=torch.tensor(p), look_at=torch.tensor(l), up=torch.tensor([0.0, 1.0, 0.0]), fov=torch.tensor([40.0]), clip_near=1e-2,
+                                  resolution=(20, 20))
+            v.shapes, v.materials, v.area_lights = views[0].shapes, views[0].materials, views[0].area_lights
+        imgs = api.render_batch(views, 4, 2, [21 + k for k in mine], sampler_type=rb.SamplerType.sobol, device=dev, backend=rb)
+        imgs.pow(2).sum().backward()
+        g = {k: v for k, v in pu.collect_grads(views[0]).items() if not k.startswith("cam.")}
+        keys = sorted(g)
+        reduced = rdist.all_reduce_packed([g[k] for k in keys])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (mine, imgs.detach().numpy()))
+        if rank == 0:
+            full = np.zeros((len(poses),) + tuple(imgs.shape[1:]), dtype=np.float32)
+            for ids, arr in gathered:
+                full[ids] = arr
+            np.savez(out_path, images=full, **{k: r.numpy() for k, r in zip(keys, reduced)})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_batch_of_poses_equals_one_rank(tmp_path):
+    """The C5 partition (independent poses, no data-path collective, one gradient all-reduce) at world size 2 against one rank: every
+    pose's image bit for bit, the summed gradients up to summation order."""
+    import numpy as np
+    import test_device_code_cpu as tdc
+    emu = tdc._build()
+    outs = {}
+    for world in (1, 2):
+        path = str(tmp_path / ("b%d.npz" % world))
+        mp.spawn(_batch_worker, args=(world, _free_port(), emu, path), nprocs=world, join=True)
+        outs[world] = dict(np.load(path))
+    a, b = outs[1], outs[2]
+    assert a["images"].shape[0] == 4 and np.array_equal(a["images"], b["images"]) and np.abs(a["images"]).sum() > 0
+    assert set(a) == set(b) and len(a) > 4
+    for k in a:
+        n = np.linalg.norm(a[k])
+        if k != "images" and n > 0:
+            assert np.linalg.norm(a[k] - b[k]) / n < 1e-5, k
